@@ -1,0 +1,192 @@
+/*
+ * rnr_b200.h -- C ABI of librnr_b200.so, the B200 (sm_100a) implementation of the
+ * per-view deferred-relighting hot path of LansburyCH/relightable-nr.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream and returns
+ * a cudaError_t as int (0 == success).  No torch types cross this boundary.  Each
+ * declaration cites the reference interface (file:line under /root/reference) that a
+ * maintainer would re-bind to it; INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - "act"  : activations, fp16, channels-last, stored with a 1-pixel halo
+ *              [N, H+2, W+2, C]  (reflect halo for forward tensors, zero halo for gradients)
+ *   - "raw"  : pre-BatchNorm conv outputs, fp32 channels-last [N, H, W, C]
+ *   - "grad" : gradients w.r.t. raw conv outputs, bf16, [N, H+2, W+2, C], zero halo
+ *   - stream : cudaStream_t passed as void*
+ */
+#ifndef RNR_B200_H
+#define RNR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* library info                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+const char* rnr_version(void);
+const char* rnr_last_error(void);          /* text of the last failing call on this thread */
+int  rnr_device_sm_count(int device);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Generic implicit-GEMM convolution problem                                                   */
+/*   replaces every ATen/cuDNN Conv2d / ConvTranspose2d (fwd, dgrad) of the U-Net:             */
+/*   pytorch_prototyping/pytorch_prototyping.py:112-115,155-160,242-264 (and their autograd).  */
+/*                                                                                            */
+/*   out[n, y*my+py, x*mx+px, co] = epi( sum_j  A_j[n, y+dy_j, x+dx_j, c0_j .. c0_j+BK)         */
+/*                                            . Wmat[co, j*BK .. (j+1)*BK) )                   */
+/*   A_j is one of up to 8 strided 4-D "views" (C,X,Y,N); out-of-range coordinates read 0.     */
+/* ------------------------------------------------------------------------------------------ */
+#define RNR_MAX_VIEWS 8
+
+enum { RNR_F16 = 0, RNR_BF16 = 1, RNR_F32 = 2 };
+
+typedef struct {
+    const void* ptr;       /* element (c=0,x=0,y=0,n=0) */
+    int32_t dim[4];        /* extents  (C, X, Y, N) */
+    int64_t stride[4];     /* element strides (C stride must be 1) */
+} rnr_view_t;
+
+typedef struct {           /* one K-step = BK consecutive channels of one view at one tap */
+    int16_t view;
+    int16_t c0;
+    int16_t dx;
+    int16_t dy;
+} rnr_kstep_t;
+
+enum {
+    RNR_EPI_BIAS  = 1,     /* += bias[co]                                            */
+    RNR_EPI_TANH  = 2,     /* tanh() after bias                                       */
+    RNR_EPI_STATS = 4      /* per-tile channel sums: stats[(tile_m*2+{0,1})*ldstats+co] */
+};
+
+typedef struct {
+    /* A side */
+    rnr_view_t views[RNR_MAX_VIEWS];
+    int32_t    n_views;
+    int32_t    ab_dtype;           /* RNR_F16 or RNR_BF16: dtype of views and Wmat */
+    int32_t    bk;                 /* channels per K-step: 16, 32 or 64 */
+    int32_t    n_ksteps;
+    const rnr_kstep_t* ksteps;     /* HOST pointer, n_ksteps entries (copied at plan creation) */
+    /* B side: Wmat [n_rows_w, n_ksteps*bk], K contiguous */
+    const void* wmat;
+    int32_t    n_rows_w;           /* rows of Wmat (>= cout, multiple of 16) */
+    int32_t    cout;               /* valid output channels */
+    /* M space */
+    int32_t    mN, mY, mX;         /* extents of the (n,y,x) iteration space */
+    int32_t    th, tw;             /* tile = th x tw pixels, th*tw == 128 */
+    /* output */
+    void*      out;
+    int32_t    out_dtype;          /* RNR_F32 / RNR_F16 / RNR_BF16 */
+    int64_t    out_sn, out_sy, out_sx;   /* element strides */
+    int32_t    out_my, out_mx, out_py, out_px;
+    int32_t    epi;                /* RNR_EPI_* flags */
+    const float* bias;
+    float*     stats;              /* [n_tiles_m, 2, ldstats] */
+    int32_t    ldstats;
+} rnr_conv_problem_t;
+
+typedef struct rnr_conv_plan rnr_conv_plan_t;   /* opaque: device k-step table + TMA tensor maps */
+
+/* impl: 0 = SIMT validation kernel, 1 = tcgen05/TMA kernel */
+int  rnr_conv_plan_create(const rnr_conv_problem_t* prob, int impl, rnr_conv_plan_t** plan);
+void rnr_conv_plan_destroy(rnr_conv_plan_t* plan);
+int  rnr_conv_run(const rnr_conv_plan_t* plan, void* stream);
+int  rnr_conv_plan_tiles_m(const rnr_conv_plan_t* plan);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Weight-gradient problem (autograd of Conv2d/ConvTranspose2d w.r.t. weight)                  */
+/*   dW[co*s_co + ci*s_ci + off_t] (+)= sum_{n,y,x} G[n,y,x,co] * A_t[n, y+dy_t, x+dx_t, ci]    */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int16_t view;        /* A view of this tap */
+    int16_t dx, dy;
+    int16_t gview;       /* G view of this tap (parity classes of ConvTranspose use different G views) */
+    int32_t c0;          /* first input channel (within the A view) */
+    int32_t ci0;         /* first ci index in dW for this entry */
+    int32_t nci;         /* number of channels */
+    int64_t off;         /* element offset of this tap in dW */
+} rnr_wtap_t;
+
+typedef struct {
+    rnr_view_t aviews[RNR_MAX_VIEWS];
+    rnr_view_t gviews[4];
+    int32_t    n_aviews, n_gviews;
+    int32_t    a_dtype, g_dtype;
+    int32_t    n_taps;
+    const rnr_wtap_t* taps;        /* HOST pointer */
+    int32_t    cout;
+    int32_t    mN, mY, mX;         /* pixel iteration space (shared by G and A views) */
+    float*     dw;                 /* fp32, accumulated with atomics: must be zeroed by caller */
+    int64_t    s_co, s_ci;
+} rnr_wgrad_problem_t;
+
+typedef struct rnr_wgrad_plan rnr_wgrad_plan_t;
+int  rnr_wgrad_plan_create(const rnr_wgrad_problem_t* prob, int impl, rnr_wgrad_plan_t** plan);
+void rnr_wgrad_plan_destroy(rnr_wgrad_plan_t* plan);
+int  rnr_wgrad_run(const rnr_wgrad_plan_t* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Weight preparation: fp32 master weights -> 16-bit K-major GEMM matrices                     */
+/*   dst[r*ld + t*cpad + c] = src[r*s_r + c*s_c + tapoff[t]]   (0 for c >= nc or r >= nr)       */
+/* ------------------------------------------------------------------------------------------ */
+int rnr_weight_prep(const float* src, void* dst, int dst_dtype,
+                    int nr, int nr_pad, int nc, int cpad, int ntaps,
+                    int64_t s_r, int64_t s_c, const int32_t* tapoff_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* BatchNorm2d (batch statistics) + activation + Dropout2d                                     */
+/*   replaces nn.BatchNorm2d / LeakyReLU / ReLU / Dropout2d of pytorch_prototyping.py:177-197,  */
+/*   250-272, 471-476 (forward and backward)                                                   */
+/* ------------------------------------------------------------------------------------------ */
+/* partial sums [T,2,ld] -> mean/invstd/scale/shift (+ running stats update, momentum)         */
+int rnr_bn_finalize(const float* partials, int T, int ld, int C, double count,
+                    const float* gamma, const float* beta, float eps,
+                    float* mean, float* invstd, float* scale, float* shift,
+                    float* running_mean, float* running_var, float momentum, void* stream);
+
+/* act = drop * act(raw*scale + shift), written fp16 with reflect halo [N,H+2,W+2,C]            */
+int rnr_bn_act_fwd(const float* raw, const float* scale, const float* shift,
+                   const float* drop /* [N,C] or NULL */, float slope,
+                   void* act, int N, int H, int W, int C, void* stream);
+
+typedef struct {
+    const void* ptr;      /* bf16 or fp32 */
+    int32_t dtype;
+    int32_t fold;         /* 1: tensor is [N,H+2,W+2,ld] = grad w.r.t. the reflect-padded input: fold halo */
+    int32_t ld;           /* channel pitch */
+    int32_t c0;           /* first channel */
+} rnr_gsrc_t;
+
+/* pass 1: gz = (sum of sources) * drop * act'(raw*scale+shift); writes gz (bf16, zero-halo layout)
+ *         and per-block partial sums of gz and gz*xhat: partials [T,2,C]                        */
+int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* raw,
+                      const float* scale, const float* shift, const float* mean, const float* invstd,
+                      const float* drop, float slope,
+                      void* gz, float* partials, int* T_out,
+                      int N, int H, int W, int C, void* stream);
+/* finalize: dgamma, dbeta, and coefficients c1=mean(gz), c2=mean(gz*xhat) */
+int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count,
+                        float* dgamma, float* dbeta, float* c1, float* c2, void* stream);
+/* pass 2 (in place): gz <- gamma*invstd*(gz - c1 - xhat*c2) */
+int rnr_bn_bwd_apply(void* gz, const float* raw, const float* gamma, const float* mean, const float* invstd,
+                     const float* c1, const float* c2, int N, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* layout glue of the module-level API (NCHW fp32 <-> channels-last 16-bit)                    */
+/*   network.RenderingNet.forward(input [N,C,H,W]) -> [N,Cout,H,W]   network.py:251-253        */
+/* ------------------------------------------------------------------------------------------ */
+int rnr_pack_nchw_to_act(const float* src, void* act, int N, int C, int Cpad, int H, int W, void* stream);
+int rnr_unpack_nhwc_to_nchw(const float* src, float* dst, int N, int C, int ld, int H, int W, void* stream);
+/* grad_out NCHW fp32 (d/d tanh-output) -> gz = grad*(1-t^2) bf16 zero-halo, + per-block bias partial sums */
+int rnr_tanh_bwd_pack(const float* grad_nchw, const float* tanh_nhwc, void* gz, float* dbias /* [C] atomics, pre-zeroed */,
+                      int N, int C, int ld, int H, int W, void* stream);
+/* folded grad w.r.t. reflect-padded input [N,H+2,W+2,ld] -> NCHW fp32 [N,C,H,W] (channels c0..c0+C) */
+int rnr_fold_to_nchw(const void* gpad, int dtype, float* dst, int N, int C, int c0, int ld, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNR_B200_H */

@@ -1,0 +1,135 @@
+"""ctypes binding of librnr_b200.so (the C ABI declared in include/rnr_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an
+exception is raised.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librnr_b200.so")
+
+F16, BF16, F32 = 0, 1, 2
+EPI_BIAS, EPI_TANH, EPI_STATS = 1, 2, 4
+MAX_VIEWS = 8
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dim", C.c_int32 * 4), ("stride", C.c_int64 * 4)]
+
+
+class KStep(C.Structure):
+    _fields_ = [("view", C.c_int16), ("c0", C.c_int16), ("dx", C.c_int16), ("dy", C.c_int16)]
+
+
+class ConvProblem(C.Structure):
+    _fields_ = [
+        ("views", View * MAX_VIEWS), ("n_views", C.c_int32), ("ab_dtype", C.c_int32), ("bk", C.c_int32),
+        ("n_ksteps", C.c_int32), ("ksteps", C.POINTER(KStep)),
+        ("wmat", C.c_void_p), ("n_rows_w", C.c_int32), ("cout", C.c_int32),
+        ("mN", C.c_int32), ("mY", C.c_int32), ("mX", C.c_int32), ("th", C.c_int32), ("tw", C.c_int32),
+        ("out", C.c_void_p), ("out_dtype", C.c_int32),
+        ("out_sn", C.c_int64), ("out_sy", C.c_int64), ("out_sx", C.c_int64),
+        ("out_my", C.c_int32), ("out_mx", C.c_int32), ("out_py", C.c_int32), ("out_px", C.c_int32),
+        ("epi", C.c_int32), ("bias", C.c_void_p), ("stats", C.c_void_p), ("ldstats", C.c_int32),
+    ]
+
+
+class WTap(C.Structure):
+    _fields_ = [("view", C.c_int16), ("dx", C.c_int16), ("dy", C.c_int16), ("gview", C.c_int16),
+                ("c0", C.c_int32), ("ci0", C.c_int32), ("nci", C.c_int32), ("off", C.c_int64)]
+
+
+class WgradProblem(C.Structure):
+    _fields_ = [
+        ("aviews", View * MAX_VIEWS), ("gviews", View * 4), ("n_aviews", C.c_int32), ("n_gviews", C.c_int32),
+        ("a_dtype", C.c_int32), ("g_dtype", C.c_int32), ("n_taps", C.c_int32), ("taps", C.POINTER(WTap)),
+        ("cout", C.c_int32), ("mN", C.c_int32), ("mY", C.c_int32), ("mX", C.c_int32),
+        ("dw", C.c_void_p), ("s_co", C.c_int64), ("s_ci", C.c_int64),
+    ]
+
+
+class GSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("fold", C.c_int32), ("ld", C.c_int32), ("c0", C.c_int32)]
+
+
+class RnrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RnrError(
+            "librnr_b200.so not found at %s -- the CUDA library must be built "
+            "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    L.rnr_version.restype = C.c_char_p
+    L.rnr_last_error.restype = C.c_char_p
+    L.rnr_device_sm_count.argtypes = [i32]
+    sigs = {
+        "rnr_conv_plan_create": [C.POINTER(ConvProblem), i32, C.POINTER(vp)],
+        "rnr_conv_run": [vp, vp],
+        "rnr_conv_plan_tiles_m": [vp],
+        "rnr_wgrad_plan_create": [C.POINTER(WgradProblem), i32, C.POINTER(vp)],
+        "rnr_wgrad_run": [vp, vp],
+        "rnr_weight_prep": [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, vp, vp],
+        "rnr_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp],
+        "rnr_bn_act_fwd": [vp, vp, vp, vp, f32, vp, i32, i32, i32, i32, vp],
+        "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
+        "rnr_bn_bwd_finalize": [vp, i32, i32, f64, vp, vp, vp, vp, vp],
+        "rnr_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "rnr_pack_nchw_to_act": [vp, vp, i32, i32, i32, i32, i32, vp],
+        "rnr_unpack_nhwc_to_nchw": [vp, vp, i32, i32, i32, i32, i32, vp],
+        "rnr_tanh_bwd_pack": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "rnr_fold_to_nchw": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = i32
+    L.rnr_conv_plan_destroy.argtypes = [vp]
+    L.rnr_conv_plan_destroy.restype = None
+    L.rnr_wgrad_plan_destroy.argtypes = [vp]
+    L.rnr_wgrad_plan_destroy.restype = None
+    _register_optional(L)
+    _lib = L
+    return L
+
+
+_OPTIONAL_SIGS = {}
+
+
+def register_sigs(sigs):
+    """Other host modules (texture, rays, raster ...) declare their entry points here."""
+    _OPTIONAL_SIGS.update(sigs)
+    if _lib is not None:
+        _register_optional(_lib)
+
+
+def _register_optional(L):
+    for name, argtypes in _OPTIONAL_SIGS.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().rnr_last_error().decode()
+        raise RnrError("%s failed (cudaError %d): %s" % (what or "librnr_b200 call", rc, msg))
+
+
+def exported_symbols():
+    """Names declared in include/rnr_b200.h (parsed), used by the ABI test."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "rnr_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(rnr_[a-z0-9_]+)\s*\(", txt)))

@@ -1,0 +1,299 @@
+// BatchNorm2d with *batch statistics* (the only mode the reference ever runs: SURVEY 3.3,
+// test_rnr.py:229-233, train_rnr.py:398-405) + LeakyReLU/ReLU + Dropout2d, forward and backward.
+// Reference operators: pytorch_prototyping/pytorch_prototyping.py:177-197 (UpBlock),
+// :250-272 (DownBlock), :470-476 (Unet.in_layer).
+//
+// HBM-bound elementwise/reduction kernels: 128-bit loads, 8 channels per thread, channels-last.
+#include "common.cuh"
+
+namespace {
+
+// -------------------------------------------------------------------------------------------
+// forward statistics finalize
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restrict__ partials, int T, int ld, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float* mean, float* invstd, float* scale, float* shift,
+                                   float* running_mean, float* running_var, float momentum) {
+    __shared__ double s_s[16][33], s_q[16][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;   // 16 warps
+    const int c = blockIdx.x * 32 + lane;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        for (int t = w; t < T; t += 16) {
+            s += (double)partials[((int64_t)t * 2 + 0) * ld + c];
+            q += (double)partials[((int64_t)t * 2 + 1) * ld + c];
+        }
+    }
+    s_s[w][lane] = s; s_q[w][lane] = q;
+    __syncthreads();
+    if (w == 0 && c < C) {
+        for (int i = 1; i < 16; i++) { s += s_s[i][lane]; q += s_q[i][lane]; }
+        const double m = s / count;
+        double var = q / count - m * m;
+        if (var < 0.0) var = 0.0;
+        const float istd = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+        mean[c] = (float)m;
+        invstd[c] = istd;
+        scale[c] = g * istd;
+        shift[c] = b - (float)m * g * istd;
+        if (running_mean) {
+            const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// forward apply: act = drop * lrelu(raw*scale + shift), fp16, reflect halo
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const float* __restrict__ drop, float slope,
+                                  __half* __restrict__ act, int N, int H, int W, int C) {
+    const int vpp = C >> 3;
+    const int64_t total = (int64_t)N * H * W * vpp;
+    const int Hp = H + 2, Wp = W + 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % vpp);
+        const int64_t pix = i / vpp;
+        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+        const int c = cv * 8;
+        const float4 r0 = *(const float4*)(raw + pix * C + c);
+        const float4 r1 = *(const float4*)(raw + pix * C + c + 4);
+        const float4 s0 = *(const float4*)(scale + c), s1 = *(const float4*)(scale + c + 4);
+        const float4 t0 = *(const float4*)(shift + c), t1 = *(const float4*)(shift + c + 4);
+        float v[8] = {r0.x * s0.x + t0.x, r0.y * s0.y + t0.y, r0.z * s0.z + t0.z, r0.w * s0.w + t0.w,
+                      r1.x * s1.x + t1.x, r1.y * s1.y + t1.y, r1.z * s1.z + t1.z, r1.w * s1.w + t1.w};
+        __align__(16) __half o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            float z = v[e];
+            z = z > 0.f ? z : z * slope;
+            if (drop) z *= drop[n * C + c + e];
+            o[e] = __float2half_rn(z);
+        }
+        const uint4 ov = *(const uint4*)o;
+        // rows / cols this pixel lands on in the padded tensor
+        int rows[3], cols[3], nr = 0, nc = 0;
+        rows[nr++] = h + 1;
+        if (h == 1) rows[nr++] = 0;
+        if (h == H - 2) rows[nr++] = H + 1;
+        cols[nc++] = w + 1;
+        if (w == 1) cols[nc++] = 0;
+        if (w == W - 2) cols[nc++] = W + 1;
+        for (int a = 0; a < nr; a++)
+            for (int b = 0; b < nc; b++)
+                *(uint4*)(act + (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * C + c) = ov;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward pass 1
+// -------------------------------------------------------------------------------------------
+struct GSrcs {
+    rnr_gsrc_t s[2];
+    int n;
+};
+
+__device__ __forceinline__ void load8(const void* base, int64_t idx, int dtype, float* out) {
+    if (dtype == RNR_F32) {
+        const float4 a = *(const float4*)((const float*)base + idx);
+        const float4 b = *(const float4*)((const float*)base + idx + 4);
+        out[0] += a.x; out[1] += a.y; out[2] += a.z; out[3] += a.w;
+        out[4] += b.x; out[5] += b.y; out[6] += b.z; out[7] += b.w;
+    } else {
+        const uint4 u = *(const uint4*)((const unsigned short*)base + idx);
+        const unsigned short* us = (const unsigned short*)&u;
+#pragma unroll
+        for (int e = 0; e < 8; e++) out[e] += cvt16(us[e], dtype);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const GSrcs srcs, const float* __restrict__ raw,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ drop, float slope,
+                                     __nv_bfloat16* __restrict__ gz, float* __restrict__ partials,
+                                     int N, int H, int W, int C, int ppb) {
+    extern __shared__ float s_red[];   // [2][C]
+    const int vpp = C >> 3;
+    const int cv = threadIdx.x % vpp, pl = threadIdx.x / vpp;
+    const int c = cv * 8;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+    const int Hp = H + 2, Wp = W + 2;
+    const int64_t npix = (int64_t)N * H * W;
+    float sg[8], sgx[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) { sg[e] = 0.f; sgx[e] = 0.f; }
+    float sc[8], sh[8], mu[8], is[8];
+    if (pl < ppb) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) { sc[e] = scale[c + e]; sh[e] = shift[c + e]; mu[e] = mean[c + e]; is[e] = invstd[c + e]; }
+    }
+    if (pl < ppb)
+    for (int64_t pix = (int64_t)blockIdx.x * ppb + pl; pix < npix; pix += (int64_t)gridDim.x * ppb) {
+        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+        float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int si = 0; si < srcs.n; si++) {
+            const rnr_gsrc_t& s = srcs.s[si];
+            if (s.fold) {
+                int rows[3], cols[3], nr = 0, nc = 0;
+                rows[nr++] = h + 1;
+                if (h == 1) rows[nr++] = 0;
+                if (h == H - 2) rows[nr++] = H + 1;
+                cols[nc++] = w + 1;
+                if (w == 1) cols[nc++] = 0;
+                if (w == W - 2) cols[nc++] = W + 1;
+                for (int a = 0; a < nr; a++)
+                    for (int b = 0; b < nc; b++)
+                        load8(s.ptr, (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * s.ld + s.c0 + c, s.dtype, g);
+            } else {
+                load8(s.ptr, pix * s.ld + s.c0 + c, s.dtype, g);
+            }
+        }
+        const float4 r0 = *(const float4*)(raw + pix * C + c);
+        const float4 r1 = *(const float4*)(raw + pix * C + c + 4);
+        const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float z = r[e] * sc[e] + sh[e];
+            float gg = g[e] * (z > 0.f ? 1.f : slope);
+            if (drop) gg *= drop[n * C + c + e];
+            const float xh = (r[e] - mu[e]) * is[e];
+            sg[e] += gg;
+            sgx[e] += gg * xh;
+            o[e] = __float2bfloat16_rn(gg);
+        }
+        *(uint4*)(gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c) = *(const uint4*)o;
+    }
+    if (pl < ppb) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            atomicAdd(&s_red[c + e], sg[e]);
+            atomicAdd(&s_red[C + c + e], sgx[e]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partials[(int64_t)blockIdx.x * 2 * C + i] = s_red[i];
+}
+
+__global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __restrict__ partials, int T, int C, double count,
+                                       float* dgamma, float* dbeta, float* c1, float* c2) {
+    __shared__ double s_s[16][33], s_q[16][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    double s = 0.0, q = 0.0;
+    if (c < C) {
+        for (int t = w; t < T; t += 16) {
+            s += (double)partials[((int64_t)t * 2 + 0) * C + c];
+            q += (double)partials[((int64_t)t * 2 + 1) * C + c];
+        }
+    }
+    s_s[w][lane] = s; s_q[w][lane] = q;
+    __syncthreads();
+    if (w == 0 && c < C) {
+        for (int i = 1; i < 16; i++) { s += s_s[i][lane]; q += s_q[i][lane]; }
+        if (dbeta) dbeta[c] = (float)s;
+        if (dgamma) dgamma[c] = (float)q;
+        if (c1) c1[c] = (float)(s / count);
+        if (c2) c2[c] = (float)(q / count);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ gz, const float* __restrict__ raw,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ c1,
+                                    const float* __restrict__ c2, int N, int H, int W, int C) {
+    const int vpp = C >> 3;
+    const int64_t total = (int64_t)N * H * W * vpp;
+    const int Hp = H + 2, Wp = W + 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % vpp);
+        const int64_t pix = i / vpp;
+        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+        const int c = cv * 8;
+        __nv_bfloat16* gp = gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c;
+        uint4 u = *(const uint4*)gp;
+        __nv_bfloat16* gb = (__nv_bfloat16*)&u;
+        const float4 r0 = *(const float4*)(raw + pix * C + c);
+        const float4 r1 = *(const float4*)(raw + pix * C + c + 4);
+        const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float is = invstd[c + e];
+            const float xh = (r[e] - mean[c + e]) * is;
+            const float g = __bfloat162float(gb[e]);
+            gb[e] = __float2bfloat16_rn(gamma[c + e] * is * (g - c1[c + e] - xh * c2[c + e]));
+        }
+        *(uint4*)gp = u;
+    }
+}
+
+inline int ew_blocks(int64_t total) {
+    int64_t b = (total + 255) / 256;
+    const int64_t cap = 148 * 8;
+    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int rnr_bn_finalize(const float* partials, int T, int ld, int C, double count, const float* gamma,
+                               const float* beta, float eps, float* mean, float* invstd, float* scale, float* shift,
+                               float* running_mean, float* running_var, float momentum, void* stream) {
+    bn_finalize_kernel<<<rnr_cdiv(C, 32), 512, 0, (cudaStream_t)stream>>>(partials, T, ld, C, count, gamma, beta, eps, mean,
+                                                                        invstd, scale, shift, running_mean, running_var, momentum);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bn_act_fwd(const float* raw, const float* scale, const float* shift, const float* drop, float slope,
+                              void* act, int N, int H, int W, int C, void* stream) {
+    RNR_REQUIRE(C % 8 == 0, "rnr_bn_act_fwd: C=%d must be a multiple of 8", C);
+    RNR_REQUIRE(H >= 2 && W >= 2, "rnr_bn_act_fwd: reflect halo needs H,W >= 2");
+    const int64_t total = (int64_t)N * H * W * (C / 8);
+    bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(raw, scale, shift, drop, slope, (__half*)act, N, H, W, C);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* raw, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, const float* drop, float slope, void* gz,
+                                 float* partials, int* T_out, int N, int H, int W, int C, void* stream) {
+    RNR_REQUIRE(C % 8 == 0 && C <= 2048, "rnr_bn_bwd_reduce: bad C=%d", C);
+    RNR_REQUIRE(nsrc >= 1 && nsrc <= 2, "rnr_bn_bwd_reduce: nsrc must be 1 or 2");
+    GSrcs gs;
+    gs.n = nsrc;
+    for (int i = 0; i < nsrc; i++) gs.s[i] = srcs[i];
+    const int vpp = C / 8;
+    int ppb = 256 / vpp;
+    if (ppb < 1) ppb = 1;
+    const int threads = vpp * ppb > 256 ? 256 : vpp * ppb;   // vpp<=256 guaranteed by C<=2048
+    const int64_t npix = (int64_t)N * H * W;
+    int T = rnr_cdiv(npix, (int64_t)ppb * 8);
+    if (T > 148 * 4) T = 148 * 4;
+    if (T < 1) T = 1;
+    if (T_out) *T_out = T;
+    bn_bwd_reduce_kernel<<<T, threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+        gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, partials, N, H, W, C, ppb);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count, float* dgamma, float* dbeta, float* c1,
+                                   float* c2, void* stream) {
+    bn_bwd_finalize_kernel<<<rnr_cdiv(C, 32), 512, 0, (cudaStream_t)stream>>>(partials, T, C, count, dgamma, dbeta, c1, c2);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bn_bwd_apply(void* gz, const float* raw, const float* gamma, const float* mean, const float* invstd,
+                                const float* c1, const float* c2, int N, int H, int W, int C, void* stream) {
+    const int64_t total = (int64_t)N * H * W * (C / 8);
+    bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, gamma, mean, invstd, c1, c2, N, H, W, C);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}

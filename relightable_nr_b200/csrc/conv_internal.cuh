@@ -1,0 +1,70 @@
+// Internal structures shared by the SIMT and tcgen05 implementations of the generic
+// implicit-GEMM convolution (rnr_conv_*) and weight-gradient (rnr_wgrad_*) problems.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+struct ConvParams {
+    ViewD views[RNR_MAX_VIEWS];
+    const rnr_kstep_t* ksteps;   // device
+    int n_ksteps, bk, ab_dtype;
+    const void* wmat;
+    int ldw, n_rows_w, cout;
+    int mN, mY, mX, th, tw, tiles_y, tiles_x, tiles_m;
+    void* out;
+    int out_dtype;
+    int64_t out_sn, out_sy, out_sx;
+    int out_my, out_mx, out_py, out_px;
+    int epi;
+    const float* bias;
+    float* stats;
+    int ldstats;
+};
+
+struct rnr_conv_plan {
+    ConvParams p;
+    int impl;
+    rnr_kstep_t* d_ksteps;
+    // tcgen05 path
+    CUtensorMap tmap_a[RNR_MAX_VIEWS];
+    CUtensorMap tmap_b;
+    int bn;            // N tile of the tensor-core kernel
+    int tiles_n;
+    int stages;
+    int smem_bytes;
+    int grid;
+};
+
+struct WgradParams {
+    ViewD aviews[RNR_MAX_VIEWS];
+    ViewD gviews[4];
+    const rnr_wtap_t* taps;      // device
+    int n_taps, a_dtype, g_dtype;
+    int cout;
+    int mN, mY, mX;
+    float* dw;
+    int64_t s_co, s_ci;
+};
+
+struct rnr_wgrad_plan {
+    WgradParams p;
+    int impl;
+    rnr_wtap_t* d_taps;
+    rnr_wtap_t* h_taps;
+    // SIMT tiling
+    int n_tiles;         // (tap, ci-block, co-block) output tiles
+    int* d_tile_tab;     // [n_tiles,3] = tap, ci block, co block
+    int splitk;
+    // tcgen05 path
+    CUtensorMap tmap_a[RNR_MAX_VIEWS];
+    CUtensorMap tmap_g[4];
+    int th, tw;
+    int smem_bytes, grid;
+    int n_work;          // tc work items
+    int* d_work_tab;
+};
+
+int rnr_conv_tc_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* prob);
+int rnr_conv_tc_run(const rnr_conv_plan* plan, cudaStream_t stream);
+int rnr_wgrad_tc_prepare(rnr_wgrad_plan* plan, const rnr_wgrad_problem_t* prob);
+int rnr_wgrad_tc_run(const rnr_wgrad_plan* plan, cudaStream_t stream);

@@ -1,0 +1,663 @@
+"""Host-side engine for the U-Net of network.RenderingNet (network.py:219-253,
+pytorch_prototyping/pytorch_prototyping.py:432-536): forward, data-gradient and weight-gradient of
+the 22 live convolution layers, each expressed as generic implicit-GEMM problems executed by
+librnr_b200.so (tcgen05 kernels, or the SIMT validation kernels with impl='simt').
+
+Data layout in HBM (per layer, allocated once per input shape and reused every step):
+  act   fp16  [N, H+2, W+2, C]  reflect halo    -- post BN/activation/dropout, operand of the next conv
+  raw   fp32  [N, H,   W,   C]                  -- conv output before BatchNorm (kept for backward)
+  gz    bf16  [N, H+2, W+2, C]  zero halo       -- gradient w.r.t. raw
+  gx    bf16  padded or dense                    -- gradient w.r.t. a layer's (padded) input
+The dead GCN branch of UnetSkipConnectionBlock.forward (pytorch_prototyping.py:407-415, overwritten
+at :416-419) is not executed; it cannot influence outputs or gradients.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import _lib
+from .._lib import BF16, EPI_BIAS, EPI_STATS, EPI_TANH, F16, F32, ConvProblem, GSrc, KStep, WgradProblem, WTap
+from .views import HaloTensor, tile_shape
+
+_TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class LayerSpec:
+    name: str
+    kind: str                  # 'c3' (3x3 s1 reflect) | 'c4s2' (4x4 s2 reflect) | 'ct' (ConvTranspose 4x4 s2 p1)
+    src: List[str]             # names of input activation tensors (concatenated along channels)
+    cin: List[int]             # channels of each source
+    cout: int
+    H: int                     # input spatial size
+    W: int
+    w_key: str
+    b_key: Optional[str]
+    bn_key: Optional[str]
+    slope: Optional[float]     # LeakyReLU slope (0.0 == ReLU); None for the final linear layer (+tanh)
+    dst: str
+    drop: bool = True
+
+    @property
+    def Ho(self):
+        return {'c3': self.H, 'c4s2': self.H // 2, 'ct': self.H * 2}[self.kind]
+
+    @property
+    def Wo(self):
+        return {'c3': self.W, 'c4s2': self.W // 2, 'ct': self.W * 2}[self.kind]
+
+
+def unet_layer_specs(in_channels, out_channels, nf0, num_down, max_channels, H, W) -> List[LayerSpec]:
+    """Live layers of pytorch_prototyping.Unet in execution order.
+    Keys are relative to the ``Unet`` module."""
+    specs = []
+    specs.append(LayerSpec('in', 'c3', ['input'], [in_channels], nf0, H, W,
+                           'in_layer.0.net.1.weight', None, 'in_layer.1', 0.2, 'x0'))
+    chans = [min(2 ** i * nf0, max_channels) for i in range(num_down)]
+    up_specs = []
+    prefix = 'unet_block'
+    h, w = H, W
+    for i in range(num_down):
+        innermost = (i == num_down - 1)
+        outer = chans[i]
+        inner = chans[i] if innermost else chans[i + 1]
+        bn = not innermost
+        # DownBlock: pad, conv3, [bn], lrelu, drop, pad, conv4s2, [bn], lrelu, drop
+        if bn:
+            k1, b1, k2, b2 = 'net.1', 'net.2', 'net.6', 'net.7'
+        else:
+            k1, b1, k2, b2 = 'net.1', None, 'net.5', None
+        specs.append(LayerSpec(f'b{i}.down1', 'c3', [f'x{i}'], [outer], outer, h, w,
+                               f'{prefix}.down.{k1}.weight', None if bn else f'{prefix}.down.{k1}.bias',
+                               f'{prefix}.down.{b1}' if bn else None, 0.2, f'd{i}'))
+        specs.append(LayerSpec(f'b{i}.down2', 'c4s2', [f'd{i}'], [outer], inner, h, w,
+                               f'{prefix}.down.{k2}.weight', None if bn else f'{prefix}.down.{k2}.bias',
+                               f'{prefix}.down.{b2}' if bn else None, 0.2, f'x{i + 1}'))
+        # UpBlock: convT, [bn], relu, drop, Conv2dSame, [bn], relu, drop
+        if bn:
+            u1, ub1, u2, ub2 = 'net.0', 'net.1', 'net.4.net.1', 'net.5'
+        else:
+            u1, ub1, u2, ub2 = 'net.0', None, 'net.3.net.1', None
+        if innermost:
+            srcs, cins = [f'x{i + 1}'], [inner]
+        else:
+            srcs, cins = [f'x{i + 1}', f'y{i + 1}'], [inner, inner]
+        up_specs.append([
+            LayerSpec(f'b{i}.up1', 'ct', srcs, cins, outer, h // 2, w // 2,
+                      f'{prefix}.up.{u1}.weight', None if bn else f'{prefix}.up.{u1}.bias',
+                      f'{prefix}.up.{ub1}' if bn else None, 0.0, f'u{i}'),
+            LayerSpec(f'b{i}.up2', 'c3', [f'u{i}'], [outer], outer, h, w,
+                      f'{prefix}.up.{u2}.weight', None if bn else f'{prefix}.up.{u2}.bias',
+                      f'{prefix}.up.{ub2}' if bn else None, 0.0, f'y{i}'),
+        ])
+        prefix += '.submodule'
+        h //= 2
+        w //= 2
+    for ups in reversed(up_specs):
+        specs.extend(ups)
+    specs.append(LayerSpec('out', 'c3', ['x0', 'y0'], [nf0, nf0], out_channels, H, W,
+                           'out_layer.0.net.1.weight', 'out_layer.0.net.1.bias', None, None, 'out', drop=False))
+    return specs
+
+
+class _Plan:
+    """RAII holder of a C-side plan handle."""
+
+    def __init__(self, handle, kind):
+        self.h = handle
+        self.kind = kind
+
+    def __del__(self):
+        try:
+            L = _lib.lib()
+            if self.h:
+                (L.rnr_conv_plan_destroy if self.kind == 'conv' else L.rnr_wgrad_plan_destroy)(self.h)
+        except Exception:
+            pass
+
+
+@dataclass
+class _WPrep:
+    src_key: str
+    src_off: int            # element offset into the fp32 parameter
+    dst: torch.Tensor
+    dtype: int
+    nr: int
+    nr_pad: int
+    nc: int
+    cpad: int
+    ntaps: int
+    s_r: int
+    s_c: int
+    tapoff: torch.Tensor    # int32 device
+
+
+@dataclass
+class _LayerState:
+    spec: LayerSpec
+    raw: Optional[torch.Tensor] = None
+    stats: Optional[torch.Tensor] = None
+    n_stat_tiles: int = 0
+    mean: Optional[torch.Tensor] = None
+    invstd: Optional[torch.Tensor] = None
+    scale: Optional[torch.Tensor] = None
+    shift: Optional[torch.Tensor] = None
+    c1: Optional[torch.Tensor] = None
+    c2: Optional[torch.Tensor] = None
+    bwd_partials: Optional[torch.Tensor] = None
+    fwd_plans: List[_Plan] = field(default_factory=list)
+    dgrad_plans: List[_Plan] = field(default_factory=list)
+    wgrad_plan: Optional[_Plan] = None
+    wprep_fwd: List[_WPrep] = field(default_factory=list)
+    wprep_dgrad: List[_WPrep] = field(default_factory=list)
+    gx: Optional[torch.Tensor] = None      # dgrad result
+    gx_fold: bool = False
+    gx_ld: int = 0
+    drop: Optional[torch.Tensor] = None
+
+
+class UNetEngine:
+    def __init__(self, specs: List[LayerSpec], params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor],
+                 N: int, in_channels: int, device, impl: str = 'tc', input_grad_range: Optional[Tuple[int, int]] = None,
+                 act_dtype: int = F16, grad_dtype: int = BF16, need_backward: bool = True, wgrad_impl: Optional[str] = None):
+        self.L = _lib.lib()
+        self.specs = specs
+        self.params = params
+        self.buffers = buffers
+        self.N = N
+        self.device = torch.device(device)
+        self.impl = {'simt': 0, 'tc': 1}[impl]
+        self.wgrad_impl = {'simt': 0, 'tc': 1}[wgrad_impl or impl]
+        self.act_dt, self.grad_dt = act_dtype, grad_dtype
+        self.in_channels = in_channels
+        self.in_cpad = _rup(in_channels, 64) if in_channels > 32 else _rup(in_channels, 16)
+        self.input_grad_range = input_grad_range
+        self.need_backward = need_backward
+        self.H, self.W = specs[0].H, specs[0].W
+        self.keep = []            # keeps ctypes arrays / tensors referenced by plans alive
+        self.gpu_launches = 0
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    # construction
+    # ------------------------------------------------------------------------------------------
+    def _alloc(self, shape, dtype, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(shape, dtype=dtype, device=self.device)
+
+    def _build(self):
+        N, dev = self.N, self.device
+        adt, gdt = _TORCH_DT[self.act_dt], _TORCH_DT[self.grad_dt]
+        self.acts: Dict[str, HaloTensor] = {}
+        self.gz: Dict[str, HaloTensor] = {}
+        self.layers: Dict[str, _LayerState] = {}
+        self.producer: Dict[str, str] = {}        # act name -> layer name producing it
+        self.consumers: Dict[str, List[Tuple[str, int]]] = {}   # act name -> [(layer name, source index)]
+        s0 = self.specs[0]
+        self.acts['input'] = HaloTensor(N, s0.H, s0.W, self.in_cpad, adt, dev, zero=True)
+        self.ones = {}
+        self.zeros = {}
+        grad_numel = 0
+        self.grad_slices = {}
+        for sp in self.specs:
+            st = _LayerState(sp)
+            self.layers[sp.name] = st
+            for si, s in enumerate(sp.src):
+                self.consumers.setdefault(s, []).append((sp.name, si))
+            self.producer[sp.dst] = sp.name
+            Ho, Wo = sp.Ho, sp.Wo
+            if sp.dst == 'out':
+                self.out_ld = _rup(sp.cout, 16)
+                st.raw = self._alloc((N, Ho, Wo, self.out_ld), torch.float32, zero=True)
+            else:
+                st.raw = self._alloc((N, Ho, Wo, sp.cout), torch.float32)
+                self.acts[sp.dst] = HaloTensor(N, Ho, Wo, sp.cout, adt, dev, zero=True)
+                for nm in ('mean', 'invstd', 'scale', 'shift', 'c1', 'c2'):
+                    setattr(st, nm, self._alloc((sp.cout,), torch.float32, zero=True))
+                st.invstd.fill_(1.0)
+                st.scale.fill_(1.0)
+            if self.need_backward:
+                ld = self.out_ld if sp.dst == 'out' else sp.cout
+                self.gz[sp.name] = HaloTensor(N, Ho, Wo, ld, gdt, dev, zero=True)
+                st.bwd_partials = self._alloc((148 * 4 * 2 * max(ld, 8),), torch.float32)
+            # flat gradient storage
+            for key in (sp.w_key, sp.b_key, (sp.bn_key + '.weight') if sp.bn_key else None,
+                        (sp.bn_key + '.bias') if sp.bn_key else None):
+                if key is not None:
+                    n = self.params[key].numel()
+                    self.grad_slices[key] = (grad_numel, n)
+                    grad_numel += _rup(n, 4)
+        self.grad_flat = self._alloc((max(grad_numel, 4),), torch.float32, zero=True) if self.need_backward else None
+        for sp in self.specs:
+            self._build_layer(self.layers[sp.name])
+
+    # ---- problem builders ---------------------------------------------------------------------
+    def _conv_problem(self, views, ksteps, ab_dtype, bk, wmat, n_rows_w, cout, mN, mY, mX, out_t, out_dtype,
+                      out_strides, out_mp, epi, bias, stats, ldstats, impl):
+        prob = ConvProblem()
+        for i, v in enumerate(views):
+            prob.views[i] = v
+        prob.n_views = len(views)
+        prob.ab_dtype = ab_dtype
+        prob.bk = bk
+        arr = (KStep * len(ksteps))()
+        for i, (v, c0, dx, dy) in enumerate(ksteps):
+            arr[i].view, arr[i].c0, arr[i].dx, arr[i].dy = v, c0, dx, dy
+        prob.n_ksteps = len(ksteps)
+        prob.ksteps = C.cast(arr, C.POINTER(KStep))
+        prob.wmat = wmat.data_ptr()
+        prob.n_rows_w = n_rows_w
+        prob.cout = cout
+        prob.mN, prob.mY, prob.mX = mN, mY, mX
+        prob.th, prob.tw = tile_shape(mX)
+        prob.out = out_t if isinstance(out_t, int) else out_t.data_ptr()
+        prob.out_dtype = out_dtype
+        prob.out_sn, prob.out_sy, prob.out_sx = out_strides
+        prob.out_my, prob.out_mx, prob.out_py, prob.out_px = out_mp
+        prob.epi = epi
+        prob.bias = bias.data_ptr() if bias is not None else None
+        prob.stats = stats if isinstance(stats, int) or stats is None else stats.data_ptr()
+        prob.ldstats = ldstats
+        h = C.c_void_p()
+        _lib.check(self.L.rnr_conv_plan_create(C.byref(prob), impl, C.byref(h)), 'rnr_conv_plan_create')
+        return _Plan(h, 'conv')
+
+    @staticmethod
+    def _bk_for(channel_counts):
+        for bk in (64, 32, 16):
+            if all(c % bk == 0 for c in channel_counts):
+                return bk
+        raise ValueError('channel counts %s must be multiples of 16' % (channel_counts,))
+
+    def _tapoff(self, offs):
+        t = torch.tensor(offs, dtype=torch.int32, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def _build_layer(self, st: _LayerState):
+        sp = st.spec
+        N = self.N
+        adt_t, gdt_t = _TORCH_DT[self.act_dt], _TORCH_DT[self.grad_dt]
+        srcs = [self.acts[s] for s in sp.src]
+        cpads = [t.C for t in srcs]           # stored channel counts (input layer is padded)
+        cin_tot = sum(sp.cin)
+        cpad_tot = sum(cpads)
+        final = sp.dst == 'out'
+        Ho, Wo = sp.Ho, sp.Wo
+        cout = sp.cout
+        ld_out = self.out_ld if final else cout
+        k = 3 if sp.kind == 'c3' else 4
+        kk = k * k
+        bk = self._bk_for(cpads)
+        n_rows = _rup(cout, 16)
+        epi = 0
+        bias_t = None
+        if final:
+            epi = EPI_BIAS | EPI_TANH
+            bias_t = self.params[sp.b_key]
+        elif sp.bn_key is not None:
+            epi = EPI_STATS
+
+        def ksteps_for(taps):
+            """taps: list of (view index per source -> list, dx, dy)"""
+            ks = []
+            for (vidx, dx, dy) in taps:
+                for si in range(len(srcs)):
+                    for c0 in range(0, cpads[si], bk):
+                        ks.append((vidx[si], c0, dx, dy))
+            return ks
+
+        # ------------------------------ forward ------------------------------
+        if sp.kind == 'c3':
+            views = [t.padded() for t in srcs]
+            taps = [([si for si in range(len(srcs))], kw, kh) for kh in range(3) for kw in range(3)]
+            tapoffs = [kh * 3 + kw for kh in range(3) for kw in range(3)]
+            wm = self._alloc((n_rows, 9 * cpad_tot), adt_t, zero=True)
+            st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 9,
+                                       cin_tot * 9, 9, self._tapoff(tapoffs)))
+            th, tw = tile_shape(Wo)
+            tiles = N * -(-Ho // th) * -(-Wo // tw)
+            if epi & EPI_STATS:
+                st.stats = self._alloc((tiles, 2, cout), torch.float32, zero=True)
+                st.n_stat_tiles = tiles
+            st.fwd_plans.append(self._conv_problem(
+                views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32,
+                (Ho * Wo * ld_out, Wo * ld_out, ld_out), (1, 1, 0, 0), epi, bias_t, st.stats, cout, self.impl))
+        elif sp.kind == 'c4s2':
+            views = []
+            for t in srcs:
+                views += [t.parity(p, q) for p in range(2) for q in range(2)]
+            taps, tapoffs = [], []
+            for kh in range(4):
+                for kw in range(4):
+                    a, p, b, q = kh // 2, kh % 2, kw // 2, kw % 2
+                    taps.append(([si * 4 + p * 2 + q for si in range(len(srcs))], b, a))
+                    tapoffs.append(kh * 4 + kw)
+            wm = self._alloc((n_rows, 16 * cpad_tot), adt_t, zero=True)
+            st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 16,
+                                       cin_tot * 16, 16, self._tapoff(tapoffs)))
+            th, tw = tile_shape(Wo)
+            tiles = N * -(-Ho // th) * -(-Wo // tw)
+            if epi & EPI_STATS:
+                st.stats = self._alloc((tiles, 2, cout), torch.float32, zero=True)
+                st.n_stat_tiles = tiles
+            st.fwd_plans.append(self._conv_problem(
+                views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32,
+                (Ho * Wo * ld_out, Wo * ld_out, ld_out), (1, 1, 0, 0), epi, bias_t, st.stats, cout, self.impl))
+        else:  # ConvTranspose 4x4 s2 p1: four parity sub-problems, each a 2x2 conv over the un-padded input
+            views = [t.interior() for t in srcs]
+            Hi, Wi = sp.H, sp.W
+            th, tw = tile_shape(Wi)
+            tiles = N * -(-Hi // th) * -(-Wi // tw)
+            if epi & EPI_STATS:
+                st.stats = self._alloc((4 * tiles, 2, cout), torch.float32, zero=True)
+                st.n_stat_tiles = 4 * tiles
+            sel = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}      # parity -> [(k index, input offset)]
+            for ph in range(2):
+                for pw in range(2):
+                    taps, tapoffs = [], []
+                    for (kh, dy) in sel[ph]:
+                        for (kw, dx) in sel[pw]:
+                            taps.append(([si for si in range(len(srcs))], dx, dy))
+                            tapoffs.append(kh * 4 + kw)
+                    wm = self._alloc((n_rows, 4 * cpad_tot), adt_t, zero=True)
+                    # weight [Cin, Cout, 4, 4]: rows = co (stride 16), cols = ci (stride Cout*16)
+                    st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 4,
+                                               16, cout * 16, self._tapoff(tapoffs)))
+                    stats_ptr = None
+                    if st.stats is not None:
+                        stats_ptr = st.stats.data_ptr() + (ph * 2 + pw) * tiles * 2 * cout * 4
+                    st.fwd_plans.append(self._conv_problem(
+                        views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Hi, Wi, st.raw, F32,
+                        (Ho * Wo * ld_out, Wo * ld_out, ld_out), (2, 2, ph, pw), epi, bias_t, stats_ptr, cout, self.impl))
+        if not self.need_backward:
+            return
+
+        # ------------------------------ weight gradient ------------------------------
+        G = self.gz[sp.name]
+        wp = WgradProblem()
+        for i, v in enumerate(views):
+            wp.aviews[i] = v
+        wp.n_aviews = len(views)
+        wp.a_dtype, wp.g_dtype = self.act_dt, self.grad_dt
+        wtaps = []
+        if sp.kind == 'c3':
+            wp.gviews[0] = G.interior()
+            wp.n_gviews = 1
+            for kh in range(3):
+                for kw in range(3):
+                    ci0 = 0
+                    for si in range(len(srcs)):
+                        wtaps.append((si, kw, kh, 0, 0, ci0, sp.cin[si], kh * 3 + kw))
+                        ci0 += sp.cin[si]
+            wp.mN, wp.mY, wp.mX = N, Ho, Wo
+            wp.s_co, wp.s_ci = cin_tot * 9, 9
+        elif sp.kind == 'c4s2':
+            wp.gviews[0] = G.interior()
+            wp.n_gviews = 1
+            for kh in range(4):
+                for kw in range(4):
+                    a, p, b, q = kh // 2, kh % 2, kw // 2, kw % 2
+                    ci0 = 0
+                    for si in range(len(srcs)):
+                        wtaps.append((si * 4 + p * 2 + q, b, a, 0, 0, ci0, sp.cin[si], kh * 4 + kw))
+                        ci0 += sp.cin[si]
+            wp.mN, wp.mY, wp.mX = N, Ho, Wo
+            wp.s_co, wp.s_ci = cin_tot * 16, 16
+        else:
+            sel = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}
+            for ph in range(2):
+                for pw in range(2):
+                    wp.gviews[ph * 2 + pw] = G.interior_parity(ph, pw)
+                    for (kh, dy) in sel[ph]:
+                        for (kw, dx) in sel[pw]:
+                            ci0 = 0
+                            for si in range(len(srcs)):
+                                wtaps.append((si, dx, dy, ph * 2 + pw, 0, ci0, sp.cin[si], kh * 4 + kw))
+                                ci0 += sp.cin[si]
+            wp.n_gviews = 4
+            wp.mN, wp.mY, wp.mX = N, sp.H, sp.W
+            wp.s_co, wp.s_ci = 16, cout * 16
+        tarr = (WTap * len(wtaps))()
+        for i, (v, dx, dy, gv, c0, ci0, nci, off) in enumerate(wtaps):
+            tarr[i].view, tarr[i].dx, tarr[i].dy, tarr[i].gview = v, dx, dy, gv
+            tarr[i].c0, tarr[i].ci0, tarr[i].nci, tarr[i].off = c0, ci0, nci, off
+        wp.n_taps = len(wtaps)
+        wp.taps = C.cast(tarr, C.POINTER(WTap))
+        wp.cout = cout
+        g0, gn = self.grad_slices[sp.w_key]
+        wp.dw = self.grad_flat.data_ptr() + 4 * g0
+        h = C.c_void_p()
+        _lib.check(self.L.rnr_wgrad_plan_create(C.byref(wp), self.wgrad_impl, C.byref(h)), 'rnr_wgrad_plan_create')
+        st.wgrad_plan = _Plan(h, 'wgrad')
+
+        # ------------------------------ data gradient ------------------------------
+        if sp.name == 'in':
+            if self.input_grad_range is None:
+                return
+            r0, r1 = self.input_grad_range
+        else:
+            r0, r1 = 0, cin_tot
+        nci = r1 - r0
+        nci_pad = _rup(nci, 16)
+        Hi, Wi = sp.H, sp.W
+        gC = G.C
+        gbk = self._bk_for([gC])
+        if sp.kind == 'c3':
+            # gxp[ih,iw,ci] = sum_{kh,kw,co} Gp[ih-kh+1, iw-kw+1, co] W[co,ci,kh,kw]   over the padded input plane
+            Hp, Wp = Hi + 2, Wi + 2
+            st.gx = self._alloc((N, Hp, Wp, nci_pad), gdt_t, zero=True)
+            st.gx_fold, st.gx_ld = True, nci_pad
+            ks, tapoffs = [], []
+            for kh in range(3):
+                for kw in range(3):
+                    for c0 in range(0, gC, gbk):
+                        ks.append((0, c0, 1 - kw, 1 - kh))
+                    tapoffs.append(kh * 3 + kw)
+            wm = self._alloc((nci_pad, 9 * gC), gdt_t, zero=True)
+            # rows = ci (stride 9), cols = co (stride Cin*9)
+            st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 9, wm, self.grad_dt, nci, nci_pad, cout, gC, 9, 9, cin_tot * 9,
+                                         self._tapoff(tapoffs)))
+            st.dgrad_plans.append(self._conv_problem(
+                [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp, Wp, st.gx, self.grad_dt,
+                (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
+        elif sp.kind == 'c4s2':
+            Hp, Wp = Hi + 2, Wi + 2
+            st.gx = self._alloc((N, Hp, Wp, nci_pad), gdt_t, zero=True)
+            st.gx_fold, st.gx_ld = True, nci_pad
+            for ph in range(2):
+                for pw in range(2):
+                    ks, tapoffs = [], []
+                    for a in range(2):
+                        for b in range(2):
+                            for c0 in range(0, gC, gbk):
+                                ks.append((0, c0, 1 - b, 1 - a))
+                            tapoffs.append((2 * a + ph) * 4 + (2 * b + pw))
+                    wm = self._alloc((nci_pad, 4 * gC), gdt_t, zero=True)
+                    st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 16, wm, self.grad_dt, nci, nci_pad, cout, gC, 4, 16,
+                                                 cin_tot * 16, self._tapoff(tapoffs)))
+                    st.dgrad_plans.append(self._conv_problem(
+                        [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp // 2, Wp // 2, st.gx, self.grad_dt,
+                        (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (2, 2, ph, pw), 0, None, None, 0, self.impl))
+        else:
+            # gX[ih,iw,ci] = sum_{kh,kw,co} Gp[2ih+kh, 2iw+kw, co] W[ci,co,kh,kw]
+            st.gx = self._alloc((N, Hi, Wi, nci_pad), gdt_t, zero=True)
+            st.gx_fold, st.gx_ld = False, nci_pad
+            gviews = [G.parity(p, q) for p in range(2) for q in range(2)]
+            ks, tapoffs = [], []
+            for kh in range(4):
+                for kw in range(4):
+                    a, p, b, q = kh // 2, kh % 2, kw // 2, kw % 2
+                    for c0 in range(0, gC, gbk):
+                        ks.append((p * 2 + q, c0, b, a))
+                    tapoffs.append(kh * 4 + kw)
+            wm = self._alloc((nci_pad, 16 * gC), gdt_t, zero=True)
+            # weight [Cin, Cout, 4,4]: rows = ci (stride Cout*16), cols = co (stride 16)
+            st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * cout * 16, wm, self.grad_dt, nci, nci_pad, cout, gC, 16, cout * 16, 16,
+                                         self._tapoff(tapoffs)))
+            st.dgrad_plans.append(self._conv_problem(
+                gviews, ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hi, Wi, st.gx, self.grad_dt,
+                (Hi * Wi * nci_pad, Wi * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _wprep(self, items: List[_WPrep], s):
+        for w in items:
+            src = self.params[w.src_key]
+            _lib.check(self.L.rnr_weight_prep(src.data_ptr() + 4 * w.src_off, w.dst.data_ptr(), w.dtype, w.nr, w.nr_pad,
+                                              w.nc, w.cpad, w.ntaps, w.s_r, w.s_c, w.tapoff.data_ptr(), s), 'rnr_weight_prep')
+            self.gpu_launches += 1
+
+    def prepare_weights(self, backward=False):
+        s = self._stream()
+        for sp in self.specs:
+            st = self.layers[sp.name]
+            self._wprep(st.wprep_fwd, s)
+            if backward:
+                self._wprep(st.wprep_dgrad, s)
+
+    def set_input_nchw(self, x: torch.Tensor):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        N, Cc, H, W = x.shape
+        assert (N, Cc, H, W) == (self.N, self.in_channels, self.H, self.W), 'engine built for a different input shape'
+        _lib.check(self.L.rnr_pack_nchw_to_act(x.data_ptr(), self.acts['input'].ptr, N, Cc, self.in_cpad, H, W, self._stream()),
+                   'rnr_pack_nchw_to_act')
+        self.gpu_launches += 1
+
+    def forward(self, training: bool, drop_masks: Optional[Dict[str, torch.Tensor]] = None, momentum: float = 0.1,
+                eps: float = 1e-5, weights_ready: bool = False):
+        """Runs all layers on the current stream.  ``drop_masks[layer name]`` = [N, C] fp32 scale tensor
+        (0 or 1/(1-p)) or None for no dropout.  Returns the final fp32 NHWC tensor [N,H,W,ld] (tanh applied)."""
+        L, s = self.L, self._stream()
+        if not weights_ready:
+            self.prepare_weights(backward=self.need_backward and training)
+        for sp in self.specs:
+            st = self.layers[sp.name]
+            for pl in st.fwd_plans:
+                _lib.check(L.rnr_conv_run(pl.h, s), 'rnr_conv_run(%s)' % sp.name)
+                self.gpu_launches += 1
+            if sp.dst == 'out':
+                continue
+            N, Ho, Wo, Cc = self.N, sp.Ho, sp.Wo, sp.cout
+            if sp.bn_key is not None:
+                rm = rv = None
+                if training:
+                    rm, rv = self.buffers[sp.bn_key + '.running_mean'], self.buffers[sp.bn_key + '.running_var']
+                _lib.check(L.rnr_bn_finalize(st.stats.data_ptr(), st.n_stat_tiles, Cc, Cc, float(N * Ho * Wo),
+                                             self.params[sp.bn_key + '.weight'].data_ptr(),
+                                             self.params[sp.bn_key + '.bias'].data_ptr(), eps,
+                                             st.mean.data_ptr(), st.invstd.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(),
+                                             rm.data_ptr() if rm is not None else None,
+                                             rv.data_ptr() if rv is not None else None, momentum, s), 'rnr_bn_finalize')
+                self.gpu_launches += 1
+                shift = st.shift
+            else:
+                shift = self.params[sp.b_key]
+            st.drop = drop_masks.get(sp.name) if (drop_masks and sp.drop) else None
+            _lib.check(L.rnr_bn_act_fwd(st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
+                                        st.drop.data_ptr() if st.drop is not None else None, sp.slope,
+                                        self.acts[sp.dst].ptr, N, Ho, Wo, Cc, s), 'rnr_bn_act_fwd')
+            self.gpu_launches += 1
+        return self.layers['out'].raw
+
+    def output_nchw(self) -> torch.Tensor:
+        sp = self.specs[-1]
+        out = torch.empty((self.N, sp.cout, sp.Ho, sp.Wo), dtype=torch.float32, device=self.device)
+        _lib.check(self.L.rnr_unpack_nhwc_to_nchw(self.layers['out'].raw.data_ptr(), out.data_ptr(), self.N, sp.cout, self.out_ld,
+                                                  sp.Ho, sp.Wo, self._stream()), 'rnr_unpack_nhwc_to_nchw')
+        self.gpu_launches += 1
+        return out
+
+    def grad_view(self, key) -> torch.Tensor:
+        o, n = self.grad_slices[key]
+        return self.grad_flat[o:o + n].view(self.params[key].shape)
+
+    def _gsrcs_for(self, act_name):
+        """Gradient sources of an activation tensor = dgrad results of its consumers."""
+        out = []
+        for (lname, si) in self.consumers.get(act_name, []):
+            st = self.layers[lname]
+            if st.gx is None:
+                continue
+            g = GSrc()
+            g.ptr = st.gx.data_ptr()
+            g.dtype = self.grad_dt
+            g.fold = 1 if st.gx_fold else 0
+            g.ld = st.gx_ld
+            g.c0 = sum(st.spec.cin[:si])
+            out.append(g)
+        return out
+
+    def backward_from_nchw(self, grad_out: torch.Tensor):
+        """grad_out: d loss / d (tanh output), NCHW fp32.  Fills self.grad_flat; returns grad wrt the input
+        channels ``input_grad_range`` as NCHW fp32 (or None)."""
+        assert self.need_backward
+        L, s = self.L, self._stream()
+        sp = self.specs[-1]
+        st = self.layers['out']
+        self.grad_flat.zero_()
+        self.gpu_launches += 1
+        go = grad_out.contiguous()
+        _lib.check(L.rnr_tanh_bwd_pack(go.data_ptr(), st.raw.data_ptr(), self.gz['out'].ptr,
+                                       self.grad_view(sp.b_key).data_ptr(), self.N, sp.cout, self.out_ld, sp.Ho, sp.Wo, s),
+                   'rnr_tanh_bwd_pack')
+        self.gpu_launches += 1
+        return self._backward_layers()
+
+    def _backward_layers(self):
+        L, s = self.L, self._stream()
+        N = self.N
+        for sp in reversed(self.specs):
+            st = self.layers[sp.name]
+            Ho, Wo, Cc = sp.Ho, sp.Wo, sp.cout
+            if sp.dst != 'out':
+                srcs = self._gsrcs_for(sp.dst)
+                assert 1 <= len(srcs) <= 2, (sp.name, len(srcs))
+                arr = (GSrc * len(srcs))(*srcs)
+                T = C.c_int(0)
+                has_bn = sp.bn_key is not None
+                shift = st.shift if has_bn else self.params[sp.b_key]
+                _lib.check(L.rnr_bn_bwd_reduce(arr, len(srcs), st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
+                                               st.mean.data_ptr(), st.invstd.data_ptr(),
+                                               st.drop.data_ptr() if st.drop is not None else None, sp.slope,
+                                               self.gz[sp.name].ptr, st.bwd_partials.data_ptr(), C.byref(T), N, Ho, Wo, Cc, s),
+                           'rnr_bn_bwd_reduce')
+                if has_bn:
+                    dgam = self.grad_view(sp.bn_key + '.weight').data_ptr()
+                    dbet = self.grad_view(sp.bn_key + '.bias').data_ptr()
+                else:
+                    dgam, dbet = None, self.grad_view(sp.b_key).data_ptr()
+                _lib.check(L.rnr_bn_bwd_finalize(st.bwd_partials.data_ptr(), T.value, Cc, float(N * Ho * Wo), dgam, dbet,
+                                                 st.c1.data_ptr(), st.c2.data_ptr(), s), 'rnr_bn_bwd_finalize')
+                self.gpu_launches += 2
+                if has_bn:
+                    _lib.check(L.rnr_bn_bwd_apply(self.gz[sp.name].ptr, st.raw.data_ptr(),
+                                                  self.params[sp.bn_key + '.weight'].data_ptr(), st.mean.data_ptr(),
+                                                  st.invstd.data_ptr(), st.c1.data_ptr(), st.c2.data_ptr(), N, Ho, Wo, Cc, s),
+                               'rnr_bn_bwd_apply')
+                    self.gpu_launches += 1
+            _lib.check(L.rnr_wgrad_run(st.wgrad_plan.h, s), 'rnr_wgrad_run(%s)' % sp.name)
+            self.gpu_launches += 1
+            for pl in st.dgrad_plans:
+                _lib.check(L.rnr_conv_run(pl.h, s), 'rnr_conv_run(dgrad %s)' % sp.name)
+                self.gpu_launches += 1
+        st = self.layers['in']
+        if st.gx is None:
+            return None
+        r0, r1 = self.input_grad_range
+        gi = torch.empty((N, r1 - r0, self.H, self.W), dtype=torch.float32, device=self.device)
+        _lib.check(L.rnr_fold_to_nchw(st.gx.data_ptr(), self.grad_dt, gi.data_ptr(), N, r1 - r0, 0, st.gx_ld, self.H, self.W, s),
+                   'rnr_fold_to_nchw')
+        self.gpu_launches += 1
+        return gi

@@ -1,0 +1,74 @@
+"""GPU parity of the U-Net engine (a15) against the CPU oracle (oracle/unet.py).
+
+Tolerances (stated, none exist in the reference): forward PSNR >= 50 dB on the tanh output
+(BASELINE.json north_star) and max-abs <= 2e-2 (fp16 operands, fp32 accumulation);
+parameter gradients cosine >= 0.999 and relative L2 <= 3e-2 (bf16 gradient tensors)."""
+import pytest
+import torch
+
+from tests.util import cosine, psnr, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(in_ch, out_ch, nf0, H, N, num_down, seed=0):
+    from oracle.unet import make_unet_state_dict
+    sd = make_unet_state_dict(in_ch, out_ch, nf0, num_down=num_down, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(N, in_ch, H, H, generator=g)
+    return sd, x
+
+
+def _engine(sd, x, out_ch, nf0, num_down, impl, grad_range, wgrad_impl=None):
+    from relightable_nr_b200.engine.unet import UNetEngine, unet_layer_specs
+    N, in_ch, H, W = x.shape
+    dev = torch.device('cuda:0')
+    params = {k: v.to(dev).contiguous() for k, v in sd.items() if v.dtype.is_floating_point and 'running' not in k}
+    buffers = {k: v.to(dev).clone() for k, v in sd.items() if 'running' in k}
+    specs = unet_layer_specs(in_ch, out_ch, nf0, num_down, 8 * nf0, H, W)
+    eng = UNetEngine(specs, params, buffers, N, in_ch, dev, impl=impl, input_grad_range=grad_range, wgrad_impl=wgrad_impl)
+    return eng, params
+
+
+def _oracle_fwd_bwd(sd, x, num_down, R, grad_range):
+    from oracle.unet import unet_forward
+    sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k else v) for k, v in sd.items()}
+    xg = x.clone().requires_grad_(True)
+    out = torch.tanh(unet_forward(sdg, xg, num_down=num_down))
+    (out * R).sum().backward()
+    grads = {k: v.grad for k, v in sdg.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    return out.detach(), grads, xg.grad[:, grad_range[0]:grad_range[1]]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("cfg", [
+    dict(in_ch=20, out_ch=6, nf0=16, H=64, N=1, num_down=5, grad_range=(4, 20)),
+    dict(in_ch=108, out_ch=78, nf0=64, H=64, N=2, num_down=5, grad_range=(84, 108)),
+])
+def test_unet_forward_backward(cfg, impl):
+    sd, x = _setup(cfg['in_ch'], cfg['out_ch'], cfg['nf0'], cfg['H'], cfg['N'], cfg['num_down'])
+    g = torch.Generator().manual_seed(7)
+    R = torch.randn(cfg['N'], cfg['out_ch'], cfg['H'], cfg['H'], generator=g) / (cfg['H'] * cfg['H'])
+    ref_out, ref_grads, ref_gx = _oracle_fwd_bwd(sd, x, cfg['num_down'], R, cfg['grad_range'])
+
+    eng, params = _engine(sd, x, cfg['out_ch'], cfg['nf0'], cfg['num_down'], impl, cfg['grad_range'],
+                          wgrad_impl='simt')
+    eng.set_input_nchw(x.cuda())
+    eng.forward(training=True, drop_masks=None)
+    out = eng.output_nchw().cpu()
+    p = psnr(out * 0.5 + 0.5, ref_out * 0.5 + 0.5)
+    err = (out - ref_out).abs().max().item()
+    print(f"[{impl}] forward psnr {p:.1f} dB  max-abs {err:.2e}")
+    assert p >= 50.0 and err <= 2e-2
+
+    gx = eng.backward_from_nchw(R.cuda())
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k, gref in ref_grads.items():
+        gm = eng.grad_view(k).cpu()
+        r, c = rel_l2(gm, gref), cosine(gm, gref)
+        worst = max(worst, r)
+        assert c >= 0.999 and r <= 3e-2, f"{k}: rel_l2 {r:.3e} cosine {c:.6f}"
+    r = rel_l2(gx.cpu(), ref_gx)
+    print(f"[{impl}] worst param-grad rel_l2 {worst:.2e}; input-grad rel_l2 {r:.2e}")
+    assert r <= 3e-2
