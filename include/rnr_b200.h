@@ -147,10 +147,12 @@ int rnr_bn_finalize(const float* partials, int T, int ld, int C, double count,
                     float* mean, float* invstd, float* scale, float* shift,
                     float* running_mean, float* running_var, float momentum, void* stream);
 
-/* act = drop * act(raw*scale + shift), written fp16 with reflect halo [N,H+2,W+2,C]            */
+/* act = drop * act(raw*scale + shift), written fp16 with reflect halo [N,H+2,W+2,C];
+ * act_bf16 (optional, same layout) receives a bf16 copy: the B operand of the weight-gradient MMA
+ * (kind::f16 needs both operands in the same 16-bit format and gradients are bf16)               */
 int rnr_bn_act_fwd(const float* raw, const float* scale, const float* shift,
                    const float* drop /* [N,C] or NULL */, float slope,
-                   void* act, int N, int H, int W, int C, void* stream);
+                   void* act, void* act_bf16, int N, int H, int W, int C, void* stream);
 
 typedef struct {
     const void* ptr;      /* bf16 or fp32 */
@@ -178,7 +180,7 @@ int rnr_bn_bwd_apply(void* gz, const float* raw, const float* gamma, const float
 /* layout glue of the module-level API (NCHW fp32 <-> channels-last 16-bit)                    */
 /*   network.RenderingNet.forward(input [N,C,H,W]) -> [N,Cout,H,W]   network.py:251-253        */
 /* ------------------------------------------------------------------------------------------ */
-int rnr_pack_nchw_to_act(const float* src, void* act, int N, int C, int Cpad, int H, int W, void* stream);
+int rnr_pack_nchw_to_act(const float* src, void* act, void* act_bf16 /* optional */, int N, int C, int Cpad, int H, int W, void* stream);
 int rnr_unpack_nhwc_to_nchw(const float* src, float* dst, int N, int C, int ld, int H, int W, void* stream);
 /* grad_out NCHW fp32 (d/d tanh-output) -> gz = grad*(1-t^2) bf16 zero-halo, + per-block bias partial sums */
 int rnr_tanh_bwd_pack(const float* grad_nchw, const float* tanh_nhwc, void* gz, float* dbias /* [C] atomics, pre-zeroed */,

@@ -32,32 +32,57 @@ def _rpad(x):
     return F.pad(x, (1, 1, 1, 1), mode='reflect')
 
 
+class _Q:
+    """Optional emulation of the engine's storage precision (test-only): weights and post-activation
+    tensors rounded to fp16 with a straight-through gradient.  With it the oracle's ReLU/LeakyReLU gates
+    agree with the engine's, so backward parity can be checked much tighter than against pure fp32
+    (where ~0.1% of gates flip and alone cause a few % relative-L2 gradient difference)."""
+    on = False
+
+
+    gates = None     # optional {layer name: bool mask [N,C,H,W]} of (pre-activation > 0) taken from the engine
+
+
+def _q(x):
+    if not _Q.on:
+        return x
+    return x + (x.half().float() - x).detach()
+
+
+def _act(y, slope, name):
+    """LeakyReLU(slope) (slope 0 == ReLU).  With _Q.gates the sign decisions come from the engine, so both
+    sides differentiate through identical gates (forward values differ only where |y| ~ 1e-3)."""
+    if _Q.gates is not None and name in _Q.gates:
+        return y * torch.where(_Q.gates[name], torch.ones_like(y), torch.full_like(y, slope))
+    return F.leaky_relu(y, slope) if slope != 0.0 else F.relu(y)
+
+
 def _down(x, sd, pfx, bn, i, drop, acts):
     k1, b1, k2, b2 = ('net.1', 'net.2', 'net.6', 'net.7') if bn else ('net.1', None, 'net.5', None)
-    y = F.conv2d(_rpad(x), sd[f'{pfx}.{k1}.weight'], None if bn else sd[f'{pfx}.{k1}.bias'])
+    y = F.conv2d(_rpad(x), _q(sd[f'{pfx}.{k1}.weight']), None if bn else sd[f'{pfx}.{k1}.bias'])
     if bn:
         y = _bn(y, sd, f'{pfx}.{b1}')
-    y = _drop(F.leaky_relu(y, 0.2), drop, f'b{i}.down1')
+    y = _q(_drop(_act(y, 0.2, f'b{i}.down1'), drop, f'b{i}.down1'))
     acts[f'd{i}'] = y
-    y = F.conv2d(_rpad(y), sd[f'{pfx}.{k2}.weight'], None if bn else sd[f'{pfx}.{k2}.bias'], stride=2)
+    y = F.conv2d(_rpad(y), _q(sd[f'{pfx}.{k2}.weight']), None if bn else sd[f'{pfx}.{k2}.bias'], stride=2)
     if bn:
         y = _bn(y, sd, f'{pfx}.{b2}')
-    y = _drop(F.leaky_relu(y, 0.2), drop, f'b{i}.down2')
+    y = _q(_drop(_act(y, 0.2, f'b{i}.down2'), drop, f'b{i}.down2'))
     acts[f'x{i + 1}'] = y
     return y
 
 
 def _up(x, sd, pfx, bn, i, drop, acts):
     u1, ub1, u2, ub2 = ('net.0', 'net.1', 'net.4.net.1', 'net.5') if bn else ('net.0', None, 'net.3.net.1', None)
-    y = F.conv_transpose2d(x, sd[f'{pfx}.{u1}.weight'], None if bn else sd[f'{pfx}.{u1}.bias'], stride=2, padding=1)
+    y = F.conv_transpose2d(x, _q(sd[f'{pfx}.{u1}.weight']), None if bn else sd[f'{pfx}.{u1}.bias'], stride=2, padding=1)
     if bn:
         y = _bn(y, sd, f'{pfx}.{ub1}')
-    y = _drop(F.relu(y), drop, f'b{i}.up1')
+    y = _q(_drop(_act(y, 0.0, f'b{i}.up1'), drop, f'b{i}.up1'))
     acts[f'u{i}'] = y
-    y = F.conv2d(_rpad(y), sd[f'{pfx}.{u2}.weight'], None if bn else sd[f'{pfx}.{u2}.bias'])
+    y = F.conv2d(_rpad(y), _q(sd[f'{pfx}.{u2}.weight']), None if bn else sd[f'{pfx}.{u2}.bias'])
     if bn:
         y = _bn(y, sd, f'{pfx}.{ub2}')
-    y = _drop(F.relu(y), drop, f'b{i}.up2')
+    y = _q(_drop(_act(y, 0.0, f'b{i}.up2'), drop, f'b{i}.up2'))
     acts[f'y{i}'] = y
     return y
 
@@ -73,17 +98,28 @@ def _block(x, sd, pfx, i, num_down, drop, acts):
     return torch.cat([x, y], 1)
 
 
-def unet_forward(sd, x, num_down=5, drop=None, prefix='', return_acts=False):
-    """sd: state_dict of the reference ``Unet`` (keys relative to ``prefix``).  Returns pre-tanh output."""
+def unet_forward(sd, x, num_down=5, drop=None, prefix='', return_acts=False, q16=False, gates=None):
+    """sd: state_dict of the reference ``Unet`` (keys relative to ``prefix``).  Returns pre-tanh output.
+    q16=True emulates the engine's fp16 storage of weights/activations (see _Q)."""
+    _Q.on = bool(q16)
+    _Q.gates = gates
+    try:
+        return _unet_forward(sd, x, num_down, drop, prefix, return_acts)
+    finally:
+        _Q.on = False
+        _Q.gates = None
+
+
+def _unet_forward(sd, x, num_down, drop, prefix, return_acts):
     if prefix:
         sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     acts = {}
-    y = F.conv2d(_rpad(x), sd['in_layer.0.net.1.weight'], None)
+    y = F.conv2d(_rpad(_q(x)), _q(sd['in_layer.0.net.1.weight']), None)
     y = _bn(y, sd, 'in_layer.1')
-    y = _drop(F.leaky_relu(y, 0.2), drop, 'in')
+    y = _q(_drop(_act(y, 0.2, 'in'), drop, 'in'))
     acts['x0'] = y
     y = _block(y, sd, 'unet_block', 0, num_down, drop, acts)
-    y = F.conv2d(_rpad(y), sd['out_layer.0.net.1.weight'], sd['out_layer.0.net.1.bias'])
+    y = F.conv2d(_rpad(y), _q(sd['out_layer.0.net.1.weight']), sd['out_layer.0.net.1.bias'])
     if return_acts:
         return y, acts
     return y

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ drop, float slope,
-                                  __half* __restrict__ act, int N, int H, int W, int C) {
+                                  __half* __restrict__ act, __nv_bfloat16* __restrict__ act_b, int N, int H, int W, int C) {
     const int vpp = C >> 3;
     const int64_t total = (int64_t)N * H * W * vpp;
     const int Hp = H + 2, Wp = W + 2;
@@ -67,14 +67,17 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
         float v[8] = {r0.x * s0.x + t0.x, r0.y * s0.y + t0.y, r0.z * s0.z + t0.z, r0.w * s0.w + t0.w,
                       r1.x * s1.x + t1.x, r1.y * s1.y + t1.y, r1.z * s1.z + t1.z, r1.w * s1.w + t1.w};
         __align__(16) __half o[8];
+        __align__(16) __nv_bfloat16 ob[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             float z = v[e];
             z = z > 0.f ? z : z * slope;
             if (drop) z *= drop[n * C + c + e];
             o[e] = __float2half_rn(z);
+            ob[e] = __float2bfloat16_rn(z);
         }
         const uint4 ov = *(const uint4*)o;
+        const uint4 ovb = *(const uint4*)ob;
         // rows / cols this pixel lands on in the padded tensor
         int rows[3], cols[3], nr = 0, nc = 0;
         rows[nr++] = h + 1;
@@ -84,8 +87,11 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
         if (w == 1) cols[nc++] = 0;
         if (w == W - 2) cols[nc++] = W + 1;
         for (int a = 0; a < nr; a++)
-            for (int b = 0; b < nc; b++)
-                *(uint4*)(act + (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * C + c) = ov;
+            for (int b = 0; b < nc; b++) {
+                const int64_t o_ = (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * C + c;
+                *(uint4*)(act + o_) = ov;
+                if (act_b) *(uint4*)(act_b + o_) = ovb;
+            }
     }
 }
 
@@ -251,11 +257,11 @@ extern "C" int rnr_bn_finalize(const float* partials, int T, int ld, int C, doub
 }
 
 extern "C" int rnr_bn_act_fwd(const float* raw, const float* scale, const float* shift, const float* drop, float slope,
-                              void* act, int N, int H, int W, int C, void* stream) {
+                              void* act, void* act_bf16, int N, int H, int W, int C, void* stream) {
     RNR_REQUIRE(C % 8 == 0, "rnr_bn_act_fwd: C=%d must be a multiple of 8", C);
     RNR_REQUIRE(H >= 2 && W >= 2, "rnr_bn_act_fwd: reflect halo needs H,W >= 2");
     const int64_t total = (int64_t)N * H * W * (C / 8);
-    bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(raw, scale, shift, drop, slope, (__half*)act, N, H, W, C);
+    bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(raw, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -58,12 +58,13 @@ struct rnr_wgrad_plan {
     // tcgen05 path
     CUtensorMap tmap_a[RNR_MAX_VIEWS];
     CUtensorMap tmap_g[4];
-    int th, tw;
-    int smem_bytes, grid;
+    int th, tw, tiles_y, tiles_x;
+    int smem_bytes, grid, stages;
     int n_work;          // tc work items
-    int* d_work_tab;
+    int* d_work_tab;     // [n_work, 8]
 };
 
+int rnr_encode_view_map(CUtensorMap* map, const rnr_view_t& v, int dtype, int box_c, int box_x, int box_y);
 int rnr_conv_tc_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* prob);
 int rnr_conv_tc_run(const rnr_conv_plan* plan, cudaStream_t stream);
 int rnr_wgrad_tc_prepare(rnr_wgrad_plan* plan, const rnr_wgrad_problem_t* prob);

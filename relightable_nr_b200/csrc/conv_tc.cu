@@ -12,6 +12,7 @@
 // expressed by the host-built k-step table, so the same kernel serves Conv2d 3x3/s1, 4x4/s2
 // (parity views), ConvTranspose2d 4x4/s2 (4 parity sub-problems) and all of their data gradients.
 #include "conv_internal.cuh"
+#include "tc_ptx.cuh"
 #include <cudaTypedefs.h>
 
 namespace {
@@ -23,125 +24,6 @@ struct TcMaps {
     CUtensorMap a[RNR_MAX_VIEWS];
     CUtensorMap b;
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand descriptor for a [rows x bk] 16-bit tile written by a TMA box with inner extent bk
-// (swizzle span == bk*2 bytes).  8-row groups are 8*bk*2 bytes apart (SBO); LBO unused for swizzled K-major.
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, int bk) {
-    const uint32_t sbo = (uint32_t)(8 * bk * 2);
-    const uint64_t layout = bk == 64 ? 2ull : (bk == 32 ? 4ull : 6ull);   // SWIZZLE_128B / 64B / 32B
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;                       // LBO (ignored)
-    d |= (uint64_t)(sbo >> 4) << 32;
-    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= layout << 61;
-    return d;
-}
-
-__device__ __forceinline__ uint32_t make_idesc(int m, int n, int ab_dtype, int a_mn_major, int b_mn_major) {
-    uint32_t d = 0;
-    d |= 1u << 4;                                 // D format: fp32
-    const uint32_t fmt = ab_dtype == RNR_BF16 ? 1u : 0u;
-    d |= fmt << 7;                                // A format
-    d |= fmt << 10;                               // B format
-    d |= (uint32_t)a_mn_major << 15;
-    d |= (uint32_t)b_mn_major << 16;
-    d |= (uint32_t)(n >> 3) << 17;
-    d |= (uint32_t)(m >> 4) << 24;
-    return d;
-}
-
-// reduce-scatter of 16 per-row values over the 32 lanes of a warp: afterwards v[0] is the sum over
-// all 32 rows of column col16(lane) (each column is held by the lane pair (l, l^1)).
-__device__ __forceinline__ float colsum16(float* v, int lane) {
-#pragma unroll
-    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-        const bool hi = lane & bit;
-#pragma unroll
-        for (int j = 0; j < half; j++) {
-            const float keep = hi ? v[j + half] : v[j];
-            const float send = hi ? v[j] : v[j + half];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-        }
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-__device__ __forceinline__ int col16_of_lane(int lane) {
-    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
@@ -205,7 +87,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const ConvParams p, int bn, 
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, bn, p.ab_dtype, 0, 0);
+            const uint32_t idesc = make_idesc(128, bn, p.ab_dtype, p.ab_dtype, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;

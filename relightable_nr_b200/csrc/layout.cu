@@ -10,7 +10,7 @@ constexpr int TP = 32;   // pixels per tile (along w)
 
 // NCHW fp32 -> fp16 [N,H+2,W+2,Cpad] with reflect halo, channels >= C zero-filled
 __global__ void __launch_bounds__(256) pack_nchw_to_act_kernel(const float* __restrict__ src, __half* __restrict__ act,
-                                                             int N, int C, int Cpad, int H, int W) {
+                                                             __nv_bfloat16* __restrict__ act_b, int N, int C, int Cpad, int H, int W) {
     extern __shared__ float tile[];   // [Cpad][TP+1]
     const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -31,15 +31,23 @@ __global__ void __launch_bounds__(256) pack_nchw_to_act_kernel(const float* __re
         const int w = w0 + px;
         if (w >= W) continue;
         __align__(16) __half o[8];
+        __align__(16) __nv_bfloat16 ob[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = __float2half_rn(tile[(cv * 8 + e) * (TP + 1) + px]);
+        for (int e = 0; e < 8; e++) {
+            const float f = tile[(cv * 8 + e) * (TP + 1) + px];
+            o[e] = __float2half_rn(f);
+            ob[e] = __float2bfloat16_rn(f);
+        }
         int cols[3], nc = 0;
         cols[nc++] = w + 1;
         if (w == 1) cols[nc++] = 0;
         if (w == W - 2) cols[nc++] = W + 1;
         for (int a = 0; a < nr; a++)
-            for (int b = 0; b < nc; b++)
-                *(uint4*)(act + (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * Cpad + cv * 8) = *(const uint4*)o;
+            for (int b = 0; b < nc; b++) {
+                const int64_t o_ = (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * Cpad + cv * 8;
+                *(uint4*)(act + o_) = *(const uint4*)o;
+                if (act_b) *(uint4*)(act_b + o_) = *(const uint4*)ob;
+            }
     }
 }
 
@@ -126,13 +134,13 @@ __global__ void __launch_bounds__(256) fold_to_nchw_kernel(const void* __restric
 
 }  // namespace
 
-extern "C" int rnr_pack_nchw_to_act(const float* src, void* act, int N, int C, int Cpad, int H, int W, void* stream) {
+extern "C" int rnr_pack_nchw_to_act(const float* src, void* act, void* act_bf16, int N, int C, int Cpad, int H, int W, void* stream) {
     RNR_REQUIRE(Cpad % 8 == 0 && Cpad >= C, "rnr_pack_nchw_to_act: bad Cpad=%d", Cpad);
     RNR_REQUIRE(H >= 2 && W >= 2, "rnr_pack_nchw_to_act: reflect halo needs H,W >= 2");
     const size_t smem = (size_t)Cpad * (TP + 1) * sizeof(float);
     RNR_REQUIRE(smem <= 48 * 1024, "rnr_pack_nchw_to_act: too many channels (%d)", Cpad);
     dim3 grid(rnr_cdiv(W, TP), H, N);
-    pack_nchw_to_act_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, (__half*)act, N, C, Cpad, H, W);
+    pack_nchw_to_act_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, (__half*)act, (__nv_bfloat16*)act_bf16, N, C, Cpad, H, W);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,116 @@
+// Spherical-harmonic lighting kernels.
+//   sph_harm.evaluate_sh_basis(lmax=2)   sph_harm.py:41-71  (per-pixel, replaces the CPU/pyshtools round trip
+//                                        of test_rnr.py:322-329 / precompute.py:239)
+//   sph_harm.reconstruct_sh              sph_harm.py:91-102 (basis x coeff inner product; LightingSH.reconstruct_lp
+//                                        network.py:622-627) forward + backward
+//   sph_harm.fit_sh_coeff                sph_harm.py:74-88  (Monte-Carlo projection 4*pi/N * sum samples*basis)
+// The inner products are warp-shuffle reductions (one warp per sample point / per basis row), HBM-bound on the
+// [P, num_basis] basis table.
+#include "pixel.cuh"
+
+namespace {
+
+// real orthonormal SH, no Condon-Shortley phase, order (l, m=-l..l), m<0 <-> sin(|m| phi)   
+__global__ void __launch_bounds__(256) sh_basis_l2_kernel(const float* __restrict__ dirs, float* __restrict__ out, int64_t P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float x = dirs[i * 3 + 0], y = dirs[i * 3 + 1], z = dirs[i * 3 + 2];
+    const float r = sqrtf(x * x + y * y + z * z);
+    if (r > 0.f) { x /= r; y /= r; z /= r; } else { x = 1.f; y = 0.f; z = 0.f; }   // atan2(0,0)=0 -> azimuth 0, colatitude 90
+    float* o = out + i * 9;
+    o[0] = 0.28209479177387814f;
+    o[1] = 0.4886025119029199f * y;
+    o[2] = 0.4886025119029199f * z;
+    o[3] = 0.4886025119029199f * x;
+    o[4] = 1.0925484305920792f * x * y;
+    o[5] = 1.0925484305920792f * y * z;
+    o[6] = 0.31539156525252005f * (3.f * z * z - 1.f);
+    o[7] = 1.0925484305920792f * x * z;
+    o[8] = 0.5462742152960396f * (x * x - y * y);
+}
+
+// out[l, p, c] = sum_b basis[p, b] * coeff[l, b, c]        one warp per (l, p)
+__global__ void __launch_bounds__(256) sh_reconstruct_kernel(const float* __restrict__ basis, const float* __restrict__ coeff,
+                                                           float* __restrict__ out, int64_t P, int B, int Cc, int Lc) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= P * Lc) return;
+    const int l = (int)(wid / P);
+    const int64_t pp = wid % P;
+    const float* brow = basis + pp * B;
+    const float* cf = coeff + (int64_t)l * B * Cc;
+    for (int c0 = 0; c0 < Cc; c0 += 4) {
+        float a[4] = {0, 0, 0, 0};
+        for (int b = lane; b < B; b += 32) {
+            const float bv = brow[b];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c0 + c < Cc) a[c] += bv * cf[b * Cc + c0 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[c] += __shfl_xor_sync(0xffffffffu, a[c], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c0 + c < Cc) out[((int64_t)l * P + pp) * Cc + c0 + c] = a[c];
+        }
+    }
+}
+
+// res[l, b, c] += scale * sum_p basis[p, b] * v[l, p, c]     (backward of reconstruct, and fit_sh_coeff)
+// block = 128 threads (one basis function each, looping if B > 128) x a chunk of points
+__global__ void __launch_bounds__(128) sh_project_kernel(const float* __restrict__ basis, const float* __restrict__ v,
+                                                       float* __restrict__ res, int64_t P, int B, int Cc, int Lc, float scale,
+                                                       int chunk) {
+    extern __shared__ float s_v[];    // [chunk][Cc]
+    const int l = blockIdx.y;
+    const int64_t p0 = (int64_t)blockIdx.x * chunk;
+    const int64_t np = (P - p0) < chunk ? (P - p0) : chunk;
+    for (int64_t i = threadIdx.x; i < np * Cc; i += 128) s_v[i] = v[((int64_t)l * P + p0) * Cc + i];
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += 128) {
+        for (int c0 = 0; c0 < Cc; c0 += 4) {
+            float a[4] = {0, 0, 0, 0};
+            for (int64_t i = 0; i < np; i++) {
+                const float bv = basis[(p0 + i) * B + b];
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c0 + c < Cc) a[c] += bv * s_v[i * Cc + c0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c0 + c < Cc) atomicAdd(res + ((int64_t)l * B + b) * Cc + c0 + c, a[c] * scale);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int rnr_sh_basis_l2(const float* dirs, float* out, int64_t P, void* stream) {
+    if (P == 0) return 0;
+    sh_basis_l2_kernel<<<rnr_cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(dirs, out, P);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_sh_reconstruct(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int Lc,
+                                  void* stream) {
+    if (P * Lc == 0) return 0;
+    sh_reconstruct_kernel<<<rnr_cdiv(P * Lc * 32, 256), 256, 0, (cudaStream_t)stream>>>(basis, coeff, out, P, B, Cc, Lc);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_sh_project(const float* basis, const float* v, float* res, int64_t P, int B, int Cc, int Lc, float scale,
+                              void* stream) {
+    if (P * Lc == 0) return 0;
+    int chunk = 256;
+    RNR_REQUIRE((size_t)chunk * Cc * 4 <= 48 * 1024, "sh_project: too many channels (%d)", Cc);
+    dim3 grid(rnr_cdiv(P, chunk), Lc);
+    sh_project_kernel<<<grid, 128, (size_t)chunk * Cc * 4, (cudaStream_t)stream>>>(basis, v, res, P, B, Cc, Lc, scale, chunk);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,228 @@
+// Neural-texture sampling: network.TextureMapper.forward (network.py:67-91) on top of
+// misc.interpolate_bilinear (misc.py:5-42), forward and backward (texture gradients only -- uv_map
+// and sh_basis_map are data, SURVEY.md 8a "Gradient flow"), plus the generic bilinear gather used by
+// network.Interpolater (network.py:322-337) and TextureMapper.flatten_mipmap (network.py:93-99).
+//
+// HBM-bound: per pixel 44 B in (uv + sh basis), 4*C B out; the 4 mip levels (33 MB total for
+// C=24) stay L2-resident.  One thread per pixel, float4 texel reads (textures are channels-last).
+#include "pixel.cuh"
+
+#define RNR_MAX_LEVELS 8
+
+struct TexLevels {
+    const float* tex[RNR_MAX_LEVELS];
+    float* gtex[RNR_MAX_LEVELS];
+    int size[RNR_MAX_LEVELS];
+    int n;
+};
+
+namespace {
+
+template <int CMAX>
+__global__ void __launch_bounds__(128) texmap_fwd_kernel(const TexLevels lv, int C, const float* __restrict__ uv,
+                                                       const float* __restrict__ sh, int sh_start,
+                                                       float* __restrict__ out, int64_t HW, int N) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW * N) return;
+    const int n = (int)(pix / HW);
+    const int64_t p = pix % HW;
+    const float u = uv[pix * 2 + 0], v = uv[pix * 2 + 1];
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) acc[c] = 0.f;
+    for (int l = 0; l < lv.n; l++) {
+        const int S = lv.size[l];
+        const float x = u * (float)(S - 1);
+        const float y = (float)(S - 1) - v * (float)(S - 1);
+        const Bilin b = bilinear_setup(x, y, S, S);
+        const float* T = lv.tex[l];
+        const float* t00 = T + (int64_t)b.i00 * C;
+        const float* t10 = T + (int64_t)b.i10 * C;
+        const float* t01 = T + (int64_t)b.i01 * C;
+        const float* t11 = T + (int64_t)b.i11 * C;
+        if ((C & 3) == 0) {
+#pragma unroll
+            for (int c = 0; c < CMAX; c += 4) {
+                if (c < C) {
+                    const float4 a = *(const float4*)(t00 + c), bb = *(const float4*)(t10 + c);
+                    const float4 cc = *(const float4*)(t01 + c), d = *(const float4*)(t11 + c);
+                    acc[c + 0] += a.x * b.w00 + bb.x * b.w10 + cc.x * b.w01 + d.x * b.w11;
+                    acc[c + 1] += a.y * b.w00 + bb.y * b.w10 + cc.y * b.w01 + d.y * b.w11;
+                    acc[c + 2] += a.z * b.w00 + bb.z * b.w10 + cc.z * b.w01 + d.z * b.w11;
+                    acc[c + 3] += a.w * b.w00 + bb.w * b.w10 + cc.w * b.w01 + d.w * b.w11;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CMAX; c++)
+                if (c < C) acc[c] += t00[c] * b.w00 + t10[c] * b.w10 + t01[c] * b.w01 + t11[c] * b.w11;
+        }
+    }
+    if (sh) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const float s = sh[pix * 9 + k];
+#pragma unroll
+            for (int c = 0; c < CMAX; c++)
+                if (c == sh_start + k) acc[c] *= s;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; c++)
+        if (c < C) out[((int64_t)n * C + c) * HW + p] = acc[c];
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(128) texmap_bwd_kernel(const TexLevels lv, int C, const float* __restrict__ uv,
+                                                       const float* __restrict__ sh, int sh_start,
+                                                       const float* __restrict__ gout, int64_t HW, int N) {
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW * N) return;
+    const int n = (int)(pix / HW);
+    const int64_t p = pix % HW;
+    const float u = uv[pix * 2 + 0], v = uv[pix * 2 + 1];
+    float g[CMAX];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) {
+        g[c] = (c < C) ? gout[((int64_t)n * C + c) * HW + p] : 0.f;
+    }
+    if (sh) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const float s = sh[pix * 9 + k];
+#pragma unroll
+            for (int c = 0; c < CMAX; c++)
+                if (c == sh_start + k) g[c] *= s;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) any |= (g[c] != 0.f);
+    if (!any) return;      // masked-out pixels contribute exact zeros: skip the atomics
+    for (int l = 0; l < lv.n; l++) {
+        const int S = lv.size[l];
+        const float x = u * (float)(S - 1);
+        const float y = (float)(S - 1) - v * (float)(S - 1);
+        const Bilin b = bilinear_setup(x, y, S, S);
+        float* T = lv.gtex[l];
+        if (!T) continue;
+        const int idx[4] = {b.i00, b.i10, b.i01, b.i11};
+        const float w[4] = {b.w00, b.w10, b.w01, b.w11};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            if (w[t] == 0.f) continue;
+            float* dst = T + (int64_t)idx[t] * C;
+            if ((C & 3) == 0) {
+#pragma unroll
+                for (int c = 0; c < CMAX; c += 4)
+                    if (c < C) atomicAdd((float4*)(dst + c), make_float4(g[c] * w[t], g[c + 1] * w[t], g[c + 2] * w[t], g[c + 3] * w[t]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < CMAX; c++)
+                    if (c < C) atomicAdd(dst + c, g[c] * w[t]);
+            }
+        }
+    }
+}
+
+// generic gather: data [Nd(1 or N), Hd, Wd, C]; x,y [N, M]; out [N, M, C]
+__global__ void __launch_bounds__(256) bilinear_fwd_kernel(const float* __restrict__ data, int Nd, int Hd, int Wd, int C,
+                                                         const float* __restrict__ xs, const float* __restrict__ ys,
+                                                         float* __restrict__ out, int64_t M, int N) {
+    const int64_t total = (int64_t)N * M * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t pt = i / C;
+        const int n = (int)(pt / M);
+        const Bilin b = bilinear_setup(xs[pt], ys[pt], Wd, Hd);
+        const float* D = data + (Nd == 1 ? 0 : (int64_t)n * Hd * Wd * C);
+        out[i] = D[(int64_t)b.i00 * C + c] * b.w00 + D[(int64_t)b.i10 * C + c] * b.w10 + D[(int64_t)b.i01 * C + c] * b.w01 +
+                 D[(int64_t)b.i11 * C + c] * b.w11;
+    }
+}
+
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(float* __restrict__ gdata, int Nd, int Hd, int Wd, int C,
+                                                         const float* __restrict__ xs, const float* __restrict__ ys,
+                                                         const float* __restrict__ gout, int64_t M, int N) {
+    const int64_t total = (int64_t)N * M * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t pt = i / C;
+        const int n = (int)(pt / M);
+        const float g = gout[i];
+        if (g == 0.f) continue;
+        const Bilin b = bilinear_setup(xs[pt], ys[pt], Wd, Hd);
+        float* D = gdata + (Nd == 1 ? 0 : (int64_t)n * Hd * Wd * C);
+        if (b.w00 != 0.f) atomicAdd(D + (int64_t)b.i00 * C + c, g * b.w00);
+        if (b.w10 != 0.f) atomicAdd(D + (int64_t)b.i10 * C + c, g * b.w10);
+        if (b.w01 != 0.f) atomicAdd(D + (int64_t)b.i01 * C + c, g * b.w01);
+        if (b.w11 != 0.f) atomicAdd(D + (int64_t)b.i11 * C + c, g * b.w11);
+    }
+}
+
+}  // namespace
+
+static int fill_levels(TexLevels& lv, const float* const* tex, float* const* gtex, const int* sizes, int L) {
+    RNR_REQUIRE(L >= 1 && L <= RNR_MAX_LEVELS, "texture mapper: 1..%d mip levels supported, got %d", RNR_MAX_LEVELS, L);
+    memset(&lv, 0, sizeof(lv));
+    lv.n = L;
+    for (int i = 0; i < L; i++) {
+        lv.tex[i] = tex ? tex[i] : nullptr;
+        lv.gtex[i] = gtex ? gtex[i] : nullptr;
+        lv.size[i] = sizes[i];
+    }
+    return 0;
+}
+
+extern "C" int rnr_texmap_fwd(const float* const* tex, const int* sizes, int L, int C, const float* uv, const float* sh,
+                              int sh_start, float* out_nchw, int N, int H, int W, void* stream) {
+    TexLevels lv;
+    int rc = fill_levels(lv, tex, nullptr, sizes, L);
+    if (rc) return rc;
+    RNR_REQUIRE(C >= 1 && C <= 32, "texture mapper: 1..32 channels supported, got %d", C);
+    RNR_REQUIRE(!sh || (sh_start >= 0 && sh_start + 9 <= C), "texture mapper: SH channels [%d,%d) exceed C=%d", sh_start, sh_start + 9, C);
+    const int64_t HW = (int64_t)H * W;
+    const int blocks = rnr_cdiv(HW * N, 128);
+    if (C <= 16) texmap_fwd_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, out_nchw, HW, N);
+    else texmap_fwd_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, out_nchw, HW, N);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_texmap_bwd(float* const* gtex, const int* sizes, int L, int C, const float* uv, const float* sh,
+                              int sh_start, const float* gout_nchw, int N, int H, int W, void* stream) {
+    TexLevels lv;
+    int rc = fill_levels(lv, nullptr, gtex, sizes, L);
+    if (rc) return rc;
+    RNR_REQUIRE(C >= 1 && C <= 32, "texture mapper: 1..32 channels supported, got %d", C);
+    const int64_t HW = (int64_t)H * W;
+    const int blocks = rnr_cdiv(HW * N, 128);
+    if (C <= 16) texmap_bwd_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, HW, N);
+    else texmap_bwd_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, HW, N);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bilinear_fwd(const float* data, int Nd, int Hd, int Wd, int C, const float* xs, const float* ys,
+                                float* out, int64_t M, int N, void* stream) {
+    RNR_REQUIRE(Nd == 1 || Nd == N, "interpolate: data batch must be 1 or N");
+    const int64_t total = (int64_t)N * M * C;
+    if (total == 0) return 0;
+    int blocks = rnr_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    bilinear_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(data, Nd, Hd, Wd, C, xs, ys, out, M, N);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bilinear_bwd(float* gdata, int Nd, int Hd, int Wd, int C, const float* xs, const float* ys,
+                                const float* gout, int64_t M, int N, void* stream) {
+    RNR_REQUIRE(Nd == 1 || Nd == N, "interpolate: data batch must be 1 or N");
+    const int64_t total = (int64_t)N * M * C;
+    if (total == 0) return 0;
+    int blocks = rnr_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    bilinear_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gdata, Nd, Hd, Wd, C, xs, ys, gout, M, N);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,13 +1,225 @@
-// tcgen05 weight-gradient kernel (MN-major operands).  See DESIGN.md "wgrad".
+// tcgen05 weight-gradient kernel.
+//
+//   dW[co, ci0+ci] (+tap offset) += sum over pixels  G[pix, co] * A[pix + tap, c0 + ci]
+//
+// As a GEMM:  D[M = co (128), N = ci (<=128)]  +=  G^T [M x K]  *  A [K x N],   K = pixels.
+// Both operands are "MN-major": the contiguous memory dimension (channels) is the M resp. N dimension,
+// so the tiles are used exactly as TMA writes them ([pixel rows x 64 channels], 128-byte rows, SWIZZLE_128B)
+// with MN-major UMMA descriptors -- no transposition pass.  G is bf16 and A is fp16: kind::f16 takes the
+// two formats independently in the instruction descriptor.
+//
+// Work item = (tap entry, co block of 128, ci chunk of <=128, pixel range); one persistent CTA per SM
+// walks its items; partial sums leave TMEM through fp32 red.global.add (dW is pre-zeroed by the caller).
+// Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue; two 128-column accumulators so the epilogue of item i overlaps item i+1.
 #include "conv_internal.cuh"
+#include "tc_ptx.cuh"
+#include <vector>
 
-int rnr_wgrad_tc_prepare(rnr_wgrad_plan* plan, const rnr_wgrad_problem_t* prob) {
-    (void)plan; (void)prob;
-    rnr_set_error("rnr_wgrad: tcgen05 implementation not available in this build");
-    return (int)cudaErrorNotSupported;
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBoxBytes = 128 * 64 * 2;     // one [128 pixels x 64 channels] 16-bit box
+constexpr int kStageBytes = 4 * kBoxBytes;  // 2 G boxes (co 0..127) + 2 A boxes (ci 0..127)
+constexpr int kStages = 3;
+
+struct WMaps {
+    CUtensorMap a[RNR_MAX_VIEWS];
+    CUtensorMap g[4];
+};
+
+struct WorkItem {          // 8 ints
+    int tap, co0, ci_off, n_ci_box, ci_valid, patch_begin, patch_end, pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const WorkItem* __restrict__ work, int n_work,
+                int th, int tw, int tiles_y, int tiles_x) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* aux = smem + (size_t)kStages * kStageBytes;
+    uint64_t* full_bar = (uint64_t*)aux;
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int v = 0; v < RNR_MAX_VIEWS; v++)
+            if (p.aviews[v].ptr) tma_prefetch_desc(&maps.a[v]);
+        for (int v = 0; v < 4; v++)
+            if (p.gviews[v].ptr) tma_prefetch_desc(&maps.g[v]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const WorkItem wi = work[w];
+                const rnr_wtap_t tap = p.taps[wi.tap];
+                for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
+                    const int tx_ = pt % tiles_x, ty_ = (pt / tiles_x) % tiles_y, n_ = pt / (tiles_x * tiles_y);
+                    const int x0 = tx_ * tw, y0 = ty_ * th;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * kStageBytes;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + wi.n_ci_box) * kBoxBytes));
+                    tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st, wi.co0, x0, y0, n_);
+                    tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st + kBoxBytes, wi.co0 + 64, x0, y0, n_);
+                    for (int b = 0; b < wi.n_ci_box; b++)
+                        tma_load_4d(&maps.a[tap.view], &full_bar[stage], st + (size_t)(2 + b) * kBoxBytes,
+                                    tap.c0 + wi.ci_off + 64 * b, x0 + tap.dx, y0 + tap.dy, n_);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
+                const WorkItem wi = work[w];
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                const uint32_t idesc = make_idesc(128, wi.n_ci_box * 64, p.g_dtype, p.a_dtype, 1, 1);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+                bool first = true;
+                for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + (size_t)stage * kStageBytes);
+                    const uint64_t dg = make_mnmajor_desc(sbase, kBoxBytes);
+                    const uint64_t da = make_mnmajor_desc(sbase + 2 * kBoxBytes, kBoxBytes);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {     // 128 pixels = 8 MMAs of K=16 (2 KB of rows each)
+                        umma_f16(d_tmem, dg + (uint64_t)(k * (2048 >> 4)), da + (uint64_t)(k * (2048 >> 4)), idesc, first ? 0u : 1u);
+                        first = false;
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
+            const WorkItem wi = work[w];
+            const rnr_wtap_t tap = p.taps[wi.tap];
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int co = wi.co0 + row;
+            float* dst = p.dw + (int64_t)co * p.s_co + (int64_t)(tap.ci0 + wi.ci_off) * p.s_ci + tap.off;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
+            const int ncols = wi.n_ci_box * 64;
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                uint32_t rv[16];
+                tmem_ld16(taddr + (uint32_t)c0, rv);
+                tmem_ld_wait();
+                if (co < p.cout) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++)
+                        if (c0 + e < wi.ci_valid) atomicAdd(dst + (int64_t)(c0 + e) * p.s_ci, __uint_as_float(rv[e]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
 }
-int rnr_wgrad_tc_run(const rnr_wgrad_plan* plan, cudaStream_t stream) {
-    (void)plan; (void)stream;
-    rnr_set_error("rnr_wgrad: tcgen05 implementation not available in this build");
-    return (int)cudaErrorNotSupported;
+
+}  // namespace
+
+int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
+    RNR_REQUIRE((prob->a_dtype == RNR_F16 || prob->a_dtype == RNR_BF16) && (prob->g_dtype == RNR_F16 || prob->g_dtype == RNR_BF16),
+                "wgrad_tc: operands must be 16-bit");
+    // pixel patches
+    int tw = 16;
+    while (tw > 1 && tw / 2 >= prob->mX) tw /= 2;
+    const int th = 128 / tw;
+    pl->tw = tw; pl->th = th;
+    pl->tiles_y = rnr_cdiv(prob->mY, th);
+    pl->tiles_x = rnr_cdiv(prob->mX, tw);
+    const int n_patches = prob->mN * pl->tiles_y * pl->tiles_x;
+    for (int i = 0; i < prob->n_aviews; i++) {
+        int rc = rnr_encode_view_map(&pl->tmap_a[i], prob->aviews[i], prob->a_dtype, 64, tw, th);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < prob->n_gviews; i++) {
+        int rc = rnr_encode_view_map(&pl->tmap_g[i], prob->gviews[i], prob->g_dtype, 64, tw, th);
+        if (rc) return rc;
+    }
+    // output tiles
+    struct OT { int tap, co0, ci_off, nbox, valid; };
+    std::vector<OT> tiles;
+    for (int t = 0; t < prob->n_taps; t++) {
+        const rnr_wtap_t& tp = prob->taps[t];
+        for (int co0 = 0; co0 < prob->cout; co0 += 128)
+            for (int ci = 0; ci < tp.nci; ci += 128) {
+                const int rem = tp.nci - ci;
+                OT o = {t, co0, ci, rem > 64 ? 2 : 1, rem > 128 ? 128 : rem};
+                tiles.push_back(o);
+            }
+    }
+    int splits = (int)((148 * 2 + (int)tiles.size() - 1) / (int)tiles.size());
+    if (splits > n_patches) splits = n_patches;
+    if (splits < 1) splits = 1;
+    const int per = rnr_cdiv(n_patches, splits);
+    std::vector<WorkItem> work;
+    for (int s = 0; s < splits; s++) {
+        const int pb = s * per, pe = (pb + per < n_patches) ? pb + per : n_patches;
+        if (pb >= pe) continue;
+        for (const OT& o : tiles) {
+            WorkItem w = {o.tap, o.co0, o.ci_off, o.nbox, o.valid, pb, pe, 0};
+            work.push_back(w);
+        }
+    }
+    pl->n_work = (int)work.size();
+    RNR_CHECK(cudaMalloc(&pl->d_work_tab, work.size() * sizeof(WorkItem)));
+    RNR_CHECK(cudaMemcpy(pl->d_work_tab, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    pl->smem_bytes = kStages * kStageBytes + 256 + 1024;
+    pl->grid = pl->n_work < 148 ? pl->n_work : 148;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RNR_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    return 0;
+}
+
+int rnr_wgrad_tc_run(const rnr_wgrad_plan* pl, cudaStream_t stream) {
+    WMaps maps;
+    memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
+    memcpy(maps.g, pl->tmap_g, sizeof(maps.g));
+    wgrad_tc_kernel<<<pl->grid, kThreads, pl->smem_bytes, stream>>>(maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
+                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x);
+    RNR_LAUNCH_CHECK();
+    return 0;
 }

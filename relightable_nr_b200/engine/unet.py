@@ -201,6 +201,11 @@ class UNetEngine:
         self.consumers: Dict[str, List[Tuple[str, int]]] = {}   # act name -> [(layer name, source index)]
         s0 = self.specs[0]
         self.acts['input'] = HaloTensor(N, s0.H, s0.W, self.in_cpad, adt, dev, zero=True)
+        # bf16 copies of the activations: B operand of the weight-gradient MMA (same format as the gradients)
+        self.acts_w: Dict[str, HaloTensor] = {}
+        self.dual = self.need_backward and self.act_dt != self.grad_dt
+        if self.dual:
+            self.acts_w['input'] = HaloTensor(N, s0.H, s0.W, self.in_cpad, gdt, dev, zero=True)
         self.ones = {}
         self.zeros = {}
         grad_numel = 0
@@ -218,6 +223,8 @@ class UNetEngine:
             else:
                 st.raw = self._alloc((N, Ho, Wo, sp.cout), torch.float32)
                 self.acts[sp.dst] = HaloTensor(N, Ho, Wo, sp.cout, adt, dev, zero=True)
+                if self.dual:
+                    self.acts_w[sp.dst] = HaloTensor(N, Ho, Wo, sp.cout, gdt, dev, zero=True)
                 for nm in ('mean', 'invstd', 'scale', 'shift', 'c1', 'c2'):
                     setattr(st, nm, self._alloc((sp.cout,), torch.float32, zero=True))
                 st.invstd.fill_(1.0)
@@ -382,10 +389,23 @@ class UNetEngine:
         # ------------------------------ weight gradient ------------------------------
         G = self.gz[sp.name]
         wp = WgradProblem()
-        for i, v in enumerate(views):
+        if self.dual:
+            wsrcs = [self.acts_w[s] for s in sp.src]
+            if sp.kind == 'c3':
+                wviews = [t.padded() for t in wsrcs]
+            elif sp.kind == 'c4s2':
+                wviews = []
+                for t in wsrcs:
+                    wviews += [t.parity(p, q) for p in range(2) for q in range(2)]
+            else:
+                wviews = [t.interior() for t in wsrcs]
+            w_dt = self.grad_dt
+        else:
+            wviews, w_dt = views, self.act_dt
+        for i, v in enumerate(wviews):
             wp.aviews[i] = v
-        wp.n_aviews = len(views)
-        wp.a_dtype, wp.g_dtype = self.act_dt, self.grad_dt
+        wp.n_aviews = len(wviews)
+        wp.a_dtype, wp.g_dtype = w_dt, self.grad_dt
         wtaps = []
         if sp.kind == 'c3':
             wp.gviews[0] = G.interior()
@@ -531,7 +551,8 @@ class UNetEngine:
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
         N, Cc, H, W = x.shape
         assert (N, Cc, H, W) == (self.N, self.in_channels, self.H, self.W), 'engine built for a different input shape'
-        _lib.check(self.L.rnr_pack_nchw_to_act(x.data_ptr(), self.acts['input'].ptr, N, Cc, self.in_cpad, H, W, self._stream()),
+        _lib.check(self.L.rnr_pack_nchw_to_act(x.data_ptr(), self.acts['input'].ptr,
+                                               self.acts_w['input'].ptr if self.dual else None, N, Cc, self.in_cpad, H, W, self._stream()),
                    'rnr_pack_nchw_to_act')
         self.gpu_launches += 1
 
@@ -567,7 +588,8 @@ class UNetEngine:
             st.drop = drop_masks.get(sp.name) if (drop_masks and sp.drop) else None
             _lib.check(L.rnr_bn_act_fwd(st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
                                         st.drop.data_ptr() if st.drop is not None else None, sp.slope,
-                                        self.acts[sp.dst].ptr, N, Ho, Wo, Cc, s), 'rnr_bn_act_fwd')
+                                        self.acts[sp.dst].ptr, self.acts_w[sp.dst].ptr if (self.dual and training) else None,
+                                        N, Ho, Wo, Cc, s), 'rnr_bn_act_fwd')
             self.gpu_launches += 1
         return self.layers['out'].raw
 
@@ -577,6 +599,17 @@ class UNetEngine:
         _lib.check(self.L.rnr_unpack_nhwc_to_nchw(self.layers['out'].raw.data_ptr(), out.data_ptr(), self.N, sp.cout, self.out_ld,
                                                   sp.Ho, sp.Wo, self._stream()), 'rnr_unpack_nhwc_to_nchw')
         self.gpu_launches += 1
+        return out
+
+    def gate_masks(self) -> Dict[str, torch.Tensor]:
+        """(pre-activation > 0) per live layer as NCHW bool tensors -- test hook: lets the oracle differentiate
+        through the same ReLU/LeakyReLU gates as the engine."""
+        out = {}
+        for sp in self.specs[:-1]:
+            st = self.layers[sp.name]
+            shift = st.shift if sp.bn_key is not None else self.params[sp.b_key]
+            z = st.raw * st.scale + shift
+            out[sp.name] = (z > 0).permute(0, 3, 1, 2).contiguous()
         return out
 
     def grad_view(self, key) -> torch.Tensor:

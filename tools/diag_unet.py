@@ -21,30 +21,33 @@ def main():
     in_ch = int(sys.argv[5]) if len(sys.argv) > 5 else 20
     out_ch = int(sys.argv[6]) if len(sys.argv) > 6 else 6
     wimpl = sys.argv[7] if len(sys.argv) > 7 else 'simt'
+    q16 = (sys.argv[8] == 'q16') if len(sys.argv) > 8 else True
     num_down = 5
     sd = make_unet_state_dict(in_ch, out_ch, nf0, num_down=num_down, seed=0)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(N, in_ch, H, H, generator=g)
     R = torch.randn(N, out_ch, H, H, generator=g) / (H * H)
 
+    dev = torch.device('cuda:0')
+    params = {k: v.to(dev).contiguous() for k, v in sd.items() if v.dtype.is_floating_point and 'running' not in k}
+    buffers = {k: v.to(dev).clone() for k, v in sd.items() if 'running' in k}
+    specs = unet_layer_specs(in_ch, out_ch, nf0, num_down, 8 * nf0, H, H)
+    adt = {'fp16': 0, 'bf16': 1}[os.environ.get('RNR_ACT_DTYPE', 'fp16')]
+    eng = UNetEngine(specs, params, buffers, N, in_ch, dev, impl=impl, input_grad_range=(0, in_ch), wgrad_impl=wimpl, act_dtype=adt)
+    eng.set_input_nchw(x.to(dev))
+    eng.forward(training=True)
+    torch.cuda.synchronize()
+    gates = {k: v.cpu() for k, v in eng.gate_masks().items()} if q16 else None
+
     sdg = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k else v) for k, v in sd.items()}
     xg = x.clone().requires_grad_(True)
     t0 = time.time()
-    pre, acts = unet_forward(sdg, xg, num_down=num_down, return_acts=True)
+    pre, acts = unet_forward(sdg, xg, num_down=num_down, return_acts=True, q16=q16, gates=gates)
     for a in acts.values():
         a.retain_grad()
     ref = torch.tanh(pre)
     (ref * R).sum().backward()
     print('oracle fwd+bwd %.2fs' % (time.time() - t0))
-
-    dev = torch.device('cuda:0')
-    params = {k: v.to(dev).contiguous() for k, v in sd.items() if v.dtype.is_floating_point and 'running' not in k}
-    buffers = {k: v.to(dev).clone() for k, v in sd.items() if 'running' in k}
-    specs = unet_layer_specs(in_ch, out_ch, nf0, num_down, 8 * nf0, H, H)
-    eng = UNetEngine(specs, params, buffers, N, in_ch, dev, impl=impl, input_grad_range=(0, in_ch), wgrad_impl=wimpl)
-    eng.set_input_nchw(x.to(dev))
-    eng.forward(training=True)
-    torch.cuda.synchronize()
     print('--- forward activations (engine vs oracle): max-abs / rel-l2')
     for sp in specs[:-1]:
         a = eng.acts[sp.dst].interior_tensor().float().permute(0, 3, 1, 2).cpu()
