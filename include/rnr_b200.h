@@ -188,6 +188,66 @@ int rnr_tanh_bwd_pack(const float* grad_nchw, const float* tanh_nhwc, void* gz, 
 /* folded grad w.r.t. reflect-padded input [N,H+2,W+2,ld] -> NCHW fp32 [N,C,H,W] (channels c0..c0+C) */
 int rnr_fold_to_nchw(const void* gpad, int dtype, float* dst, int N, int C, int c0, int ld, int H, int W, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Neural texture: network.TextureMapper.forward (network.py:67-91), misc.interpolate_bilinear */
+/* (misc.py:5-42), TextureMapper.flatten_mipmap (network.py:93-99), network.Interpolater       */
+/* (network.py:322-337).  tex / gtex / sizes are HOST arrays of L device pointers / sizes.       */
+/*   uv [N,H,W,2], sh [N,H,W,9] or NULL, out / gout NCHW fp32 [N,C,H,W]; textures [S,S,C] fp32.  */
+/* ------------------------------------------------------------------------------------------ */
+int rnr_texmap_fwd(const float* const* tex, const int* sizes, int L, int C, const float* uv, const float* sh,
+                   int sh_start, float* out_nchw, int N, int H, int W, void* stream);
+int rnr_texmap_bwd(float* const* gtex /* accumulated */, const int* sizes, int L, int C, const float* uv, const float* sh,
+                   int sh_start, const float* gout_nchw, int N, int H, int W, void* stream);
+int rnr_flatten_mipmap(const float* const* tex, float* const* gtex, const int* sizes, int L, int C, int c0, int nc,
+                       float* out /* [S0,S0,nc] */, const float* gout, int backward, void* stream);
+/* data [Nd(1|N),Hd,Wd,C]; xs, ys [N,M] -> out [N,M,C]; bwd accumulates into gdata */
+int rnr_bilinear_fwd(const float* data, int Nd, int Hd, int Wd, int C, const float* xs, const float* ys,
+                     float* out, int64_t M, int N, void* stream);
+int rnr_bilinear_bwd(float* gdata, int Nd, int Hd, int Wd, int C, const float* xs, const float* ys,
+                     const float* gout, int64_t M, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Rays: network.RaySampler.forward (network.py:445-472), network.RayRenderer.forward           */
+/* (network.py:481-527) and its backward.  tbn [P,3,3], vdt [P,3], alpha [P], pivots [3,R];      */
+/* rays_dir [P,3,R], rays_uv [P,2,R]; rays_lt / rays_color [N,R,3,H,W]; images NCHW.             */
+/* ------------------------------------------------------------------------------------------ */
+int rnr_ray_sampler_fwd(const float* tbn, const float* vdt, const float* alpha, const float* pivots, int R,
+                        int reflect, float* rays_dir, float* rays_uv, float* rays_dir_tangent, int64_t P, void* stream);
+int rnr_ray_render_fwd(const float* alb_s, const float* alb_d, const float* rays_uv, const float* rays_lt,
+                       const float* lp, int Nl, int Hl, int Wl, int R, int Rd, int no_albedo, int separate,
+                       float* out, float* out_s, float* out_d, float* ltt_s, float* ltt_d, float* rays_color,
+                       int N, int H, int W, void* stream);
+int rnr_ray_render_bwd(const float* alb_s, const float* alb_d, const float* rays_uv, const float* rays_lt,
+                       const float* lp, int Nl, int Hl, int Wl, int R, int Rd, int no_albedo, int separate,
+                       const float* g_out, const float* g_os, const float* g_od, const float* g_ls, const float* g_ld,
+                       const float* ltt_s, const float* ltt_d, float* g_alb_s, float* g_alb_d, float* g_lt,
+                       float* g_lp /* accumulated */, int N, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Spherical harmonics: sph_harm.evaluate_sh_basis(lmax=2) (sph_harm.py:41-71),                 */
+/* sph_harm.reconstruct_sh (:91-102) fwd/bwd, sph_harm.fit_sh_coeff (:74-88)                    */
+/* ------------------------------------------------------------------------------------------ */
+int rnr_sh_basis_l2(const float* dirs /* [P,3] */, float* out /* [P,9] */, int64_t P, void* stream);
+/* out[l,p,c] = sum_b basis[p,b] coeff[l,b,c] */
+int rnr_sh_reconstruct(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int Lc, void* stream);
+/* res[l,b,c] += scale * sum_p basis[p,b] v[l,p,c]   (res pre-zeroed / accumulated) */
+int rnr_sh_project(const float* basis, const float* v, float* res, int64_t P, int B, int Cc, int Lc, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Losses and optimiser: network.RaysLTChromLoss (network.py:395-411), masked cropped L1         */
+/* (train_rnr.py:565-585), torch.optim.Adam step (train_rnr.py:376,622)                          */
+/* ------------------------------------------------------------------------------------------ */
+/* sums[0] += sum(diff), sums[1] += sum(alpha) (double, pre-zeroed); optional full outputs */
+int rnr_chrom_loss_fwd(const float* rays_lt, const float* alpha, const float* img, int R, int N, int H, int W,
+                       float* chrom, float* chrom_mean, float* diff, double* sums, void* stream);
+int rnr_chrom_loss_bwd(const float* rays_lt, const float* alpha, const float* img, int R, int N, int H, int W,
+                       const double* sums, const float* gscale_dev, float gscale, float* g_lt, int accumulate, void* stream);
+/* loss_sum += weight * mean|out*a - gt*a| over the central crop; g_out = d(weight*loss)/d out */
+int rnr_l1_masked(const float* out, const float* gt, const float* alpha, int N, int C, int H, int W, int crop,
+                  float weight, float* g_out, double* loss_sum, void* stream);
+int rnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, int step, float gscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,3 +226,68 @@ extern "C" int rnr_bilinear_bwd(float* gdata, int Nd, int Hd, int Wd, int C, con
     RNR_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// TextureMapper.flatten_mipmap (network.py:93-99): level 0 + F.interpolate(bilinear, align_corners=False)
+// of the coarser levels, channels [c0, c0+nc).  out [1,S0,S0,nc].  Backward scatters into the levels.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void up_coord(int dst, int in, int out, int& i0, int& i1, float& l1) {
+    const float scale = (float)in / (float)out;
+    float src = ((float)dst + 0.5f) * scale - 0.5f;
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(256) flatten_mipmap_kernel(const TexLevels lv, int C, int c0, int nc, float* __restrict__ out,
+                                                           const float* __restrict__ gout, int backward) {
+    const int S0 = lv.size[0];
+    const int64_t total = (int64_t)S0 * S0 * nc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % nc);
+        const int x = (int)((i / nc) % S0), y = (int)(i / ((int64_t)nc * S0));
+        float acc = 0.f;
+        const float g = backward ? gout[i] : 0.f;
+        if (!backward) acc = lv.tex[0][((int64_t)y * S0 + x) * C + c0 + c];
+        else if (lv.gtex[0]) atomicAdd(lv.gtex[0] + ((int64_t)y * S0 + x) * C + c0 + c, g);
+        for (int l = 1; l < lv.n; l++) {
+            const int S = lv.size[l];
+            int y0, y1, x0, x1;
+            float ly, lx;
+            up_coord(y, S, S0, y0, y1, ly);
+            up_coord(x, S, S0, x0, x1, lx);
+            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+            const int64_t o00 = ((int64_t)y0 * S + x0) * C + c0 + c, o01 = ((int64_t)y0 * S + x1) * C + c0 + c;
+            const int64_t o10 = ((int64_t)y1 * S + x0) * C + c0 + c, o11 = ((int64_t)y1 * S + x1) * C + c0 + c;
+            if (!backward) {
+                const float* T = lv.tex[l];
+                acc += w00 * T[o00] + w01 * T[o01] + w10 * T[o10] + w11 * T[o11];
+            } else if (lv.gtex[l]) {
+                float* T = lv.gtex[l];
+                atomicAdd(T + o00, g * w00); atomicAdd(T + o01, g * w01);
+                atomicAdd(T + o10, g * w10); atomicAdd(T + o11, g * w11);
+            }
+        }
+        if (!backward) out[i] = acc;
+    }
+}
+
+}  // namespace
+
+extern "C" int rnr_flatten_mipmap(const float* const* tex, float* const* gtex, const int* sizes, int L, int C, int c0, int nc,
+                                  float* out, const float* gout, int backward, void* stream) {
+    TexLevels lv;
+    int rc = fill_levels(lv, tex, gtex, sizes, L);
+    if (rc) return rc;
+    RNR_REQUIRE(c0 >= 0 && c0 + nc <= C, "flatten_mipmap: channel slice [%d,%d) outside C=%d", c0, c0 + nc, C);
+    const int64_t total = (int64_t)sizes[0] * sizes[0] * nc;
+    int blocks = rnr_cdiv(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    flatten_mipmap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lv, C, c0, nc, out, gout, backward);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
