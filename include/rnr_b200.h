@@ -29,6 +29,7 @@ extern "C" {
 const char* rnr_version(void);
 const char* rnr_last_error(void);          /* text of the last failing call on this thread */
 int  rnr_device_sm_count(int device);
+unsigned long long rnr_launch_count(void); /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------ */
 /* Generic implicit-GEMM convolution problem                                                   */
@@ -224,10 +225,28 @@ int rnr_ray_render_bwd(const float* alb_s, const float* alb_d, const float* rays
                        float* g_lp /* accumulated */, int N, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Per-pixel maps derived from the G-buffer: camera.get_view_dir_map (camera.py:5-32),          */
+/* render.get_TBN_map (render.py:124-168), render.interp_vertex_attr (render.py:11-28)          */
+/* ------------------------------------------------------------------------------------------ */
+/* proj_inv, R_inv [N,3,3] -> view_dir_map [N,H,W,3] (world), optional camera-space map          */
+int rnr_view_dir_map(const float* proj_inv, const float* R_inv, float* out_world, float* out_cam, int N, int H, int W,
+                     void* stream);
+/* faces_v [nf,3,3], faces_vt [nf,3,2] -> normalised per-face tangent [nf,3]; nan_flag[0] |= 1 on NaN */
+int rnr_face_tangents(const float* faces_v, const float* faces_vt, float* tangent, int* nan_flag, int nf, void* stream);
+/* normal_map [P,3], face_index_map [P] (i32, -1 = background) -> TBN [P,3,3] (columns T,B,N)     */
+int rnr_tbn_map(const float* normal_map, const int* face_index_map, const float* tangent, float* tbn, int* nan_flag,
+                int64_t P, int nf, void* stream);
+/* attr [1|N,nv,A], faces [N,nf,3] i32, face_index_map [N,P] i32, weight_map [N,P,3] -> out [N,P,A] */
+int rnr_interp_vertex_attr(const float* attr, int attr_batch, int nv, int A, const int* faces, int nf,
+                           const int* face_index_map, const float* weight_map, float* out, int N, int64_t P, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Spherical harmonics: sph_harm.evaluate_sh_basis(lmax=2) (sph_harm.py:41-71),                 */
 /* sph_harm.reconstruct_sh (:91-102) fwd/bwd, sph_harm.fit_sh_coeff (:74-88)                    */
 /* ------------------------------------------------------------------------------------------ */
 int rnr_sh_basis_l2(const float* dirs /* [P,3] */, float* out /* [P,9] */, int64_t P, void* stream);
+/* general degree, fp64 table [P,(lmax+1)^2] (set-up time: network.py:557,581,696) */
+int rnr_sh_basis(const float* dirs /* [P,3] */, double* out, int64_t P, int lmax, void* stream);
 /* out[l,p,c] = sum_b basis[p,b] coeff[l,b,c] */
 int rnr_sh_reconstruct(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int Lc, void* stream);
 /* res[l,b,c] += scale * sum_p basis[p,b] v[l,p,c]   (res pre-zeroed / accumulated) */

@@ -74,6 +74,8 @@ def lib():
     L.rnr_version.restype = C.c_char_p
     L.rnr_last_error.restype = C.c_char_p
     L.rnr_device_sm_count.argtypes = [i32]
+    L.rnr_launch_count.restype = C.c_ulonglong
+    L.rnr_launch_count.argtypes = []
     sigs = {
         "rnr_conv_plan_create": [C.POINTER(ConvProblem), i32, C.POINTER(vp)],
         "rnr_conv_run": [vp, vp],

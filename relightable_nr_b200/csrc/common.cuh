@@ -10,6 +10,7 @@
 
 // ---- error plumbing -------------------------------------------------------------------------
 void rnr_set_error(const char* fmt, ...);
+void rnr_count_launch(void);          // every kernel launch of the library is counted (rnr_launch_count)
 
 #define RNR_CHECK(expr)                                                                   \
     do {                                                                                  \
@@ -30,6 +31,7 @@ void rnr_set_error(const char* fmt, ...);
 
 #define RNR_LAUNCH_CHECK()                                                                \
     do {                                                                                  \
+        rnr_count_launch();                                                               \
         cudaError_t _e = cudaGetLastError();                                              \
         if (_e != cudaSuccess) {                                                          \
             rnr_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -29,6 +29,41 @@ __global__ void __launch_bounds__(256) sh_basis_l2_kernel(const float* __restric
     o[8] = 0.5462742152960396f * (x * x - y * y);
 }
 
+
+// General-degree basis table (LightingSH.__init__ network.py:557,581; LightingLP.fit_sh :696 call
+// sph_harm.evaluate_sh_basis(lmax=10) once at set-up).  fp64 throughout, one thread per direction; the
+// associated Legendre functions are built per order m by the stable upward recurrence in l, so no
+// per-thread table is needed.  out [P, (lmax+1)^2] double, same (l, m=-l..l) order as the l2 kernel.
+__global__ void __launch_bounds__(128) sh_basis_general_kernel(const float* __restrict__ dirs, double* __restrict__ out,
+                                                             int64_t P, int lmax) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const double x = dirs[i * 3 + 0], y = dirs[i * 3 + 1], z = dirs[i * 3 + 2];
+    const double rxy = sqrt(x * x + y * y);
+    const double r = sqrt(rxy * rxy + z * z);
+    const double ct = r > 0.0 ? z / r : 0.0, st = r > 0.0 ? rxy / r : 1.0;
+    const double phi = atan2(y, x);
+    const int nb = (lmax + 1) * (lmax + 1);
+    double* o = out + i * nb;
+    double pmm = 1.0;                                  // P_m^m without Condon-Shortley phase
+    for (int m = 0; m <= lmax; m++) {
+        if (m > 0) pmm *= (2 * m - 1) * st;
+        const double cm = cos(m * phi), sm = sin(m * phi);
+        double p2 = 0.0, p1 = pmm;                     // P_{l-2}^m, P_{l-1}^m
+        for (int l = m; l <= lmax; l++) {
+            double pl;
+            if (l == m) pl = pmm;
+            else if (l == m + 1) pl = (2 * m + 1) * ct * pmm;
+            else pl = ((2 * l - 1) * ct * p1 - (l + m - 1) * p2) / (l - m);
+            if (l > m) { p2 = p1; p1 = pl; }
+            const double nrm = sqrt((m == 0 ? 1.0 : 2.0) * (2 * l + 1) / (4.0 * 3.14159265358979323846) *
+                                    exp(lgamma((double)(l - m + 1)) - lgamma((double)(l + m + 1))));
+            o[l * l + l + m] = nrm * pl * cm;
+            if (m > 0) o[l * l + l - m] = nrm * pl * sm;
+        }
+    }
+}
+
 // out[l, p, c] = sum_b basis[p, b] * coeff[l, b, c]        one warp per (l, p)
 __global__ void __launch_bounds__(256) sh_reconstruct_kernel(const float* __restrict__ basis, const float* __restrict__ coeff,
                                                            float* __restrict__ out, int64_t P, int B, int Cc, int Lc) {
@@ -92,6 +127,14 @@ __global__ void __launch_bounds__(128) sh_project_kernel(const float* __restrict
 extern "C" int rnr_sh_basis_l2(const float* dirs, float* out, int64_t P, void* stream) {
     if (P == 0) return 0;
     sh_basis_l2_kernel<<<rnr_cdiv(P, 256), 256, 0, (cudaStream_t)stream>>>(dirs, out, P);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_sh_basis(const float* dirs, double* out, int64_t P, int lmax, void* stream) {
+    RNR_REQUIRE(lmax >= 0 && lmax <= 32, "rnr_sh_basis: lmax %d out of range [0, 32]", lmax);
+    if (P == 0) return 0;
+    sh_basis_general_kernel<<<rnr_cdiv(P, 128), 128, 0, (cudaStream_t)stream>>>(dirs, out, P, lmax);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -165,7 +165,8 @@ class _LayerState:
 class UNetEngine:
     def __init__(self, specs: List[LayerSpec], params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor],
                  N: int, in_channels: int, device, impl: str = 'tc', input_grad_range: Optional[Tuple[int, int]] = None,
-                 act_dtype: int = F16, grad_dtype: int = BF16, need_backward: bool = True, wgrad_impl: Optional[str] = None):
+                 act_dtype: int = F16, grad_dtype: int = BF16, need_backward: bool = True, wgrad_impl: Optional[str] = None,
+                 final_tanh: bool = True):
         self.L = _lib.lib()
         self.specs = specs
         self.params = params
@@ -179,9 +180,12 @@ class UNetEngine:
         self.in_cpad = _rup(in_channels, 64) if in_channels > 32 else _rup(in_channels, 16)
         self.input_grad_range = input_grad_range
         self.need_backward = need_backward
+        self.final_tanh = final_tanh
+        self._zeros_out = None
         self.H, self.W = specs[0].H, specs[0].W
         self.keep = []            # keeps ctypes arrays / tensors referenced by plans alive
         self.gpu_launches = 0
+        self.timing = None        # list of (kind, layer, start_event, end_event) when enabled (bench.py roofline leg)
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -306,7 +310,7 @@ class UNetEngine:
         epi = 0
         bias_t = None
         if final:
-            epi = EPI_BIAS | EPI_TANH
+            epi = EPI_BIAS | (EPI_TANH if self.final_tanh else 0)
             bias_t = self.params[sp.b_key]
         elif sp.bn_key is not None:
             epi = EPI_STATS
@@ -532,6 +536,25 @@ class UNetEngine:
     def _stream():
         return torch.cuda.current_stream().cuda_stream
 
+    def _mark(self, kind=None, name=None, start=None):
+        """CUDA-event bracket around a group of launches on the current stream (only when ``self.timing`` is a list)."""
+        if self.timing is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if start is not None:
+            self.timing.append((kind, name, start, ev))
+        return ev
+
+    @staticmethod
+    def layer_flops(sp, N):
+        """2*MAC of one live layer (forward); dgrad and wgrad each cost the same."""
+        cin = sum(sp.cin)
+        if sp.kind == 'ct':
+            return 2.0 * N * sp.H * sp.W * cin * sp.cout * 16
+        k = 3 if sp.kind == 'c3' else 4
+        return 2.0 * N * sp.Ho * sp.Wo * cin * sp.cout * k * k
+
     def _wprep(self, items: List[_WPrep], s):
         for w in items:
             src = self.params[w.src_key]
@@ -557,17 +580,19 @@ class UNetEngine:
         self.gpu_launches += 1
 
     def forward(self, training: bool, drop_masks: Optional[Dict[str, torch.Tensor]] = None, momentum: float = 0.1,
-                eps: float = 1e-5, weights_ready: bool = False):
+                eps: float = 1e-5, weights_ready: bool = False, need_backward_prep: Optional[bool] = None):
         """Runs all layers on the current stream.  ``drop_masks[layer name]`` = [N, C] fp32 scale tensor
         (0 or 1/(1-p)) or None for no dropout.  Returns the final fp32 NHWC tensor [N,H,W,ld] (tanh applied)."""
         L, s = self.L, self._stream()
         if not weights_ready:
-            self.prepare_weights(backward=self.need_backward and training)
+            self.prepare_weights(backward=self.need_backward)
         for sp in self.specs:
             st = self.layers[sp.name]
+            t0 = self._mark()
             for pl in st.fwd_plans:
                 _lib.check(L.rnr_conv_run(pl.h, s), 'rnr_conv_run(%s)' % sp.name)
                 self.gpu_launches += 1
+            self._mark('fwd', sp.name, t0)
             if sp.dst == 'out':
                 continue
             N, Ho, Wo, Cc = self.N, sp.Ho, sp.Wo, sp.cout
@@ -588,7 +613,7 @@ class UNetEngine:
             st.drop = drop_masks.get(sp.name) if (drop_masks and sp.drop) else None
             _lib.check(L.rnr_bn_act_fwd(st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
                                         st.drop.data_ptr() if st.drop is not None else None, sp.slope,
-                                        self.acts[sp.dst].ptr, self.acts_w[sp.dst].ptr if (self.dual and training) else None,
+                                        self.acts[sp.dst].ptr, self.acts_w[sp.dst].ptr if self.dual else None,
                                         N, Ho, Wo, Cc, s), 'rnr_bn_act_fwd')
             self.gpu_launches += 1
         return self.layers['out'].raw
@@ -642,7 +667,12 @@ class UNetEngine:
         self.grad_flat.zero_()
         self.gpu_launches += 1
         go = grad_out.contiguous()
-        _lib.check(L.rnr_tanh_bwd_pack(go.data_ptr(), st.raw.data_ptr(), self.gz['out'].ptr,
+        th = st.raw
+        if not self.final_tanh:      # linear output: d/d raw = grad * (1 - 0^2)
+            if self._zeros_out is None:
+                self._zeros_out = torch.zeros_like(st.raw)
+            th = self._zeros_out
+        _lib.check(L.rnr_tanh_bwd_pack(go.data_ptr(), th.data_ptr(), self.gz['out'].ptr,
                                        self.grad_view(sp.b_key).data_ptr(), self.N, sp.cout, self.out_ld, sp.Ho, sp.Wo, s),
                    'rnr_tanh_bwd_pack')
         self.gpu_launches += 1
@@ -680,11 +710,15 @@ class UNetEngine:
                                                   st.invstd.data_ptr(), st.c1.data_ptr(), st.c2.data_ptr(), N, Ho, Wo, Cc, s),
                                'rnr_bn_bwd_apply')
                     self.gpu_launches += 1
+            t0 = self._mark()
             _lib.check(L.rnr_wgrad_run(st.wgrad_plan.h, s), 'rnr_wgrad_run(%s)' % sp.name)
             self.gpu_launches += 1
+            t1 = self._mark('wgrad', sp.name, t0)
             for pl in st.dgrad_plans:
                 _lib.check(L.rnr_conv_run(pl.h, s), 'rnr_conv_run(dgrad %s)' % sp.name)
                 self.gpu_launches += 1
+            if st.dgrad_plans:
+                self._mark('dgrad', sp.name, t1)
         st = self.layers['in']
         if st.gx is None:
             return None

@@ -1,0 +1,145 @@
+"""Autograd bridge between the drop-in ``Unet`` parameter tree and the tcgen05 engine.
+
+``UnetRunner(module)(x, apply_tanh)`` is what ``Unet.forward`` / ``RenderingNet.forward`` call
+(network.py:251-253; pytorch_prototyping/pytorch_prototyping.py:532-536).  It keeps one UNetEngine
+per (device, N, H, W, needs-grad, tanh) -- plans, TMA descriptors and all activation storage are
+created once and reused every step -- and exposes the run as a ``torch.autograd.Function`` so the
+caller's ``loss.backward()`` / ``torch.optim`` work unchanged.
+"""
+import weakref
+
+import torch
+
+from .unet import UNetEngine, unet_layer_specs
+
+
+def _live_params(unet):
+    """{engine key: Parameter} for the live layers, {key: buffer} for BN running stats."""
+    sd_params = dict(unet.named_parameters(remove_duplicate=False))
+    sd_bufs = dict(unet.named_buffers())
+    return sd_params, sd_bufs
+
+
+class _UnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, eng, training_bn, drop_masks, x, *params):
+        eng.set_input_nchw(x)
+        eng.forward(training=training_bn, drop_masks=drop_masks, need_backward_prep=eng.need_backward)
+        out = eng.output_nchw()
+        eng.version += 1
+        ctx.eng = eng
+        ctx.version = eng.version
+        ctx.runner = runner
+        ctx.n_params = len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.eng
+        if eng.version != ctx.version:
+            raise RuntimeError('U-Net engine buffers were overwritten by a later forward of the same shape before backward(); '
+                               'run backward before the next grad-enabled forward')
+        gx = eng.backward_from_nchw(grad_out.contiguous().float())
+        flat = eng.grad_flat.clone()          # hand out a private copy: the engine buffer is reused next step
+        grads = []
+        for key in ctx.runner.param_keys:
+            if key in eng.grad_slices:
+                o, n = eng.grad_slices[key]
+                grads.append(flat[o:o + n].view(eng.params[key].shape))
+            else:
+                grads.append(None)
+        gin = None
+        if gx is not None:
+            r0, r1 = eng.input_grad_range
+            if (r0, r1) == (0, eng.in_channels):
+                gin = gx
+            else:
+                gin = torch.zeros((eng.N, eng.in_channels, eng.H, eng.W), dtype=torch.float32, device=gx.device)
+                gin[:, r0:r1] = gx
+        return (None, None, None, None, gin, *grads)
+
+
+class UnetRunner:
+    def __init__(self, unet):
+        self._unet = weakref.ref(unet)
+        self._engines = {}
+        self.param_keys = None
+        #: channels of the input that need a gradient (None = all).  network.RenderingNet narrows this to the
+        #: neural-texture channels, the only differentiable part of the 108-channel RNR input.
+        self.input_grad_range = None
+
+    def _engine(self, x, need_backward, apply_tanh):
+        unet = self._unet()
+        cfg = unet._cfg
+        N, Cin, H, W = x.shape
+        if Cin != cfg['in_channels']:
+            raise ValueError('expected %d input channels, got %d' % (cfg['in_channels'], Cin))
+        rng = self.input_grad_range if (need_backward and x.requires_grad) else None
+        if need_backward and x.requires_grad and rng is None:
+            rng = (0, Cin)
+        key = (x.device, N, H, W, need_backward, apply_tanh, rng)
+        params, bufs = _live_params(unet)
+        eng = self._engines.get(key)
+        if eng is not None:
+            # parameters may have been re-created (module.to(), load_state_dict keeps them): re-bind by identity
+            if all(eng.params[k] is params[k] for k in eng.params):
+                return eng
+            del self._engines[key]
+        if H % (2 ** cfg['num_down']) or W % (2 ** cfg['num_down']) or min(H, W) < 2 ** (cfg['num_down'] + 1):
+            raise ValueError('input size %dx%d must be a multiple of %d and at least %d' % (
+                H, W, 2 ** cfg['num_down'], 2 ** (cfg['num_down'] + 1)))
+        specs = unet_layer_specs(cfg['in_channels'], cfg['out_channels'], cfg['nf0'], cfg['num_down'], cfg['max_channels'], H, W)
+        live = {}
+        for sp in specs:
+            for k in (sp.w_key, sp.b_key, sp.bn_key + '.weight' if sp.bn_key else None, sp.bn_key + '.bias' if sp.bn_key else None):
+                if k is not None:
+                    live[k] = params[k]
+        for k, p in live.items():
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise TypeError('U-Net parameter %s must be a contiguous fp32 CUDA tensor (librnr_b200 has no CPU path)' % k)
+        live_bufs = {k: v for k, v in bufs.items() if 'running' in k}
+        eng = UNetEngine(specs, live, live_bufs, N, Cin, x.device, impl='tc', input_grad_range=rng,
+                         need_backward=need_backward, final_tanh=apply_tanh)
+        eng.version = 0
+        # bound memory: keep at most 4 shapes alive
+        if len(self._engines) >= 4:
+            self._engines.pop(next(iter(self._engines)))
+        self._engines[key] = eng
+        return eng
+
+    def __call__(self, x, apply_tanh):
+        unet = self._unet()
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            raise TypeError('Unet input must be a CUDA tensor (librnr_b200 has no CPU path)')
+        x = x.float().contiguous()
+        params, bufs = _live_params(unet)
+        if self.param_keys is None:
+            cfg = unet._cfg
+            probe = unet_layer_specs(cfg['in_channels'], cfg['out_channels'], cfg['nf0'], cfg['num_down'], cfg['max_channels'], 64, 64)
+            keys = []
+            for sp in probe:
+                for k in (sp.w_key, sp.b_key, sp.bn_key + '.weight' if sp.bn_key else None, sp.bn_key + '.bias' if sp.bn_key else None):
+                    if k is not None:
+                        keys.append(k)
+            self.param_keys = keys
+        plist = [params[k] for k in self.param_keys]
+        need_backward = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist))
+        eng = self._engine(x, need_backward, apply_tanh)
+        bn_mod = unet.in_layer[1]
+        drop_mod = unet.in_layer[3]
+        training_bn = bool(bn_mod.training)
+        drop_masks = None
+        if drop_mod.training and drop_mod.p > 0:
+            p = float(drop_mod.p)
+            names = [sp.name for sp in eng.specs if sp.drop and sp.dst != 'out']
+            chans = [eng.layers[n].spec.cout for n in names]
+            r = (torch.rand((eng.N, sum(chans)), device=x.device) >= p).float() * (1.0 / (1.0 - p))
+            drop_masks, o = {}, 0
+            for n, c in zip(names, chans):
+                drop_masks[n] = r[:, o:o + c].contiguous()
+                o += c
+        if training_bn:
+            nbt = [b for k, b in bufs.items() if k.endswith('num_batches_tracked') and '.fuse.' not in k]
+            if nbt:
+                torch._foreach_add_(nbt, 1)
+        return _UnetFn.apply(self, eng, training_bn, drop_masks, x, *plist)
