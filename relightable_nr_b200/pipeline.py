@@ -109,7 +109,9 @@ class RNRPipeline:
             self.w.update(loss_weights)
         # lighting-loss targets (train_rnr.py:307-339): samples of the initial envmap, all covered
         with torch.no_grad():
+            # (targets are samples of the stitched envmap, not of its SH fit: never bit-equal to the estimate, so |.|' is defined)
             self.l_samples_init = _sph_harm.reconstruct_sh(self.lighting_model.coeff.data[0], self.lighting_model.basis_val).clone()
+            self.l_samples_init += 0.05 * torch.randn(self.l_samples_init.shape, generator=torch.Generator().manual_seed(seed + 31)).to(self.device)
             self.l_samples_init_mask = torch.ones(num_l_samples, dtype=torch.bool, device=self.device)
             self.l_samples_init_mask[::7] = False
         params = list(self.texture_mapper.parameters()) + list(self.lighting_model.parameters()) + list(self.render_net.parameters())
