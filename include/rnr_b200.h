@@ -241,6 +241,42 @@ int rnr_interp_vertex_attr(const float* attr, int attr_batch, int nv, int A, con
                            const int* face_index_map, const float* weight_map, float* out, int N, int64_t P, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Proxy-mesh rasterizer.  Replaces neural_renderer's projection (projection.py:6-53),          */
+/* vertices_to_faces (vertices_to_faces.py:4-25), rasterize_cuda.forward_face_index_map         */
+/* (cuda/rasterize_cuda.cpp:70-95, cuda/rasterize_cuda_kernel.cu:24-169), the vertical flip of   */
+/* rasterize_rgbad (rasterize.py:313-321) and the attribute interpolation of                    */
+/* network.Rasterizer.forward (network.py:176-214).                                             */
+/* ------------------------------------------------------------------------------------------ */
+/* vertices [1|N,nv,3], K/R [N,3,3], t [N,3], dist_coeffs [N,5]|NULL, offset/scale [N,2]|NULL -> uvz [N,nv,3] */
+int rnr_project_vertices(const float* vertices, int v_batch, int nv, const float* K, const float* R, const float* t,
+                         const float* dist_coeffs, const float* offset, const float* scale, float orig_size, float eps,
+                         float* out_uvz, int N, void* stream);
+/* per-face set-up.  Either faces_in [N,nf,3,3] is given (the reference extension's calling convention) or the faces are
+ * gathered from uvz [N,nv,3] through faces_idx [1|N,nf,3] (and optionally written to faces_out).
+ * Outputs: faces_inv [N,nf,3,3] (zeros for back faces, like torch.zeros_like in rasterize.py:163) and
+ * bbox [N,nf,2] int32 = packed pixel bounding boxes (x0 | x1<<16, y0 | y1<<16; x0 > x1 = culled).           */
+int rnr_raster_face_setup(const float* uvz, int nv, const int32_t* faces_idx, int f_batch, const float* faces_in, int nf,
+                          int image_size, float* faces_out, float* faces_inv, int32_t* bbox, int N, void* stream);
+typedef struct {               /* optional fused outputs of network.Rasterizer.forward; NULL members are skipped */
+    const float* v;  const int32_t* f_v_idx;      /* [nv,3],  [nf,3] */
+    const float* vt; const int32_t* f_vt_idx;     /* [nvt,2], [nf,3] */
+    const float* vn; const int32_t* f_vn_idx;     /* [nvn,3], [nf,3] */
+    const float* pose_R;                          /* [N,3,3] */
+    const float* pose_t;                          /* [N,3]   */
+    float* weight_pc;                             /* [N,is,is,3] perspective-correct weights (network.py:176-180) */
+    float* uv_map;                                /* [N,is,is,2] wrapped to [0,1) (:187-190) */
+    float* normal_map;                            /* [N,is,is,3] world, normalised (:197-200) */
+    float* normal_map_cam;                        /* (:203-205) */
+    float* position_map;                          /* (:208-210) */
+    float* position_map_cam;                      /* (:213-214) */
+} rnr_raster_attrs_t;
+/* z-buffered coverage of every pixel; every output pixel is written (background: index -1, weights 0, depth `far`),
+ * so no pre-fill is needed.  flip_y folds rasterize_rgbad's vertical flip into the store address.          */
+int rnr_raster_tiles(const float* faces, const float* faces_inv, const int32_t* bbox, int nf, int image_size, float near,
+                     float far, int flip_y, int32_t* face_index_map, float* weight_map, float* depth_map, float* alpha_map,
+                     float* face_inv_map, const rnr_raster_attrs_t* attrs, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Spherical harmonics: sph_harm.evaluate_sh_basis(lmax=2) (sph_harm.py:41-71),                 */
 /* sph_harm.reconstruct_sh (:91-102) fwd/bwd, sph_harm.fit_sh_coeff (:74-88)                    */
 /* ------------------------------------------------------------------------------------------ */

@@ -112,11 +112,77 @@ def gen_unet(ref):
     return out
 
 
+def _load_ref_file(name, relpath):
+    """Import one pure-Python file of the reference's neural_renderer package without its CUDA-extension imports."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join('/root/reference/neural_renderer/neural_renderer', relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_raster():
+    """projection / vertices_to_faces from the reference's Python; the z-buffer from the reference's own CUDA kernel bodies
+    compiled for the CPU (oracle/_ref/libref_raster.so, see oracle/build_oracle.py)."""
+    from oracle import build_oracle, raster as Rr, ref_raster
+    build_oracle.build(verbose=False)
+    proj_mod = _load_ref_file('ref_nr_projection', 'projection.py')
+    v2f_mod = _load_ref_file('ref_nr_v2f', 'vertices_to_faces.py')
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    # --- projection with distortion, offset and scale, batch 2
+    N, nv = 2, 50
+    verts = torch.randn(1, nv, 3, generator=g) * 0.5
+    K = torch.tensor([[[80.0, 0.3, 31.0], [0, 82.0, 33.0], [0, 0, 1]]]).repeat(N, 1, 1)
+    Rm = torch.linalg.qr(torch.randn(N, 3, 3, generator=g))[0]
+    t = torch.tensor([[[0.1, -0.2, 3.0]], [[-0.1, 0.05, 2.5]]])
+    dist = torch.tensor([[0.05, -0.01, 0.002, -0.003, 0.001], [0.0, 0.0, 0.0, 0.0, 0.0]])
+    off = torch.tensor([[1.0, -2.0], [0.0, 0.0]])
+    sc = torch.tensor([[0.9, 1.1], [1.0, 1.0]])
+    out.update(pj_v=verts, pj_K=K, pj_R=Rm, pj_t=t, pj_dist=dist, pj_off=off, pj_sc=sc,
+               pj_out=proj_mod.projection(verts.repeat(N, 1, 1), K, Rm, t, dist, 64, off, sc),
+               pj_out_plain=proj_mod.projection(verts.repeat(N, 1, 1), K, Rm, t, torch.zeros(N, 5), 64, None, None))
+    faces = torch.randint(0, nv, (1, 30, 3), generator=g).int()
+    out.update(vf_faces=faces, vf_out=v2f_mod.vertices_to_faces(out['pj_out'], faces),
+               vf_attr=v2f_mod.vertex_attrs_to_faces(torch.randn(1, nv, 2, generator=torch.Generator().manual_seed(9)), faces))
+    out['vf_attr_in'] = torch.randn(1, nv, 2, generator=torch.Generator().manual_seed(9))
+    # --- z-buffer of a UV sphere seen by a spiral camera + a soup of random triangles (ties, slivers, back faces), 48 px
+    import math
+    m = Rr.uv_sphere(12, 24)
+    size = 48
+    azi, ele = math.radians(-20.0), math.radians(15.0)
+    pos = np.array([3 * math.cos(ele) * math.sin(azi), 3 * math.sin(ele), 3 * math.cos(ele) * math.cos(azi)])
+    fwd = -pos / np.linalg.norm(pos)
+    right = np.cross(fwd, [0, 1, 0]); right /= np.linalg.norm(right)
+    down = np.cross(fwd, right)
+    Rc = np.stack([right, down, fwd]).astype(np.float32)
+    pose = torch.eye(4)[None].clone()
+    pose[0, :3, :3] = torch.from_numpy(Rc)
+    pose[0, :3, 3] = torch.from_numpy(-Rc @ pos.astype(np.float32))
+    Kc = torch.tensor([[[1.2 * size, 0, size / 2], [0, 1.2 * size, size / 2], [0, 0, 1]]])
+    uvz = proj_mod.projection(torch.from_numpy(m['v'])[None], Kc, pose[:, :3, :3], pose[:, :3, -1, None].permute(0, 2, 1),
+                              torch.zeros(1, 5), size, None, None)
+    f_sphere = v2f_mod.vertices_to_faces(uvz, torch.from_numpy(m['f'])[None]).numpy()
+    soup = (torch.rand(1, 60, 3, 3, generator=g) * 2 - 1)
+    soup[..., 2] = soup[..., 2] * 0.5 + 1.5
+    soup[0, 10] = soup[0, 9]                        # exact duplicate: depth tie -> lowest index wins
+    soup[0, 20, :, 2] = -1.0                        # behind the near plane
+    soup[0, 21, :, 2] = 2e5                         # beyond far
+    f_soup = soup.numpy()
+    for nm, f in (('sphere', f_sphere), ('soup', f_soup)):
+        fim, wm, dm, fiv, finv = ref_raster.forward_face_index_map(f, size, 0.0, 1e5)
+        out.update({'zb_%s_faces' % nm: f, 'zb_%s_fim' % nm: fim, 'zb_%s_wm' % nm: wm, 'zb_%s_dm' % nm: dm,
+                    'zb_%s_finv' % nm: np.nan_to_num(finv, nan=0.0, posinf=0.0, neginf=0.0)})
+    out.update(zb_size=np.array(size), zb_pose=pose, zb_K=Kc, zb_mesh_v=m['v'], zb_mesh_vt=m['vt'], zb_mesh_vn=m['vn'], zb_mesh_f=m['f'])
+    return out
+
+
 def main():
     ref = import_reference()
     np.savez_compressed(os.path.join(HERE, 'pixel_ops.npz'), **_np(gen_pixel_ops(ref)))
     np.savez_compressed(os.path.join(HERE, 'unet_small.npz'), **_np(gen_unet(ref)))
-    for f in ('pixel_ops.npz', 'unet_small.npz'):
+    np.savez_compressed(os.path.join(HERE, 'raster.npz'), **_np(gen_raster()))
+    for f in ('pixel_ops.npz', 'unet_small.npz', 'raster.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
 
 
