@@ -137,6 +137,20 @@ int rnr_weight_prep(const float* src, void* dst, int dst_dtype,
                     int nr, int nr_pad, int nc, int cpad, int ntaps,
                     int64_t s_r, int64_t s_c, const int32_t* tapoff_dev, void* stream);
 
+/* batched form: all layers' matrices in ONE launch (the job table lives in a plan) */
+typedef struct {
+    const float* src;          /* fp32 parameter (element offset already applied) */
+    void*        dst;          /* 16-bit matrix [nr_pad, ntaps*cpad] */
+    int32_t      dst_dtype;    /* RNR_F16 / RNR_BF16 */
+    int32_t      nr, nr_pad, nc, cpad, ntaps;
+    int64_t      s_r, s_c;     /* element strides of row / column index in src; min(s_r, s_c) = taps per (row, col) pair <= 16 */
+    int32_t      tapoff[16];   /* source tap index of each destination tap */
+} rnr_wprep_job_t;
+typedef struct rnr_wprep_plan rnr_wprep_plan_t;
+int  rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr_wprep_plan_t** plan);
+void rnr_wprep_plan_destroy(rnr_wprep_plan_t* plan);
+int  rnr_wprep_run(const rnr_wprep_plan_t* plan, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* BatchNorm2d (batch statistics) + activation + Dropout2d                                     */
 /*   replaces nn.BatchNorm2d / LeakyReLU / ReLU / Dropout2d of pytorch_prototyping.py:177-197,  */

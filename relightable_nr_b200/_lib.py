@@ -53,6 +53,12 @@ class GSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("fold", C.c_int32), ("ld", C.c_int32), ("c0", C.c_int32)]
 
 
+class WPrepJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_dtype", C.c_int32), ("nr", C.c_int32), ("nr_pad", C.c_int32),
+                ("nc", C.c_int32), ("cpad", C.c_int32), ("ntaps", C.c_int32), ("s_r", C.c_int64), ("s_c", C.c_int64),
+                ("tapoff", C.c_int32 * 16)]
+
+
 class RnrError(RuntimeError):
     pass
 
@@ -83,6 +89,8 @@ def lib():
         "rnr_wgrad_plan_create": [C.POINTER(WgradProblem), i32, C.POINTER(vp)],
         "rnr_wgrad_run": [vp, vp],
         "rnr_weight_prep": [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, vp, vp],
+        "rnr_wprep_plan_create": [C.POINTER(WPrepJob), i32, C.POINTER(vp)],
+        "rnr_wprep_run": [vp, vp],
         "rnr_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp],
         "rnr_bn_act_fwd": [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
@@ -101,6 +109,8 @@ def lib():
     L.rnr_conv_plan_destroy.restype = None
     L.rnr_wgrad_plan_destroy.argtypes = [vp]
     L.rnr_wgrad_plan_destroy.restype = None
+    L.rnr_wprep_plan_destroy.argtypes = [vp]
+    L.rnr_wprep_plan_destroy.restype = None
     _register_optional(L)
     _lib = L
     return L

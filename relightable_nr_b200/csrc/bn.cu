@@ -52,47 +52,53 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ drop, float slope,
                                   __half* __restrict__ act, __nv_bfloat16* __restrict__ act_b, int N, int H, int W, int C) {
-    const int vpp = C >> 3;
-    const int64_t total = (int64_t)N * H * W * vpp;
+    // grid.y = image row (n*H + h); threads of a row = (w, 8-channel vector): 32-bit index math only
+    const unsigned vpp = (unsigned)C >> 3;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)W * vpp) return;
+    const int row = blockIdx.y;
+    const int n = row / H, h = row - n * H;
+    const int w = (int)(idx / vpp);
+    const int c = (int)(idx - (unsigned)w * vpp) * 8;
     const int Hp = H + 2, Wp = W + 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % vpp);
-        const int64_t pix = i / vpp;
-        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
-        const int c = cv * 8;
-        const float4 r0 = *(const float4*)(raw + pix * C + c);
-        const float4 r1 = *(const float4*)(raw + pix * C + c + 4);
-        const float4 s0 = *(const float4*)(scale + c), s1 = *(const float4*)(scale + c + 4);
-        const float4 t0 = *(const float4*)(shift + c), t1 = *(const float4*)(shift + c + 4);
-        float v[8] = {r0.x * s0.x + t0.x, r0.y * s0.y + t0.y, r0.z * s0.z + t0.z, r0.w * s0.w + t0.w,
-                      r1.x * s1.x + t1.x, r1.y * s1.y + t1.y, r1.z * s1.z + t1.z, r1.w * s1.w + t1.w};
-        __align__(16) __half o[8];
-        __align__(16) __nv_bfloat16 ob[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            float z = v[e];
-            z = z > 0.f ? z : z * slope;
-            if (drop) z *= drop[n * C + c + e];
-            o[e] = __float2half_rn(z);
-            ob[e] = __float2bfloat16_rn(z);
-        }
-        const uint4 ov = *(const uint4*)o;
-        const uint4 ovb = *(const uint4*)ob;
-        // rows / cols this pixel lands on in the padded tensor
-        int rows[3], cols[3], nr = 0, nc = 0;
-        rows[nr++] = h + 1;
-        if (h == 1) rows[nr++] = 0;
-        if (h == H - 2) rows[nr++] = H + 1;
-        cols[nc++] = w + 1;
-        if (w == 1) cols[nc++] = 0;
-        if (w == W - 2) cols[nc++] = W + 1;
-        for (int a = 0; a < nr; a++)
-            for (int b = 0; b < nc; b++) {
-                const int64_t o_ = (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * C + c;
-                *(uint4*)(act + o_) = ov;
-                if (act_b) *(uint4*)(act_b + o_) = ovb;
-            }
+    const int64_t pix = (int64_t)row * W + w;
+    const float4 r0 = __ldcs((const float4*)(raw + pix * C + c));
+    const float4 r1 = __ldcs((const float4*)(raw + pix * C + c + 4));
+    const float4 s0 = *(const float4*)(scale + c), s1 = *(const float4*)(scale + c + 4);
+    const float4 t0 = *(const float4*)(shift + c), t1 = *(const float4*)(shift + c + 4);
+    float v[8] = {r0.x * s0.x + t0.x, r0.y * s0.y + t0.y, r0.z * s0.z + t0.z, r0.w * s0.w + t0.w,
+                  r1.x * s1.x + t1.x, r1.y * s1.y + t1.y, r1.z * s1.z + t1.z, r1.w * s1.w + t1.w};
+    float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    if (drop) {
+        const float4 d0 = *(const float4*)(drop + n * C + c), d1 = *(const float4*)(drop + n * C + c + 4);
+        dm[0] = d0.x; dm[1] = d0.y; dm[2] = d0.z; dm[3] = d0.w; dm[4] = d1.x; dm[5] = d1.y; dm[6] = d1.z; dm[7] = d1.w;
     }
+    __align__(16) __half o[8];
+    __align__(16) __nv_bfloat16 ob[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        float z = v[e];
+        z = z > 0.f ? z : z * slope;
+        z *= dm[e];
+        o[e] = __float2half_rn(z);
+        ob[e] = __float2bfloat16_rn(z);
+    }
+    const uint4 ov = *(const uint4*)o;
+    const uint4 ovb = *(const uint4*)ob;
+    // rows / cols this pixel lands on in the padded tensor (reflect halo)
+    int rows[3], cols[3], nr = 0, nc = 0;
+    rows[nr++] = h + 1;
+    if (h == 1) rows[nr++] = 0;
+    if (h == H - 2) rows[nr++] = H + 1;
+    cols[nc++] = w + 1;
+    if (w == 1) cols[nc++] = 0;
+    if (w == W - 2) cols[nc++] = W + 1;
+    for (int a = 0; a < nr; a++)
+        for (int b = 0; b < nc; b++) {
+            const int64_t o_ = (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * C + c;
+            *(uint4*)(act + o_) = ov;
+            if (act_b) *(uint4*)(act_b + o_) = ovb;
+        }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -123,6 +129,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const GSrcs srcs, co
                                      const float* __restrict__ drop, float slope,
                                      __nv_bfloat16* __restrict__ gz, float* __restrict__ partials,
                                      int N, int H, int W, int C, int ppb) {
+    // block b walks row segments (row = n*H + h, segment = ppb*SEG consecutive pixels); thread = (pixel lane pl, 8-channel vector cv)
     extern __shared__ float s_red[];   // [2][C]
     const int vpp = C >> 3;
     const int cv = threadIdx.x % vpp, pl = threadIdx.x / vpp;
@@ -130,7 +137,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const GSrcs srcs, co
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
     __syncthreads();
     const int Hp = H + 2, Wp = W + 2;
-    const int64_t npix = (int64_t)N * H * W;
     float sg[8], sgx[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) { sg[e] = 0.f; sgx[e] = 0.f; }
@@ -139,9 +145,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const GSrcs srcs, co
 #pragma unroll
         for (int e = 0; e < 8; e++) { sc[e] = scale[c + e]; sh[e] = shift[c + e]; mu[e] = mean[c + e]; is[e] = invstd[c + e]; }
     }
+    const int segs_per_row = (W + ppb - 1) / ppb;            // one segment = ppb pixels (one per pixel lane)
+    const int nseg = N * H * segs_per_row;
     if (pl < ppb)
-    for (int64_t pix = (int64_t)blockIdx.x * ppb + pl; pix < npix; pix += (int64_t)gridDim.x * ppb) {
-        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+    for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        const int row = seg / segs_per_row;
+        const int w = (seg - row * segs_per_row) * ppb + pl;
+        if (w >= W) continue;
+        const int n = row / H, h = row - n * H;
+        const int64_t pix = (int64_t)row * W + w;
         float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int si = 0; si < srcs.n; si++) {
             const rnr_gsrc_t& s = srcs.s[si];
@@ -214,35 +226,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __rest
                                     const float* __restrict__ gamma, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ c1,
                                     const float* __restrict__ c2, int N, int H, int W, int C) {
-    const int vpp = C >> 3;
-    const int64_t total = (int64_t)N * H * W * vpp;
+    const unsigned vpp = (unsigned)C >> 3;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)W * vpp) return;
+    const int row = blockIdx.y;
+    const int n = row / H, h = row - n * H;
+    const int w = (int)(idx / vpp);
+    const int c = (int)(idx - (unsigned)w * vpp) * 8;
     const int Hp = H + 2, Wp = W + 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % vpp);
-        const int64_t pix = i / vpp;
-        const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
-        const int c = cv * 8;
-        __nv_bfloat16* gp = gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c;
-        uint4 u = *(const uint4*)gp;
-        __nv_bfloat16* gb = (__nv_bfloat16*)&u;
-        const float4 r0 = *(const float4*)(raw + pix * C + c);
-        const float4 r1 = *(const float4*)(raw + pix * C + c + 4);
-        const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const int64_t pix = (int64_t)row * W + w;
+    __nv_bfloat16* gp = gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c;
+    uint4 u = *(const uint4*)gp;
+    __nv_bfloat16* gb = (__nv_bfloat16*)&u;
+    const float4 r0 = __ldcs((const float4*)(raw + pix * C + c));
+    const float4 r1 = __ldcs((const float4*)(raw + pix * C + c + 4));
+    const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const float is = invstd[c + e];
-            const float xh = (r[e] - mean[c + e]) * is;
-            const float g = __bfloat162float(gb[e]);
-            gb[e] = __float2bfloat16_rn(gamma[c + e] * is * (g - c1[c + e] - xh * c2[c + e]));
-        }
-        *(uint4*)gp = u;
+    for (int e = 0; e < 8; e++) {
+        const float is = invstd[c + e];
+        const float xh = (r[e] - mean[c + e]) * is;
+        const float g = __bfloat162float(gb[e]);
+        gb[e] = __float2bfloat16_rn(gamma[c + e] * is * (g - c1[c + e] - xh * c2[c + e]));
     }
-}
-
-inline int ew_blocks(int64_t total) {
-    int64_t b = (total + 255) / 256;
-    const int64_t cap = 148 * 8;
-    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+    *(uint4*)gp = u;
 }
 
 }  // namespace
@@ -260,8 +266,9 @@ extern "C" int rnr_bn_act_fwd(const float* raw, const float* scale, const float*
                               void* act, void* act_bf16, int N, int H, int W, int C, void* stream) {
     RNR_REQUIRE(C % 8 == 0, "rnr_bn_act_fwd: C=%d must be a multiple of 8", C);
     RNR_REQUIRE(H >= 2 && W >= 2, "rnr_bn_act_fwd: reflect halo needs H,W >= 2");
-    const int64_t total = (int64_t)N * H * W * (C / 8);
-    bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(raw, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
+    RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_act_fwd: N*H=%lld exceeds the grid limit", (long long)N * H);
+    dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
+    bn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -278,9 +285,9 @@ extern "C" int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* 
     int ppb = 256 / vpp;
     if (ppb < 1) ppb = 1;
     const int threads = vpp * ppb > 256 ? 256 : vpp * ppb;   // vpp<=256 guaranteed by C<=2048
-    const int64_t npix = (int64_t)N * H * W;
-    int T = rnr_cdiv(npix, (int64_t)ppb * 8);
-    if (T > 148 * 4) T = 148 * 4;
+    const int64_t nseg = (int64_t)N * H * rnr_cdiv(W, ppb);
+    int T = rnr_cdiv(nseg, 4);
+    if (T > 148 * 8) T = 148 * 8;
     if (T < 1) T = 1;
     if (T_out) *T_out = T;
     bn_bwd_reduce_kernel<<<T, threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
@@ -298,8 +305,9 @@ extern "C" int rnr_bn_bwd_finalize(const float* partials, int T, int C, double c
 
 extern "C" int rnr_bn_bwd_apply(void* gz, const float* raw, const float* gamma, const float* mean, const float* invstd,
                                 const float* c1, const float* c2, int N, int H, int W, int C, void* stream) {
-    const int64_t total = (int64_t)N * H * W * (C / 8);
-    bn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, gamma, mean, invstd, c1, c2, N, H, W, C);
+    RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_bwd_apply: N*H=%lld exceeds the grid limit", (long long)N * H);
+    dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
+    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, gamma, mean, invstd, c1, c2, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -67,37 +67,59 @@ __global__ void __launch_bounds__(256) unpack_nhwc_to_nchw_kernel(const float* _
 }
 
 // grad wrt tanh output (NCHW fp32) -> gz = g*(1-t^2) in bf16 zero-halo [N,H+2,W+2,ld]; dbias += sum
+// One CTA walks TANH_ROWS image rows of a 32-pixel column strip and keeps its bias partial sums in registers, so the
+// per-channel atomics on dbias drop from one per (row, strip) to one per (TANH_ROWS rows, strip).
+constexpr int TANH_ROWS = 16;
+constexpr int TANH_MAXC8 = 16;       // ld <= 128
 __global__ void __launch_bounds__(256) tanh_bwd_pack_kernel(const float* __restrict__ grad, const float* __restrict__ th,
                                                           __nv_bfloat16* __restrict__ gz, float* __restrict__ dbias,
                                                           int N, int C, int ld, int H, int W) {
     extern __shared__ float tile[];   // [ld][TP+1]
-    const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
+    const int w0 = blockIdx.x * TP, n = blockIdx.z;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    for (int c = wp; c < ld; c += 8) {
-        float v = 0.f;
-        if (c < C && w0 + lane < W) v = grad[(((int64_t)n * C + c) * H + h) * W + w0 + lane];
-        tile[c * (TP + 1) + lane] = v;
-    }
-    __syncthreads();
     const int Hp = H + 2, Wp = W + 2;
-    for (int i = threadIdx.x; i < TP * ld; i += 256) {
-        const int px = i / ld, c = i % ld;
-        const int w = w0 + px;
-        float g = 0.f;
-        if (w < W && c < C) {
-            const float t = th[(((int64_t)n * H + h) * W + w) * ld + c];
-            g = tile[c * (TP + 1) + px] * (1.f - t * t);
-        }
-        tile[c * (TP + 1) + px] = g;
-        if (w < W) gz[(((int64_t)n * Hp + h + 1) * Wp + w + 1) * ld + c] = __float2bfloat16_rn(g);
-    }
-    __syncthreads();
-    if (dbias) {
-        for (int c = wp; c < C; c += 8) {
-            float v = tile[c * (TP + 1) + lane];
+    float bsum[TANH_MAXC8];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) atomicAdd(dbias + c, v);
+    for (int j = 0; j < TANH_MAXC8; j++) bsum[j] = 0.f;
+    const int h_end = min(H, (int)(blockIdx.y + 1) * TANH_ROWS);
+    for (int h = blockIdx.y * TANH_ROWS; h < h_end; h++) {
+        for (int c = wp; c < ld; c += 8) {
+            float v = 0.f;
+            if (c < C && w0 + lane < W) v = grad[(((int64_t)n * C + c) * H + h) * W + w0 + lane];
+            tile[c * (TP + 1) + lane] = v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < TP * ld; i += 256) {
+            const int px = i / ld, c = i % ld;
+            const int w = w0 + px;
+            float g = 0.f;
+            if (w < W && c < C) {
+                const float t = th[(((int64_t)n * H + h) * W + w) * ld + c];
+                g = tile[c * (TP + 1) + px] * (1.f - t * t);
+            }
+            tile[c * (TP + 1) + px] = g;
+            if (w < W) gz[(((int64_t)n * Hp + h + 1) * Wp + w + 1) * ld + c] = __float2bfloat16_rn(g);
+        }
+        __syncthreads();
+        if (dbias) {
+#pragma unroll
+            for (int j = 0; j < TANH_MAXC8; j++) {
+                const int c = wp + 8 * j;
+                if (c < C) bsum[j] += tile[c * (TP + 1) + lane];
+            }
+        }
+        __syncthreads();
+    }
+    if (dbias) {
+#pragma unroll
+        for (int j = 0; j < TANH_MAXC8; j++) {
+            const int c = wp + 8 * j;
+            if (c < C) {
+                float v = bsum[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) atomicAdd(dbias + c, v);
+            }
         }
     }
 }
@@ -157,8 +179,8 @@ extern "C" int rnr_unpack_nhwc_to_nchw(const float* src, float* dst, int N, int 
 extern "C" int rnr_tanh_bwd_pack(const float* grad_nchw, const float* tanh_nhwc, void* gz, float* dbias, int N, int C,
                                  int ld, int H, int W, void* stream) {
     const size_t smem = (size_t)ld * (TP + 1) * sizeof(float);
-    RNR_REQUIRE(smem <= 48 * 1024, "rnr_tanh_bwd_pack: too many channels (%d)", ld);
-    dim3 grid(rnr_cdiv(W, TP), H, N);
+    RNR_REQUIRE(smem <= 48 * 1024 && ld <= 8 * TANH_MAXC8, "rnr_tanh_bwd_pack: too many channels (%d)", ld);
+    dim3 grid(rnr_cdiv(W, TP), rnr_cdiv(H, TANH_ROWS), N);
     tanh_bwd_pack_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(grad_nchw, tanh_nhwc, (__nv_bfloat16*)gz, dbias, N, C, ld, H, W);
     RNR_LAUNCH_CHECK();
     return 0;

@@ -72,22 +72,79 @@ __global__ void __launch_bounds__(128) texmap_fwd_kernel(const TexLevels lv, int
         if (c < C) out[((int64_t)n * C + c) * HW + p] = acc[c];
 }
 
+// Backward of the texture sampling: scatter-add of gout * bilinear weight into the 4 mip levels.
+// 262 144 pixels x 4 levels x 4 taps x C channels of atomics funnel into as few as 64^2 texels, so contributions are
+// aggregated in the warp first.  A warp owns an 8x4 pixel block (neighbouring pixels hit the same / neighbouring
+// texels); for every distinct texel the block touches at a level, each lane sums the weights of its taps on that
+// texel, and the C-channel products are reduced across the warp by a transposing butterfly (31 shuffles for 32
+// channels, lane c ends up with the sum of channel c) followed by ONE coalesced red.global.add of C floats.
+// Texels no pixel maps to receive no atomic at all, so their gradient stays exactly 0 (the albedo-mean loss of
+// train_rnr.py:598 relies on bit-identical untouched texels).
+template <int CMAX>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[CMAX], int lane) {
+    // after the call lane c (c < CMAX) holds sum over lanes of v[c]; CMAX in {16, 32}
+    if (CMAX == 32) {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const float keep = hi ? v[j + 16] : v[j], send = hi ? v[j] : v[j + 16];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    } else {
+        // 16 channels: fold the two half-warps first (both halves end with the full sums of 16 channels)
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float keep = hi ? v[j + 8] : v[j], send = hi ? v[j] : v[j + 8];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float keep = hi ? v[j + 4] : v[j], send = hi ? v[j] : v[j + 4];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const float keep = hi ? v[j + 2] : v[j], send = hi ? v[j] : v[j + 2];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+    }
+    {
+        const bool hi = lane & 1;
+        const float keep = hi ? v[1] : v[0], send = hi ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    return v[0];
+}
+
 template <int CMAX>
 __global__ void __launch_bounds__(128) texmap_bwd_kernel(const TexLevels lv, int C, const float* __restrict__ uv,
                                                        const float* __restrict__ sh, int sh_start,
-                                                       const float* __restrict__ gout, int64_t HW, int N) {
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= HW * N) return;
-    const int n = (int)(pix / HW);
-    const int64_t p = pix % HW;
-    const float u = uv[pix * 2 + 0], v = uv[pix * 2 + 1];
+                                                       const float* __restrict__ gout, int H, int W, int N) {
+    // block = 4 warps = 16 x 8 pixels; warp = 8 x 4 pixels
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int n = blockIdx.z;
+    const int64_t HW = (int64_t)H * W;
+    const bool inb = x < W && y < H;
+    const int64_t p = inb ? (int64_t)y * W + x : 0;
+    const int64_t pix = (int64_t)n * HW + p;
     float g[CMAX];
     bool any = false;
 #pragma unroll
-    for (int c = 0; c < CMAX; c++) {
-        g[c] = (c < C) ? gout[((int64_t)n * C + c) * HW + p] : 0.f;
-    }
-    if (sh) {
+    for (int c = 0; c < CMAX; c++) g[c] = (inb && c < C) ? gout[((int64_t)n * C + c) * HW + p] : 0.f;
+    if (sh && inb) {
 #pragma unroll
         for (int k = 0; k < 9; k++) {
             const float s = sh[pix * 9 + k];
@@ -97,29 +154,37 @@ __global__ void __launch_bounds__(128) texmap_bwd_kernel(const TexLevels lv, int
         }
     }
 #pragma unroll
-    for (int c = 0; c < CMAX; c++) any |= (g[c] != 0.f);
-    if (!any) return;      // masked-out pixels contribute exact zeros: skip the atomics
+    for (int c = 0; c < CMAX; c++) any |= (g[c] != 0.f);       // masked-out pixels contribute exact zeros: no atomics
+    if (!__any_sync(0xffffffffu, any)) return;
+    float u = 0.f, v = 0.f;
+    if (inb) { u = uv[pix * 2 + 0]; v = uv[pix * 2 + 1]; }
+    // which of the 32 lanes is responsible for which channel after the transposing reduction
+    const int my_c = (CMAX == 32) ? lane : (lane & 15);
+    const bool writer = (CMAX == 32) ? (lane < C) : (lane < 16 && lane < C);
     for (int l = 0; l < lv.n; l++) {
-        const int S = lv.size[l];
-        const float x = u * (float)(S - 1);
-        const float y = (float)(S - 1) - v * (float)(S - 1);
-        const Bilin b = bilinear_setup(x, y, S, S);
         float* T = lv.gtex[l];
         if (!T) continue;
-        const int idx[4] = {b.i00, b.i10, b.i01, b.i11};
-        const float w[4] = {b.w00, b.w10, b.w01, b.w11};
+        const int S = lv.size[l];
+        const Bilin b = bilinear_setup(u * (float)(S - 1), (float)(S - 1) - v * (float)(S - 1), S, S);
+        int key[4] = {b.i00, b.i10, b.i01, b.i11};
+        float w[4] = {b.w00, b.w10, b.w01, b.w11};
+        if (!any) { w[0] = w[1] = w[2] = w[3] = 0.f; }
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-            if (w[t] == 0.f) continue;
-            float* dst = T + (int64_t)idx[t] * C;
-            if ((C & 3) == 0) {
+            while (true) {
+                const unsigned pend = __ballot_sync(0xffffffffu, w[t] != 0.f);
+                if (!pend) break;
+                const int leader = __ffs(pend) - 1;
+                const int k = __shfl_sync(0xffffffffu, key[t], leader);
+                float wk = 0.f;
 #pragma unroll
-                for (int c = 0; c < CMAX; c += 4)
-                    if (c < C) atomicAdd((float4*)(dst + c), make_float4(g[c] * w[t], g[c + 1] * w[t], g[c + 2] * w[t], g[c + 3] * w[t]));
-            } else {
+                for (int tt = 0; tt < 4; tt++)
+                    if (key[tt] == k) { wk += w[tt]; w[tt] = 0.f; }      // (weights of coincident taps add: same as separate atomics)
+                float prod[CMAX];
 #pragma unroll
-                for (int c = 0; c < CMAX; c++)
-                    if (c < C) atomicAdd(dst + c, g[c] * w[t]);
+                for (int c = 0; c < CMAX; c++) prod[c] = g[c] * wk;
+                const float sum = warp_transpose_reduce<CMAX>(prod, lane);
+                if (writer) atomicAdd(T + (int64_t)k * C + my_c, sum);
             }
         }
     }
@@ -195,10 +260,9 @@ extern "C" int rnr_texmap_bwd(float* const* gtex, const int* sizes, int L, int C
     int rc = fill_levels(lv, nullptr, gtex, sizes, L);
     if (rc) return rc;
     RNR_REQUIRE(C >= 1 && C <= 32, "texture mapper: 1..32 channels supported, got %d", C);
-    const int64_t HW = (int64_t)H * W;
-    const int blocks = rnr_cdiv(HW * N, 128);
-    if (C <= 16) texmap_bwd_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, HW, N);
-    else texmap_bwd_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, HW, N);
+    dim3 blocks(rnr_cdiv(W, 16), rnr_cdiv(H, 8), N);
+    if (C <= 16) texmap_bwd_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, H, W, N);
+    else texmap_bwd_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, H, W, N);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import _lib
-from .._lib import BF16, EPI_BIAS, EPI_STATS, EPI_TANH, F16, F32, ConvProblem, GSrc, KStep, WgradProblem, WTap
+from .._lib import BF16, EPI_BIAS, EPI_STATS, EPI_TANH, F16, F32, ConvProblem, GSrc, KStep, WgradProblem, WPrepJob, WTap
 from .views import HaloTensor, tile_shape
 
 _TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
@@ -117,7 +117,7 @@ class _Plan:
         try:
             L = _lib.lib()
             if self.h:
-                (L.rnr_conv_plan_destroy if self.kind == 'conv' else L.rnr_wgrad_plan_destroy)(self.h)
+                {'conv': L.rnr_conv_plan_destroy, 'wgrad': L.rnr_wgrad_plan_destroy, 'wprep': L.rnr_wprep_plan_destroy}[self.kind](self.h)
         except Exception:
             pass
 
@@ -136,6 +136,7 @@ class _WPrep:
     s_r: int
     s_c: int
     tapoff: torch.Tensor    # int32 device
+    tapoff_host: Tuple[int, ...] = ()
 
 
 @dataclass
@@ -236,7 +237,7 @@ class UNetEngine:
             if self.need_backward:
                 ld = self.out_ld if sp.dst == 'out' else sp.cout
                 self.gz[sp.name] = HaloTensor(N, Ho, Wo, ld, gdt, dev, zero=True)
-                st.bwd_partials = self._alloc((148 * 4 * 2 * max(ld, 8),), torch.float32)
+                st.bwd_partials = self._alloc((148 * 8 * 2 * max(ld, 8),), torch.float32)
             # flat gradient storage
             for key in (sp.w_key, sp.b_key, (sp.bn_key + '.weight') if sp.bn_key else None,
                         (sp.bn_key + '.bias') if sp.bn_key else None):
@@ -247,6 +248,10 @@ class UNetEngine:
         self.grad_flat = self._alloc((max(grad_numel, 4),), torch.float32, zero=True) if self.need_backward else None
         for sp in self.specs:
             self._build_layer(self.layers[sp.name])
+        fwd_items = [w for sp in self.specs for w in self.layers[sp.name].wprep_fwd]
+        all_items = fwd_items + [w for sp in self.specs for w in self.layers[sp.name].wprep_dgrad]
+        self.wprep_fwd_plan = self._wprep_plan(fwd_items)
+        self.wprep_all_plan = self._wprep_plan(all_items) if len(all_items) > len(fwd_items) else self.wprep_fwd_plan
 
     # ---- problem builders ---------------------------------------------------------------------
     def _conv_problem(self, views, ksteps, ab_dtype, bk, wmat, n_rows_w, cout, mN, mY, mX, out_t, out_dtype,
@@ -288,8 +293,24 @@ class UNetEngine:
 
     def _tapoff(self, offs):
         t = torch.tensor(offs, dtype=torch.int32, device=self.device)
+        t.host = tuple(int(o) for o in offs)
         self.keep.append(t)
         return t
+
+    def _wprep_plan(self, items):
+        """One batched weight-preparation plan (a single launch) for a list of _WPrep jobs."""
+        arr = (WPrepJob * len(items))()
+        for j, w in zip(arr, items):
+            src = self.params[w.src_key]
+            j.src = src.data_ptr() + 4 * w.src_off
+            j.dst = w.dst.data_ptr()
+            j.dst_dtype, j.nr, j.nr_pad, j.nc, j.cpad, j.ntaps = w.dtype, w.nr, w.nr_pad, w.nc, w.cpad, w.ntaps
+            j.s_r, j.s_c = w.s_r, w.s_c
+            for t, o in enumerate(w.tapoff.host):
+                j.tapoff[t] = o
+        h = C.c_void_p()
+        _lib.check(self.L.rnr_wprep_plan_create(arr, len(items), C.byref(h)), 'rnr_wprep_plan_create')
+        return _Plan(h, 'wprep')
 
     def _build_layer(self, st: _LayerState):
         sp = st.spec
@@ -563,6 +584,13 @@ class UNetEngine:
             self.gpu_launches += 1
 
     def prepare_weights(self, backward=False):
+        """fp32 parameters -> 16-bit GEMM matrices of every layer (forward, and data-gradient when ``backward``): one launch."""
+        plan = self.wprep_all_plan if backward else self.wprep_fwd_plan
+        _lib.check(self.L.rnr_wprep_run(plan.h, self._stream()), 'rnr_wprep_run')
+        self.gpu_launches += 1
+
+    def prepare_weights_per_layer(self, backward=False):
+        """Same result through the single-matrix entry point (kept as the cross-check of the batched kernel)."""
         s = self._stream()
         for sp in self.specs:
             st = self.layers[sp.name]

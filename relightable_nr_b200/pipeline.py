@@ -115,7 +115,8 @@ class RNRPipeline:
             self.l_samples_init_mask = torch.ones(num_l_samples, dtype=torch.bool, device=self.device)
             self.l_samples_init_mask[::7] = False
         params = list(self.texture_mapper.parameters()) + list(self.lighting_model.parameters()) + list(self.render_net.parameters())
-        self.optimizer = torch.optim.Adam(params, lr=lr)
+        # torch.optim.Adam like train_rnr.py:376; ``fused=True`` only picks torch's single-kernel multi-tensor implementation
+        self.optimizer = torch.optim.Adam(params, lr=lr, fused=True)
         self.optimizer.zero_grad()
         self.lighting_idx = 0
 

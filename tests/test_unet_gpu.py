@@ -79,3 +79,21 @@ def test_unet_forward_backward(cfg, impl):
     r = rel_l2(gx.cpu(), ref_gx)
     print(f"[{impl}] worst param-grad rel_l2 {worst:.2e}; input-grad rel_l2 {r:.2e}")
     assert r <= 3e-2
+
+
+def test_batched_weight_prep_is_bit_identical_to_per_layer():
+    """rnr_wprep_run (one launch, smem-staged) against rnr_weight_prep (one launch per matrix): identical 16-bit matrices for
+    every forward / data-gradient matrix of the RNR U-Net (incl. the input-gradient channel range and ConvTranspose parities)."""
+    sd, x = _setup(108, 78, 64, 64, 1, 5)
+    eng, _ = _engine(sd, x, 78, 64, 5, 'tc', (84, 108))
+    items = [w for sp in eng.specs for w in eng.layers[sp.name].wprep_fwd + eng.layers[sp.name].wprep_dgrad]
+    assert len(items) >= 70
+    eng.prepare_weights_per_layer(backward=True)
+    torch.cuda.synchronize()
+    ref = [w.dst.clone() for w in items]
+    for w in items:
+        w.dst.fill_(float('nan'))
+    eng.prepare_weights(backward=True)
+    torch.cuda.synchronize()
+    for w, r in zip(items, ref):
+        assert torch.equal(w.dst.view(torch.int16), r.view(torch.int16)), (w.src_key, w.ntaps, w.s_r, w.s_c)
