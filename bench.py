@@ -183,7 +183,7 @@ def run_reference(args):
 def _config(args, world):
     return {'workload': 'RNR train step (train_rnr.py:490-623), %dx%d material-sphere proxy views, 1 view/GPU/step, texture 512^2x24ch x4 mips, '
                         'U-Net 108->78 nf0=64, 26 rays, SH lmax 10 envmap 256x512' % (args.size, args.size),
-            'views_per_step': max(world, 1), 'parallelism': 'dp%d (views sharded, NCCL grad all-reduce)' % max(world, 1),
+            'views_per_step': max(world, 1), 'parallelism': 'dp%d (views sharded, NCCL grad all-reduce)' % max(world, 1), 'launch': 'eager' if args.no_graph else 'one CUDA graph per step',
             'l2': 'per-step working set (~3 GB of activations/gradients) >> 126 MB L2; 4 distinct views cycled'}
 
 
@@ -205,7 +205,7 @@ def run_ours(args):
     from relightable_nr_b200 import _lib
     from relightable_nr_b200.pipeline import RNRPipeline, synthetic_view
     L = _lib.lib()
-    pipe = RNRPipeline(device=dev, img_size=args.size, seed=0)
+    pipe = RNRPipeline(device=dev, img_size=args.size, seed=0, capturable=not args.no_graph)
     nviews = 4
     views = [synthetic_view(args.size, view_idx=7 * (rank * nviews + i), device=dev) for i in range(nviews)]
     host_views = [{k: v.cpu().pin_memory() for k, v in vw.items()} for vw in views]
@@ -224,7 +224,7 @@ def run_ours(args):
             g.copy_(flat[o:o + g.numel()].view_as(g))
             o += g.numel()
 
-    def step(view):
+    def eager_step(view):
         final, rays_lt, alpha_map = pipe.forward(view)
         loss, _ = pipe.losses(view, final, rays_lt, alpha_map)
         loss.backward()
@@ -232,6 +232,12 @@ def run_ours(args):
         pipe.optimizer.step()
         pipe.optimizer.zero_grad()
         return loss
+
+    if args.no_graph:
+        step = eager_step
+    else:
+        # the whole iteration (incl. the gradient all-reduce) as one CUDA graph; per-view maps are copied into its static inputs
+        step, _static = pipe.make_graphed_step(views[0], grad_hook=(lambda ps: sync_grads()) if world > 1 else None)
 
     def barrier():
         if world > 1:
@@ -260,6 +266,8 @@ def run_ours(args):
     n0 = L.rnr_launch_count()
     ms = timed(lambda i: step(views[i % nviews]), args.steps)
     launches = L.rnr_launch_count() - n0
+    if not args.no_graph:
+        launches = pipe.graph_launches * args.steps      # kernels of librnr_b200.so recorded in the replayed graph
     clk = clocks.stop() if rank == 0 else None
     value = world * args.steps / (ms / 1e3)
 
@@ -304,7 +312,7 @@ def run_ours(args):
         eng = [e for k, e in pipe.render_net.net._runner._engines.items() if e.need_backward][0]
         eng.timing = []
         for i in range(3):
-            step(views[i % nviews])
+            eager_step(views[i % nviews])
         torch.cuda.synchronize()
         rec, eng.timing = eng.timing, None
         t = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
@@ -362,6 +370,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -32,6 +32,7 @@ class TextureMapper(nn.Module):
         self.register_buffer('mipmap_level', torch.tensor(mipmap_level))
         self.register_buffer('apply_sh', torch.tensor(apply_sh))
         S0, C, L = _i(texture_size), _i(texture_num_ch), _i(mipmap_level)
+        self._apply_sh = bool(apply_sh)          # host copy of the ``apply_sh`` buffer: reading the buffer would sync every step
         self.textures = nn.ParameterList([])
         self.textures_size = []
         for lvl in range(L):
@@ -60,7 +61,12 @@ class TextureMapper(nn.Module):
     def forward(self, uv_map, sh_basis_map=None, sh_start_ch=3):
         """uv_map [N,H,W,2], sh_basis_map [N,H,W,9] -> [N,C,H,W]: sum over the mip levels of the bilinear sample at
         (u (S-1), (S-1) - v (S-1)); channels [sh_start_ch, sh_start_ch+9) multiplied by the SH basis (network.py:67-91)."""
-        return ops.texture_mapper(list(self.textures), uv_map, sh_basis_map, sh_start_ch, apply_sh=bool(self.apply_sh))
+        return ops.texture_mapper(list(self.textures), uv_map, sh_basis_map, sh_start_ch, apply_sh=self._apply_sh)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        if prefix + 'apply_sh' in state_dict:
+            self._apply_sh = bool(state_dict[prefix + 'apply_sh'])
 
     def flatten_mipmap(self, start_ch, end_ch):
         """Full-resolution sum of the (bilinearly up-sampled) mip levels for a channel slice (network.py:93-99)."""

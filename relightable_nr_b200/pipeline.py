@@ -72,7 +72,8 @@ class RNRPipeline:
     256x512 SH envmap) and the step of train_rnr.py:490-623."""
 
     def __init__(self, device='cuda', img_size=512, texture_size=512, texture_num_ch=24, mipmap_level=4, nf0=64, sh_lmax=10,
-                 num_l_samples=4096, lp_recon_h=256, lp_recon_w=512, lr=1e-3, seed=0, loss_weights=None, dropout=True):
+                 num_l_samples=4096, lp_recon_h=256, lp_recon_w=512, lr=1e-3, seed=0, loss_weights=None, dropout=True,
+                 capturable=False):
         self.device = torch.device(device)
         self.img_size = img_size
         torch.manual_seed(seed)
@@ -116,7 +117,7 @@ class RNRPipeline:
             self.l_samples_init_mask[::7] = False
         params = list(self.texture_mapper.parameters()) + list(self.lighting_model.parameters()) + list(self.render_net.parameters())
         # torch.optim.Adam like train_rnr.py:376; ``fused=True`` only picks torch's single-kernel multi-tensor implementation
-        self.optimizer = torch.optim.Adam(params, lr=lr, fused=True)
+        self.optimizer = torch.optim.Adam(params, lr=lr, fused=True, capturable=capturable)
         self.optimizer.zero_grad()
         self.lighting_idx = 0
 
@@ -170,6 +171,52 @@ class RNRPipeline:
             self.optimizer.step()
             self.optimizer.zero_grad()
         return loss.detach(), final.detach()
+
+    def make_graphed_step(self, example_view, grad_hook=None, warmup=3):
+        """Capture ``train_step`` (forward, four losses, backward, [grad_hook], Adam) into ONE CUDA graph.
+
+        Returns ``(step, static_view)``: ``step(view)`` copies the per-view maps into the static input buffers, replays the
+        graph and returns the (static) loss tensor.  ~400 kernel launches per iteration collapse into one graph launch, which
+        removes the Python / launch overhead that otherwise bounds the step once the kernels are fast.  ``grad_hook(params)``,
+        if given, runs between backward and the optimiser step inside the capture (the data-parallel all-reduce).  The
+        pipeline must have been built with ``capturable=True``."""
+        dev = self.device
+        static_view = {k: v.detach().clone() for k, v in example_view.items()}
+        params = [p for grp in self.optimizer.param_groups for p in grp['params']]
+
+        def body():
+            self.optimizer.zero_grad(set_to_none=True)
+            final, rays_lt, alpha_map = self.forward(static_view)
+            loss, _ = self.losses(static_view, final, rays_lt, alpha_map)
+            loss.backward()
+            if grad_hook is not None:
+                grad_hook(params)
+            self.optimizer.step()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):          # builds every plan / workspace and warms the allocator outside the capture
+                body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().rnr_launch_count()
+        with torch.cuda.graph(graph):
+            static_loss = body()
+        self._graph = graph
+        self.graph_launches = int(_lib.lib().rnr_launch_count() - n0)     # librnr_b200 kernels recorded in the graph
+
+        def step(view=None):
+            if view is not None and view is not static_view:
+                for k, v in view.items():
+                    static_view[k].copy_(v, non_blocking=True)
+            graph.replay()
+            return static_loss
+
+        return step, static_view
 
     @torch.no_grad()
     def render(self, view):
