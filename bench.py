@@ -257,6 +257,18 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    if args.profile_steps:
+        # ncu --profile-from-start off: only these eager steps are captured (tools/gpu_profile.sh)
+        for i in range(3):
+            eager_step(views[i % nviews])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        for i in range(args.profile_steps):
+            eager_step(views[i % nviews])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
+
     # ---- device-resident arm -----------------------------------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
         step(views[i % nviews])
@@ -370,6 +382,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-steps', type=int, default=0, help='run K eager steps between cudaProfilerStart/Stop and exit (for ncu)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -96,6 +96,10 @@ int  rnr_conv_plan_create(const rnr_conv_problem_t* prob, int impl, rnr_conv_pla
 void rnr_conv_plan_destroy(rnr_conv_plan_t* plan);
 int  rnr_conv_run(const rnr_conv_plan_t* plan, void* stream);
 int  rnr_conv_plan_tiles_m(const rnr_conv_plan_t* plan);
+/* profiling aid: device buffer [4 CTAs][4 roles][64] of clock64 stamps written by the halo kernel (NULL = off) */
+int  rnr_debug_set_trace(long long* buf);
+/* rows of `stats` the plan writes ([rows, 2, ldstats]; the caller sizes / zero-fills the buffer accordingly) */
+int  rnr_conv_plan_stat_rows(const rnr_conv_plan_t* plan);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Weight-gradient problem (autograd of Conv2d/ConvTranspose2d w.r.t. weight)                  */
@@ -132,10 +136,11 @@ int  rnr_wgrad_run(const rnr_wgrad_plan_t* plan, void* stream);
 /* ------------------------------------------------------------------------------------------ */
 /* Weight preparation: fp32 master weights -> 16-bit K-major GEMM matrices                     */
 /*   dst[r*ld + t*cpad + c] = src[r*s_r + c*s_c + tapoff[t]]   (0 for c >= nc or r >= nr)       */
+/*   chunked: dst[r*ld + ((c/64)*ntaps + t)*64 + c%64]  (taps of a 64-channel chunk adjacent)    */
 /* ------------------------------------------------------------------------------------------ */
 int rnr_weight_prep(const float* src, void* dst, int dst_dtype,
                     int nr, int nr_pad, int nc, int cpad, int ntaps,
-                    int64_t s_r, int64_t s_c, const int32_t* tapoff_dev, void* stream);
+                    int64_t s_r, int64_t s_c, const int32_t* tapoff_dev, int chunked, void* stream);
 
 /* batched form: all layers' matrices in ONE launch (the job table lives in a plan) */
 typedef struct {
@@ -145,6 +150,7 @@ typedef struct {
     int32_t      nr, nr_pad, nc, cpad, ntaps;
     int64_t      s_r, s_c;     /* element strides of row / column index in src; min(s_r, s_c) = taps per (row, col) pair <= 16 */
     int32_t      tapoff[16];   /* source tap index of each destination tap */
+    int32_t      chunked;      /* 0: columns [tap][cpad]; 1: columns [cpad/64][tap][64] (all taps of a 64-channel chunk adjacent) */
 } rnr_wprep_job_t;
 typedef struct rnr_wprep_plan rnr_wprep_plan_t;
 int  rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr_wprep_plan_t** plan);
@@ -184,12 +190,13 @@ int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* raw,
                       const float* drop, float slope,
                       void* gz, float* partials, int* T_out,
                       int N, int H, int W, int C, void* stream);
-/* finalize: dgamma, dbeta, and coefficients c1=mean(gz), c2=mean(gz*xhat) */
+/* finalize: dgamma, dbeta, c1 = mean(gz), c2 = mean(gz*xhat) and (optional) the fused per-channel coefficients
+ * coef [3,C] = (A, B, D) with  gamma*invstd*(gz - c1 - xhat*c2) == A*gz + B*raw + D                      */
 int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count,
-                        float* dgamma, float* dbeta, float* c1, float* c2, void* stream);
-/* pass 2 (in place): gz <- gamma*invstd*(gz - c1 - xhat*c2) */
-int rnr_bn_bwd_apply(void* gz, const float* raw, const float* gamma, const float* mean, const float* invstd,
-                     const float* c1, const float* c2, int N, int H, int W, int C, void* stream);
+                        float* dgamma, float* dbeta, float* c1, float* c2,
+                        const float* gamma, const float* mean, const float* invstd, float* coef, void* stream);
+/* pass 2 (in place): gz <- A*gz + B*raw + D */
+int rnr_bn_bwd_apply(void* gz, const float* raw, const float* coef, int N, int H, int W, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* layout glue of the module-level API (NCHW fp32 <-> channels-last 16-bit)                    */

@@ -56,7 +56,7 @@ class GSrc(C.Structure):
 class WPrepJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_dtype", C.c_int32), ("nr", C.c_int32), ("nr_pad", C.c_int32),
                 ("nc", C.c_int32), ("cpad", C.c_int32), ("ntaps", C.c_int32), ("s_r", C.c_int64), ("s_c", C.c_int64),
-                ("tapoff", C.c_int32 * 16)]
+                ("tapoff", C.c_int32 * 16), ("chunked", C.c_int32)]
 
 
 class RnrError(RuntimeError):
@@ -86,16 +86,18 @@ def lib():
         "rnr_conv_plan_create": [C.POINTER(ConvProblem), i32, C.POINTER(vp)],
         "rnr_conv_run": [vp, vp],
         "rnr_conv_plan_tiles_m": [vp],
+        "rnr_conv_plan_stat_rows": [vp],
+        "rnr_debug_set_trace": [vp],
         "rnr_wgrad_plan_create": [C.POINTER(WgradProblem), i32, C.POINTER(vp)],
         "rnr_wgrad_run": [vp, vp],
-        "rnr_weight_prep": [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, vp, vp],
+        "rnr_weight_prep": [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, vp, i32, vp],
         "rnr_wprep_plan_create": [C.POINTER(WPrepJob), i32, C.POINTER(vp)],
         "rnr_wprep_run": [vp, vp],
         "rnr_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp],
         "rnr_bn_act_fwd": [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
-        "rnr_bn_bwd_finalize": [vp, i32, i32, f64, vp, vp, vp, vp, vp],
-        "rnr_bn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "rnr_bn_bwd_finalize": [vp, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "rnr_bn_bwd_apply": [vp, vp, vp, i32, i32, i32, i32, vp],
         "rnr_pack_nchw_to_act": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "rnr_unpack_nhwc_to_nchw": [vp, vp, i32, i32, i32, i32, i32, vp],
         "rnr_tanh_bwd_pack": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -123,29 +123,31 @@ __device__ __forceinline__ void load8(const void* base, int64_t idx, int dtype, 
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const GSrcs srcs, const float* __restrict__ raw,
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const GSrcs srcs, const float* __restrict__ raw,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ drop, float slope,
                                      __nv_bfloat16* __restrict__ gz, float* __restrict__ partials,
                                      int N, int H, int W, int C, int ppb) {
-    // block b walks row segments (row = n*H + h, segment = ppb*SEG consecutive pixels); thread = (pixel lane pl, 8-channel vector cv)
-    extern __shared__ float s_red[];   // [2][C]
+    // block b walks row segments (row = n*H + h, segment = ppb consecutive pixels); thread = (pixel lane pl, 8-channel vector cv).
+    // Per-channel constants live in shared memory (not registers) so that 4 CTAs fit per SM; the second moment is accumulated
+    // as sum(g * (x - mean)) and scaled by invstd once per block.  Block-level reduction: every thread parks its 16 sums in
+    // shared memory [pl][2C] and 2C threads add the ppb rows (conflict-free), no atomics.
+    extern __shared__ float smem[];    // [3][C] scale / shift / mean, then [ppb][2C] per-thread sums
+    float* s_sc = smem;
+    float* s_sh = s_sc + C;
+    float* s_mu = s_sh + C;
+    float* s_part = s_mu + C;
     const int vpp = C >> 3;
     const int cv = threadIdx.x % vpp, pl = threadIdx.x / vpp;
     const int c = cv * 8;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; s_mu[i] = mean[i]; }
     __syncthreads();
     const int Hp = H + 2, Wp = W + 2;
     float sg[8], sgx[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) { sg[e] = 0.f; sgx[e] = 0.f; }
-    float sc[8], sh[8], mu[8], is[8];
-    if (pl < ppb) {
-#pragma unroll
-        for (int e = 0; e < 8; e++) { sc[e] = scale[c + e]; sh[e] = shift[c + e]; mu[e] = mean[c + e]; is[e] = invstd[c + e]; }
-    }
-    const int segs_per_row = (W + ppb - 1) / ppb;            // one segment = ppb pixels (one per pixel lane)
+    const int segs_per_row = (W + ppb - 1) / ppb;
     const int nseg = N * H * segs_per_row;
     if (pl < ppb)
     for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
@@ -154,36 +156,46 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const GSrcs srcs, co
         if (w >= W) continue;
         const int n = row / H, h = row - n * H;
         const int64_t pix = (int64_t)row * W + w;
+        const float4 r0 = __ldcs((const float4*)(raw + pix * C + c));
+        const float4 r1 = __ldcs((const float4*)(raw + pix * C + c + 4));
         float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const bool border = (h == 1) | (h == H - 2) | (w == 1) | (w == W - 2);
         for (int si = 0; si < srcs.n; si++) {
             const rnr_gsrc_t& s = srcs.s[si];
             if (s.fold) {
-                int rows[3], cols[3], nr = 0, nc = 0;
-                rows[nr++] = h + 1;
-                if (h == 1) rows[nr++] = 0;
-                if (h == H - 2) rows[nr++] = H + 1;
-                cols[nc++] = w + 1;
-                if (w == 1) cols[nc++] = 0;
-                if (w == W - 2) cols[nc++] = W + 1;
-                for (int a = 0; a < nr; a++)
-                    for (int b = 0; b < nc; b++)
-                        load8(s.ptr, (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * s.ld + s.c0 + c, s.dtype, g);
+                const int64_t center = (((int64_t)n * Hp + h + 1) * Wp + w + 1) * s.ld + s.c0 + c;
+                load8(s.ptr, center, s.dtype, g);
+                if (border) {
+                    // reflect halo: halo row 0 mirrors image row 1, halo row H+1 mirrors row H-2 (same for columns)
+                    const int dr = (h == 1) ? -(h + 1) : ((h == H - 2) ? 2 : 0);       // padded row offset of the mirrored copy
+                    const int dc = (w == 1) ? -(w + 1) : ((w == W - 2) ? 2 : 0);
+                    if (dr) load8(s.ptr, center + (int64_t)dr * Wp * s.ld, s.dtype, g);
+                    if (dc) load8(s.ptr, center + (int64_t)dc * s.ld, s.dtype, g);
+                    if (dr && dc) load8(s.ptr, center + ((int64_t)dr * Wp + dc) * s.ld, s.dtype, g);
+                    // (an image of height/width 3 has h == 1 == H-2: both halo rows mirror the same row)
+                    if (h == 1 && h == H - 2) {
+                        load8(s.ptr, center + (int64_t)2 * Wp * s.ld, s.dtype, g);
+                        if (dc) load8(s.ptr, center + ((int64_t)2 * Wp + dc) * s.ld, s.dtype, g);
+                    }
+                    if (w == 1 && w == W - 2) {
+                        load8(s.ptr, center + (int64_t)2 * s.ld, s.dtype, g);
+                        if (dr) load8(s.ptr, center + ((int64_t)dr * Wp + 2) * s.ld, s.dtype, g);
+                        if (h == 1 && h == H - 2) load8(s.ptr, center + ((int64_t)2 * Wp + 2) * s.ld, s.dtype, g);
+                    }
+                }
             } else {
                 load8(s.ptr, pix * s.ld + s.c0 + c, s.dtype, g);
             }
         }
-        const float4 r0 = *(const float4*)(raw + pix * C + c);
-        const float4 r1 = *(const float4*)(raw + pix * C + c + 4);
         const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const float z = r[e] * sc[e] + sh[e];
+            const float z = r[e] * s_sc[c + e] + s_sh[c + e];
             float gg = g[e] * (z > 0.f ? 1.f : slope);
             if (drop) gg *= drop[n * C + c + e];
-            const float xh = (r[e] - mu[e]) * is[e];
             sg[e] += gg;
-            sgx[e] += gg * xh;
+            sgx[e] += gg * (r[e] - s_mu[c + e]);
             o[e] = __float2bfloat16_rn(gg);
         }
         *(uint4*)(gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c) = *(const uint4*)o;
@@ -191,16 +203,22 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const GSrcs srcs, co
     if (pl < ppb) {
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            atomicAdd(&s_red[c + e], sg[e]);
-            atomicAdd(&s_red[C + c + e], sgx[e]);
+            s_part[pl * 2 * C + c + e] = sg[e];
+            s_part[pl * 2 * C + C + c + e] = sgx[e];
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partials[(int64_t)blockIdx.x * 2 * C + i] = s_red[i];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float a = 0.f;
+        for (int q = 0; q < ppb; q++) a += s_part[q * 2 * C + i];
+        if (i >= C) a *= invstd[i - C];
+        partials[(int64_t)blockIdx.x * 2 * C + i] = a;
+    }
 }
 
 __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __restrict__ partials, int T, int C, double count,
-                                       float* dgamma, float* dbeta, float* c1, float* c2) {
+                                       float* dgamma, float* dbeta, float* c1, float* c2, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd, float* coef) {
     __shared__ double s_s[16][33], s_q[16][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
@@ -219,13 +237,20 @@ __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __res
         if (dgamma) dgamma[c] = (float)q;
         if (c1) c1[c] = (float)(s / count);
         if (c2) c2[c] = (float)(q / count);
+        if (coef) {
+            // gz_out = gamma*invstd*(g - c1 - xhat*c2) = A*g + B*raw + D
+            const double gi = (double)gamma[c] * (double)invstd[c];
+            const double k1 = s / count, k2 = q / count;
+            coef[c] = (float)gi;
+            coef[C + c] = (float)(-gi * (double)invstd[c] * k2);
+            coef[2 * C + c] = (float)(gi * ((double)mean[c] * (double)invstd[c] * k2 - k1));
+        }
     }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ gz, const float* __restrict__ raw,
-                                    const float* __restrict__ gamma, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ c1,
-                                    const float* __restrict__ c2, int N, int H, int W, int C) {
+                                    const float* __restrict__ coef, int N, int H, int W, int C) {
+    // gz <- A*gz + B*raw + D with the per-channel coefficients of bn_bwd_finalize (3 vector loads instead of 5x8 scalars)
     const unsigned vpp = (unsigned)C >> 3;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)W * vpp) return;
@@ -240,14 +265,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __rest
     __nv_bfloat16* gb = (__nv_bfloat16*)&u;
     const float4 r0 = __ldcs((const float4*)(raw + pix * C + c));
     const float4 r1 = __ldcs((const float4*)(raw + pix * C + c + 4));
+    const float4 a0 = *(const float4*)(coef + c), a1 = *(const float4*)(coef + c + 4);
+    const float4 b0 = *(const float4*)(coef + C + c), b1 = *(const float4*)(coef + C + c + 4);
+    const float4 d0 = *(const float4*)(coef + 2 * C + c), d1 = *(const float4*)(coef + 2 * C + c + 4);
     const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const float is = invstd[c + e];
-        const float xh = (r[e] - mean[c + e]) * is;
-        const float g = __bfloat162float(gb[e]);
-        gb[e] = __float2bfloat16_rn(gamma[c + e] * is * (g - c1[c + e] - xh * c2[c + e]));
-    }
+    for (int e = 0; e < 8; e++) gb[e] = __float2bfloat16_rn(A[e] * __bfloat162float(gb[e]) + B[e] * r[e] + D[e]);
     *(uint4*)gp = u;
 }
 
@@ -287,27 +313,30 @@ extern "C" int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* 
     const int threads = vpp * ppb > 256 ? 256 : vpp * ppb;   // vpp<=256 guaranteed by C<=2048
     const int64_t nseg = (int64_t)N * H * rnr_cdiv(W, ppb);
     int T = rnr_cdiv(nseg, 4);
-    if (T > 148 * 8) T = 148 * 8;
+    if (T > 148 * 4) T = 148 * 4;
     if (T < 1) T = 1;
     if (T_out) *T_out = T;
-    bn_bwd_reduce_kernel<<<T, threads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+    bn_bwd_reduce_kernel<<<T, threads, (3 * C + (size_t)ppb * 2 * C) * sizeof(float), (cudaStream_t)stream>>>(
         gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, partials, N, H, W, C, ppb);
     RNR_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count, float* dgamma, float* dbeta, float* c1,
-                                   float* c2, void* stream) {
-    bn_bwd_finalize_kernel<<<rnr_cdiv(C, 32), 512, 0, (cudaStream_t)stream>>>(partials, T, C, count, dgamma, dbeta, c1, c2);
+                                   float* c2, const float* gamma, const float* mean, const float* invstd, float* coef,
+                                   void* stream) {
+    RNR_REQUIRE(!coef || (gamma && mean && invstd), "rnr_bn_bwd_finalize: coef needs gamma / mean / invstd");
+    bn_bwd_finalize_kernel<<<rnr_cdiv(C, 32), 512, 0, (cudaStream_t)stream>>>(partials, T, C, count, dgamma, dbeta, c1, c2, gamma, mean,
+                                                                            invstd, coef);
     RNR_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int rnr_bn_bwd_apply(void* gz, const float* raw, const float* gamma, const float* mean, const float* invstd,
-                                const float* c1, const float* c2, int N, int H, int W, int C, void* stream) {
+extern "C" int rnr_bn_bwd_apply(void* gz, const float* raw, const float* coef, int N, int H, int W, int C, void* stream) {
+    RNR_REQUIRE(C % 8 == 0, "rnr_bn_bwd_apply: C=%d must be a multiple of 8", C);
     RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_bwd_apply: N*H=%lld exceeds the grid limit", (long long)N * H);
     dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
-    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, gamma, mean, invstd, c1, c2, N, H, W, C);
+    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, coef, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }

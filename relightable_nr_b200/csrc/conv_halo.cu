@@ -1,0 +1,551 @@
+// tcgen05 implicit-GEMM convolution with SHARED-MEMORY HALO REUSE of the activation operand.
+//
+// conv_tc.cu loads one [128 pixel x 64 channel] A tile per (tap, channel chunk): a 3x3 convolution re-reads every input
+// pixel 9 times from L2, and the kernel runs at the L2->SM delivery limit (~6 TB/s on B200) with the tensor pipe 85 % idle
+// (profiles/r01_conv_tc_v0_raw.csv).  Here the K loop is re-grouped: for every (view, 64-channel chunk) ONE TMA box load
+// brings the whole halo tile [(16+ey) rows x (8+ex) pixels x 64 ch] (18x10 for 3x3, 17x9 for the 2x2 sub-convolutions of the
+// stride-2 / transposed layers) into shared memory, and each tap of the group is an MMA whose A descriptor simply starts
+// (dy*(8+ex)+dx) pixels further into that tile:
+//      start address += (dy*pitch + dx) * 128 B,   stride between 8-row groups (SBO) = pitch * 128 B,  SWIZZLE_128B.
+// A 16x8-pixel output tile makes every 8-row core-matrix group one image row, so the tap shift is a pure address offset
+// (the 128B-swizzle XOR is a function of the absolute shared-memory address for both the TMA write and the UMMA read).
+// L2->SM traffic of the A operand drops 9x -> 1.4x (3x3) and 4x -> 1.2x (2x2).
+//
+// Warp roles as in conv_tc.cu: warp 0 TMA producer (A-halo ring + B ring), warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue.  BatchNorm statistics are accumulated per CTA across all of its tiles and written once
+// (stats rows = gridDim.x), so the finalize kernel reads <= 148 rows instead of one per tile.
+#include "conv_internal.cuh"
+#include "tc_ptx.cuh"
+#include <cudaTypedefs.h>
+#include <algorithm>
+#include <stdlib.h>
+#include <vector>
+
+namespace {
+
+constexpr int kThreads = 384;          // warps 0-3: TMA / MMA / TMEM / idle; warps 4-11: epilogue
+constexpr int TH = 16, TW = 8;          // output tile (pixels): M = 128, one 8-row UMMA group per image row
+constexpr int kMaxGroups = 64;
+constexpr int kMaxTaps = 512;
+constexpr int kAStages = 2;
+
+struct HaloCfg {           // per-problem constants of the tap pattern (kernel parameter -> constant bank -> uniform registers)
+    int a_off[16];         // byte offset of tap k inside the halo tile (identical for every group)
+};
+
+struct HaloMaps {
+    CUtensorMap a[RNR_MAX_VIEWS];
+    CUtensorMap b;       // 3-D: T taps x bn rows x 64 ch in one box (cluster size 1)
+    CUtensorMap b2;      // 2-D: (bn / cluster size) rows x 64 ch, multicast slice of one tap
+};
+
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1); __expf / __fdividef keep the relative error ~1e-6 (tanhf costs ~40 instructions)
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(2.f * fminf(fmaxf(x, -15.f), 15.f));
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+__device__ long long* g_trace = nullptr;     // profiling only: [cta][role][64] clock64 stamps (set by rnr_debug_set_trace)
+__device__ __forceinline__ void trace(long long* base, int role, int& idx) {
+    if (base && idx < 64) base[role * 64 + idx++] = clock64();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, const HaloGroup* __restrict__ groups, int n_groups,
+                 const HaloTap* __restrict__ taps, int n_taps, int bn, int tiles_n, int b_stages, int a_stage_bytes,
+                 int b_stage_bytes, int pitch, int a_bytes, int dbg, int T, int cs, int gtaps, const HaloCfg hc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)kAStages * a_stage_bytes;
+    uint8_t* aux = smem_b + (size_t)b_stages * b_stage_bytes;
+    uint64_t* afull = (uint64_t*)aux;                    // [kAStages]
+    uint64_t* aempty = afull + kAStages;                 // [kAStages]
+    uint64_t* bfull = aempty + kAStages;                 // [b_stages]
+    uint64_t* bempty = bfull + 8;                        // [b_stages]
+    uint64_t* tfull_bar = bempty + 8;                    // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    HaloGroup* s_groups = (HaloGroup*)(tmem_slot + 4);               // [kMaxGroups]
+    HaloTap* s_taps = (HaloTap*)(s_groups + kMaxGroups);             // [kMaxTaps]
+    float* s_acc = (float*)(s_taps + kMaxTaps);                      // [2][512] per-CTA BatchNorm sums
+    float* s_stage = s_acc + 1024;                                   // [128][68] epilogue staging slab (16-byte aligned)
+    int64_t* s_rowoff = (int64_t*)(s_stage + 128 * 68);              // [128] output offset of each tile row
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // cluster of `cs` CTAs: same N tile, `cs` adjacent M tiles (rank r takes M tile mg*cs + r); the B (weight) stage is loaded once
+    // per cluster -- every CTA fetches 1/cs of its rows and multicasts them to all members.
+    const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
+    const int m_groups = (p.tiles_m + cs - 1) / cs;
+    const int total_tiles = m_groups * tiles_n;             // cluster-level work items
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    long long* tr = (g_trace && blockIdx.x < 4) ? g_trace + (size_t)blockIdx.x * 4 * 64 : nullptr;
+    int ti = 0;
+    if (threadIdx.x == 0) { int z = 0; trace(tr, 3, z); }
+
+    for (int i = threadIdx.x; i < n_groups; i += kThreads) s_groups[i] = groups[i];
+    for (int i = threadIdx.x; i < n_taps; i += kThreads) s_taps[i] = taps[i];
+    for (int i = threadIdx.x; i < 1024; i += kThreads) s_acc[i] = 0.f;
+
+    if (warp == 0 && lane == 0) {
+        for (int v = 0; v < RNR_MAX_VIEWS; v++)
+            if (p.views[v].ptr) tma_prefetch_desc(&maps.a[v]);
+        tma_prefetch_desc(&maps.b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kAStages; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < b_stages; s++) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], (uint32_t)cs); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    if (cs > 1) cluster_sync_all();          // peers' barriers must exist before anyone multicasts into them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        for (int t = cid; t < total_tiles; t += ncl) {
+            const int tile_m = (t / tiles_n) * cs + crank, tile_n = t % tiles_n;
+            const int tx_ = tile_m % p.tiles_x, ty_ = (tile_m / p.tiles_x) % p.tiles_y, n_ = tile_m / (p.tiles_x * p.tiles_y);
+            const int x0 = tx_ * TW, y0 = ty_ * TH, n0 = tile_n * bn;
+            if (lane == 0) trace(tr, 0, ti);
+            for (int g = 0; g < n_groups; g++) {
+                const HaloGroup G = s_groups[g];
+                mbar_wait(&aempty[as], aph ^ 1);
+                if (elect_one_sync()) {
+                    if (dbg & 16) mbar_arrive(&afull[as]);
+                    else {
+                        mbar_expect_tx(&afull[as], (uint32_t)a_bytes);
+                        tma_load_4d(&maps.a[G.view], &afull[as], smem_a + (size_t)as * a_stage_bytes, G.c0, x0 + G.ox, y0 + G.oy, n_);
+                    }
+                }
+                __syncwarp();
+                if (++as == kAStages) { as = 0; aph ^= 1; }
+                for (int k = 0; k < gtaps; k += T) {
+                    const int kblk = g * gtaps + k;
+                    mbar_wait(&bempty[bs], bph ^ 1);
+                    if (elect_one_sync()) {
+                        if (dbg & 4) mbar_arrive(&bfull[bs]);
+                        else {
+                            mbar_expect_tx(&bfull[bs], (uint32_t)(T * bn * 128));
+                            if (cs == 1) tma_load_3d(&maps.b, &bfull[bs], smem_b + (size_t)bs * b_stage_bytes, 0, n0, kblk);
+                            else {
+                                const int rows = bn / cs;             // my slice of every tap tile, multicast to the whole cluster
+                                for (int tt = 0; tt < T; tt++)
+                                    tma_load_2d_mc(&maps.b2, &bfull[bs], smem_b + (size_t)bs * b_stage_bytes + (size_t)tt * bn * 128 +
+                                                   (size_t)crank * rows * 128, (kblk + tt) * 64, n0 + crank * rows, cmask);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (++bs == b_stages) { bs = 0; bph ^= 1; }
+                }
+            }
+            if (lane == 0) trace(tr, 0, ti);
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
+        const uint32_t idesc = make_idesc(128, bn, p.ab_dtype, p.ab_dtype, 0, 0);
+        const uint32_t sbo = (uint32_t)pitch * 128u;
+        const uint32_t b_tap_bytes = (uint32_t)bn * 128u;
+        const uint32_t a_smem0 = smem_u32(smem_a), b_smem0 = smem_u32(smem_b);
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        int it = 0;
+        for (int t = cid; t < total_tiles; t += ncl, it++) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            if (lane == 0) trace(tr, 1, ti);
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+            uint32_t accum = 0;
+            for (int g = 0; g < n_groups; g++) {
+                mbar_wait(&afull[as], aph);
+                tc_fence_after();
+                if (g == 0 && lane == 0) trace(tr, 1, ti);
+                const uint32_t a_base = a_smem0 + (uint32_t)as * (uint32_t)a_stage_bytes;
+                for (int k = 0; k < gtaps; k += T) {
+                    mbar_wait(&bfull[bs], bph);
+                    tc_fence_after();
+                    const uint32_t b_base = b_smem0 + (uint32_t)bs * (uint32_t)b_stage_bytes;
+                    if (elect_one_sync()) {
+                        if (!(dbg & 8)) {
+                            for (int tt = 0; tt < T; tt++) {
+                                const uint64_t da = make_halo_desc(a_base + (uint32_t)hc.a_off[k + tt], sbo);
+                                const uint64_t db = make_kmajor_desc(b_base + (uint32_t)tt * b_tap_bytes, 64);
+#pragma unroll
+                                for (int kk = 0; kk < 4; kk++) {
+                                    umma_f16((dbg & 64) ? (d_tmem ^ ((uint32_t)(kk & 1) << 8)) : d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accum);
+                                    accum = 1;
+                                }
+                            }
+                        }
+                        if (cs == 1) umma_commit(&bempty[bs]); else umma_commit_mc(&bempty[bs], cmask);
+                    }
+                    __syncwarp();
+                    accum = 1;
+                    if (++bs == b_stages) { bs = 0; bph ^= 1; }
+                }
+                if (elect_one_sync()) umma_commit(&aempty[as]);
+                __syncwarp();
+                if (++as == kAStages) { as = 0; aph ^= 1; }
+            }
+            if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+            __syncwarp();
+            if (lane == 0) trace(tr, 1, ti);
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue (8 warps) =================
+        // A lone warp per scheduler issues one dependent instruction every ~4 cycles, so the epilogue is spread over 8 warps:
+        // warp w owns TMEM lanes 32*(w%4).. (hardware rule) and column half (w-4)/4 of each 64-column pass.
+        // Per pass: tcgen05.ld burst (32 columns per warp, one wait), bias / tanh in registers, the pass parked in shared
+        // memory [128 rows][68 floats]; then (a) full-row coalesced global stores (16 lanes per 256-byte row) and (b) per-column
+        // BatchNorm sums read column-wise from the staging tile.  The accumulator is handed back to the MMA warp as soon as
+        // its last pass is in registers.
+        const int q = warp & 3, hcol = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const int ry = r / TW, rx = r % TW;
+        const int e = threadIdx.x - 128;                       // 0..255
+        int it = 0;
+        int t3 = 1;
+        const bool tr4 = (warp == 4 && lane == 0);
+        for (int t = cid; t < total_tiles; t += ncl, it++) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int tile_m = (t / tiles_n) * cs + crank, tile_n = t % tiles_n;
+            const int tx_ = tile_m % p.tiles_x, ty_ = (tile_m / p.tiles_x) % p.tiles_y, n_ = tile_m / (p.tiles_x * p.tiles_y);
+            const int y = ty_ * TH + ry, x = tx_ * TW + rx, n0 = tile_n * bn;
+            const bool valid = (y < p.mY && x < p.mX && tile_m < p.tiles_m);
+            if (hcol == 0)      // output element offset of every tile row (-1: outside the image)
+                s_rowoff[r] = valid ? ((int64_t)n_ * p.out_sn + (int64_t)(y * p.out_my + p.out_py) * p.out_sy +
+                                       (int64_t)(x * p.out_mx + p.out_px) * p.out_sx) : (int64_t)-1;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            if (tr4) trace(tr, 2, ti);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+            for (int c0 = 0; c0 < ((dbg & 32) ? 0 : bn); c0 += 64) {
+                const int pw = min(64, bn - c0);                 // pass width (multiple of 16)
+                const int mc0 = hcol * 32;                       // my first column inside the pass
+                const int mw = max(0, min(32, pw - mc0));        // my width: 0, 16 or 32
+                uint32_t rv[32];
+                if (mw > 0) tmem_ld16(taddr + (uint32_t)(c0 + mc0), rv);
+                if (mw > 16) tmem_ld16(taddr + (uint32_t)(c0 + mc0 + 16), rv + 16);
+                tmem_ld_wait();
+                if (tr4 && it == 0) trace(tr, 3, t3);
+                if (c0 + 64 >= bn) {
+                    // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+                float* srow = s_stage + r * 68 + mc0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (j * 4 < mw) {
+                        float v[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            float f = __uint_as_float(rv[j * 4 + k]);
+                            const int co = n0 + c0 + mc0 + j * 4 + k;
+                            if (p.epi & RNR_EPI_BIAS) f += (co < p.cout) ? p.bias[co] : 0.f;
+                            if (p.epi & RNR_EPI_TANH) f = fast_tanh(f);
+                            v[k] = valid ? f : 0.f;
+                        }
+                        *(float4*)(srow + j * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tr4 && it == 0) trace(tr, 3, t3);
+                // ---- (a) coalesced stores: 256 threads sweep the [128 x pw] pass row-major ----
+                if (!(dbg & 1)) {
+                    const bool f32 = (p.out_dtype == RNR_F32);
+                    const int ppr = f32 ? (pw >> 2) : (pw >> 3);     // 16-byte pieces per row: 4 floats or 8 halves
+                    const int epp = f32 ? 4 : 8;
+                    const int npieces = 128 * ppr;
+                    const int sh = (ppr == 16) ? 4 : (ppr == 8) ? 3 : (ppr == 4) ? 2 : (ppr == 2) ? 1 : -1;
+                    for (int i = e; i < npieces; i += 256) {
+                        const int rr = sh >= 0 ? (i >> sh) : (i / ppr);
+                        const int pc = (i - rr * ppr) * epp;
+                        const int64_t rb = s_rowoff[rr];
+                        if (rb < 0) continue;
+                        const int64_t ob = rb + n0 + c0 + pc;
+                        const float4 v0 = *(const float4*)(s_stage + rr * 68 + pc);
+                        if (f32) {
+                            if (n0 + c0 + pc + 4 <= p.cout) *(float4*)((float*)p.out + ob) = v0;
+                            else {
+                                const float vv[4] = {v0.x, v0.y, v0.z, v0.w};
+                                for (int k = 0; k < 4; k++)
+                                    if (n0 + c0 + pc + k < p.cout) ((float*)p.out)[ob + k] = vv[k];
+                            }
+                        } else {
+                            const float4 v1 = *(const float4*)(s_stage + rr * 68 + pc + 4);
+                            const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                            if (n0 + c0 + pc + 8 <= p.cout) {
+                                __align__(16) unsigned short h[8];
+#pragma unroll
+                                for (int k = 0; k < 8; k++) h[k] = f2b16(vv[k], p.out_dtype);
+                                *(uint4*)((unsigned short*)p.out + ob) = *(const uint4*)h;
+                            } else {
+                                for (int k = 0; k < 8; k++)
+                                    if (n0 + c0 + pc + k < p.cout) st_out(p.out, ob + k, vv[k], p.out_dtype);
+                            }
+                        }
+                    }
+                }
+                if (tr4 && it == 0) trace(tr, 3, t3);
+                // ---- (b) BatchNorm partial sums: thread e sums column e%64 over rows [32*(e/64), +32) ----
+                if ((p.epi & RNR_EPI_STATS) && !(dbg & 2)) {
+                    const int col = e & 63, part = e >> 6;
+                    const int co = n0 + c0 + col;
+                    if (col < pw && co < p.cout && co < 512) {
+                        float a1 = 0.f, a2 = 0.f;
+                        const float* sp = s_stage + (part * 32) * 68 + col;
+#pragma unroll 8
+                        for (int k = 0; k < 32; k++) { const float v = sp[k * 68]; a1 += v; a2 += v * v; }
+                        atomicAdd(&s_acc[co], a1);
+                        atomicAdd(&s_acc[512 + co], a2);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // staging tile is free again
+                if (tr4 && it == 0) trace(tr, 3, t3);
+            }
+            if (dbg & 32) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            if (tr4) trace(tr, 2, ti);
+        }
+        if (p.epi & RNR_EPI_STATS) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int co = e; co < p.cout; co += 256) {
+                p.stats[((int64_t)blockIdx.x * 2 + 0) * p.ldstats + co] = s_acc[co];
+                p.stats[((int64_t)blockIdx.x * 2 + 1) * p.ldstats + co] = s_acc[512 + co];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (cs > 1) cluster_sync_all();          // no CTA may exit while a peer can still arrive on its barriers
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (PFN_cuTensorMapEncodeTiled_v12000)ptr;
+    return fn;
+}
+
+}  // namespace
+
+// Returns 0 and sets pl->halo = 1 when the problem fits the halo scheme, 0 with pl->halo = 0 when it does not
+// (the caller then uses the generic per-tap kernel), or an error code.
+int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
+    pl->halo = 0;
+    const char* env = getenv("RNR_CONV_HALO");
+    if (env && env[0] == '0') return 0;
+    if (prob->bk != 64) return 0;
+    if (prob->cout > 512 && (prob->epi & RNR_EPI_STATS)) return 0;
+    // ---- group the K-steps: maximal runs of consecutive K-steps on the same (view, channel chunk) ----
+    // (the engine emits the K-steps chunk-major, so all taps of a chunk are adjacent in K and in Wmat)
+    struct Key { int view, c0; };
+    std::vector<Key> keys;
+    std::vector<std::vector<int>> members;
+    for (int j = 0; j < prob->n_ksteps; j++) {
+        const rnr_kstep_t& ks = prob->ksteps[j];
+        if (keys.empty() || keys.back().view != ks.view || keys.back().c0 != ks.c0) { keys.push_back({ks.view, ks.c0}); members.emplace_back(); }
+        members.back().push_back(j);
+    }
+    if ((int)keys.size() > kMaxGroups || prob->n_ksteps > kMaxTaps) return 0;
+    int ex = 0, ey = 0;
+    std::vector<HaloGroup> groups(keys.size());
+    bool uniform = true;
+    for (size_t g = 0; g < keys.size(); g++) {
+        int dx0 = 1 << 20, dx1 = -(1 << 20), dy0 = 1 << 20, dy1 = -(1 << 20);
+        for (int j : members[g]) {
+            dx0 = std::min(dx0, (int)prob->ksteps[j].dx); dx1 = std::max(dx1, (int)prob->ksteps[j].dx);
+            dy0 = std::min(dy0, (int)prob->ksteps[j].dy); dy1 = std::max(dy1, (int)prob->ksteps[j].dy);
+        }
+        ex = std::max(ex, dx1 - dx0); ey = std::max(ey, dy1 - dy0);
+        groups[g].view = (int16_t)keys[g].view; groups[g].c0 = (int16_t)keys[g].c0;
+        groups[g].ox = (int16_t)dx0; groups[g].oy = (int16_t)dy0;
+        uniform &= (members[g].size() == members[0].size());
+    }
+    if (ex > 4 || ey > 4) return 0;
+    if (!uniform || members[0].size() > 16) return 0;       // every (view, chunk) group must carry the same <= 16 taps
+    const int pitch = TW + ex, rows = TH + ey;
+    std::vector<HaloTap> taps;
+    for (size_t g = 0; g < keys.size(); g++) {
+        groups[g].first_tap = (int16_t)taps.size();
+        groups[g].n_taps = (int16_t)members[g].size();
+        for (int j : members[g]) {
+            HaloTap t;
+            t.a_off = ((prob->ksteps[j].dy - groups[g].oy) * pitch + (prob->ksteps[j].dx - groups[g].ox)) * 128;
+            t.wcol = j * 64;
+            taps.push_back(t);
+        }
+    }
+    // the halo kernel addresses tap k of every group through one offset table: all groups must share the tap pattern
+    for (size_t g = 0; g < keys.size(); g++)
+        for (size_t k = 0; k < members[g].size(); k++)
+            if (taps[groups[g].first_tap + k].a_off != taps[k].a_off) return 0;
+    for (size_t k = 0; k < 16; k++) pl->halo_a_off[k] = k < members[0].size() ? taps[k].a_off : 0;
+    pl->halo_gtaps = (int)members[0].size();
+    // ---- tiling ----
+    ConvParams& p = pl->p;
+    p.th = TH; p.tw = TW;
+    p.tiles_y = rnr_cdiv(prob->mY, TH); p.tiles_x = rnr_cdiv(prob->mX, TW);
+    p.tiles_m = p.tiles_y * p.tiles_x * prob->mN;
+    int bn = prob->n_rows_w < 256 ? prob->n_rows_w : 256;
+    if (prob->n_rows_w > 256 && prob->n_rows_w % 256 != 0) {
+        for (bn = 256; bn >= 16; bn -= 16)
+            if (prob->n_rows_w % bn == 0) break;
+    }
+    int tiles_n = rnr_cdiv(prob->n_rows_w, bn);
+    while (bn > 64 && bn % 32 == 0 && p.tiles_m * tiles_n < 148) { bn /= 2; tiles_n = rnr_cdiv(prob->n_rows_w, bn); }
+    pl->bn = bn;
+    pl->tiles_n = tiles_n;
+    const int a_stage = ((rows * pitch * 128) + 1023) / 1024 * 1024;
+    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 1024 * 4 + 128 * 68 * 4 + 128 * 8;
+    const int budget = 212 * 1024 - aux - kAStages * a_stage;
+    // taps per B stage: one mbarrier hand-shake (~400 cycles of latency in the single-thread producer / issuer loops) must
+    // cover enough tensor work, so a stage holds T taps = T*4 MMAs; T divides the taps of a group
+    const int gtaps = uniform ? (int)members[0].size() : 1;
+    int T = 1;
+    for (int cand = gtaps; cand >= 1; cand--) {
+        if (gtaps % cand) continue;
+        const int stage = cand * bn * 128;
+        if (stage <= 72 * 1024 && budget / stage >= 2) { T = cand; break; }
+    }
+    const int b_stage = T * bn * 128;                      // multiple of 1024 (bn is a multiple of 16 -> 2048 B)
+    int b_stages = budget / b_stage;
+    if (b_stages > 8) b_stages = 8;
+    if (b_stages < 2) return 0;
+    pl->halo_T = T;
+    // cluster size: weights are the dominant L2->SM stream; share them across `cs` CTAs working on adjacent M tiles
+    int cs = 1;
+    {
+        const char* ce = getenv("RNR_CONV_CLUSTER");
+        const int want = ce ? atoi(ce) : 2;
+        for (int c = want; c >= 2; c >>= 1)
+            if ((bn / c) % 8 == 0 && bn % c == 0 && p.tiles_m >= 2 * c) { cs = c; break; }
+    }
+    pl->halo_cs = cs;
+    pl->stages = b_stages;
+    pl->halo_a_stage = a_stage;
+    pl->halo_b_stage = b_stage;
+    pl->halo_pitch = pitch;
+    pl->halo_a_bytes = rows * pitch * 128;
+    pl->smem_bytes = kAStages * a_stage + b_stages * b_stage + aux + 1024;
+    {
+        const int groups_total = rnr_cdiv(p.tiles_m, cs) * tiles_n;
+        const int max_clusters = 148 / cs;
+        pl->grid = (groups_total < max_clusters ? groups_total : max_clusters) * cs;
+    }
+    // ---- tensor maps ----
+    auto enc = encode_fn();
+    RNR_REQUIRE(enc, "cuTensorMapEncodeTiled not available from the driver");
+    for (int i = 0; i < prob->n_views; i++) {
+        int rc = rnr_encode_view_map(&pl->tmap_a[i], prob->views[i], prob->ab_dtype, 64, pitch, rows);
+        if (rc) return rc;
+    }
+    {
+        // Wmat [n_rows, ldw] viewed as (64 channels, n rows, K blocks): one box = T consecutive K blocks = T [bn x 64] tiles
+        cuuint64_t gdim[3] = {64, (cuuint64_t)prob->n_rows_w, (cuuint64_t)(p.ldw / 64)};
+        cuuint64_t gstr[2] = {(cuuint64_t)p.ldw * 2, 128};
+        cuuint32_t box[3] = {64u, (cuuint32_t)bn, (cuuint32_t)T};
+        cuuint32_t estr[3] = {1, 1, 1};
+        RNR_REQUIRE(gstr[0] % 16 == 0 && ((uintptr_t)prob->wmat & 15) == 0, "conv_halo: Wmat is not 16-byte aligned");
+        CUresult r = enc(&pl->tmap_b, prob->ab_dtype == RNR_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                         3, const_cast<void*>(prob->wmat), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RNR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(Wmat 3-D) failed with CUresult %d", (int)r);
+    }
+    if (cs > 1) {
+        cuuint64_t gdim[2] = {(cuuint64_t)p.ldw, (cuuint64_t)prob->n_rows_w};
+        cuuint64_t gstr[1] = {(cuuint64_t)p.ldw * 2};
+        cuuint32_t box[2] = {64u, (cuuint32_t)(bn / cs)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&pl->tmap_b2, prob->ab_dtype == RNR_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                         2, const_cast<void*>(prob->wmat), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RNR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(Wmat slice) failed with CUresult %d", (int)r);
+    } else {
+        pl->tmap_b2 = pl->tmap_b;
+    }
+    // ---- device tables ----
+    RNR_CHECK(cudaMalloc(&pl->d_groups, sizeof(HaloGroup) * groups.size()));
+    RNR_CHECK(cudaMemcpy(pl->d_groups, groups.data(), sizeof(HaloGroup) * groups.size(), cudaMemcpyHostToDevice));
+    RNR_CHECK(cudaMalloc(&pl->d_taps, sizeof(HaloTap) * taps.size()));
+    RNR_CHECK(cudaMemcpy(pl->d_taps, taps.data(), sizeof(HaloTap) * taps.size(), cudaMemcpyHostToDevice));
+    pl->n_groups = (int)groups.size();
+    pl->n_taps = (int)taps.size();
+    static bool attr_set = false;
+    if (!attr_set) {
+        RNR_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    { const char* d = getenv("RNR_CONV_DBG"); pl->dbg = d ? atoi(d) : 0; }
+    pl->halo = 1;
+    return 0;
+}
+
+extern "C" int rnr_debug_set_trace(long long* buf) {
+    RNR_CHECK(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+    return 0;
+}
+
+int rnr_conv_halo_run(const rnr_conv_plan* pl, cudaStream_t stream) {
+    HaloMaps maps;
+    memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
+    maps.b = pl->tmap_b;
+    maps.b2 = pl->tmap_b2;
+    HaloCfg hc;
+    memcpy(hc.a_off, pl->halo_a_off, sizeof(hc.a_off));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(pl->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl->halo_cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RNR_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel, maps, pl->p, (const HaloGroup*)pl->d_groups, pl->n_groups,
+                                 (const HaloTap*)pl->d_taps, pl->n_taps, pl->bn, pl->tiles_n, pl->stages, pl->halo_a_stage,
+                                 pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc));
+    rnr_count_launch();
+    return 0;
+}

@@ -21,6 +21,14 @@ struct ConvParams {
     int ldstats;
 };
 
+struct HaloGroup {       // one (view, 64-channel chunk): a single halo box load serves all of its taps
+    int16_t view, c0, ox, oy, first_tap, n_taps;
+};
+struct HaloTap {
+    int32_t a_off;       // byte offset of the tap's first pixel inside the halo tile
+    int32_t wcol;        // first Wmat column (element index) of this K-step
+};
+
 struct rnr_conv_plan {
     ConvParams p;
     int impl;
@@ -33,6 +41,16 @@ struct rnr_conv_plan {
     int stages;
     int smem_bytes;
     int grid;
+    // halo-reuse kernel (conv_halo.cu)
+    int halo;
+    int halo_a_stage, halo_b_stage, halo_pitch, halo_a_bytes, halo_T, halo_cs;
+    CUtensorMap tmap_b2;
+    int halo_gtaps;
+    int halo_a_off[16];
+    HaloGroup* d_groups;
+    HaloTap* d_taps;
+    int n_groups, n_taps;
+    int dbg;             // RNR_CONV_DBG ablation bits (profiling only)
 };
 
 struct WgradParams {
@@ -67,5 +85,7 @@ struct rnr_wgrad_plan {
 int rnr_encode_view_map(CUtensorMap* map, const rnr_view_t& v, int dtype, int box_c, int box_x, int box_y);
 int rnr_conv_tc_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* prob);
 int rnr_conv_tc_run(const rnr_conv_plan* plan, cudaStream_t stream);
+int rnr_conv_halo_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* prob);
+int rnr_conv_halo_run(const rnr_conv_plan* plan, cudaStream_t stream);
 int rnr_wgrad_tc_prepare(rnr_wgrad_plan* plan, const rnr_wgrad_problem_t* prob);
 int rnr_wgrad_tc_run(const rnr_wgrad_plan* plan, cudaStream_t stream);

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradParams p, co
 
 __global__ void weight_prep_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_dtype,
                                    int nr, int nr_pad, int nc, int cpad, int ntaps,
-                                   int64_t s_r, int64_t s_c, const int32_t* __restrict__ tapoff) {
+                                   int64_t s_r, int64_t s_c, const int32_t* __restrict__ tapoff, int chunked) {
     const int64_t total = (int64_t)nr_pad * ntaps * cpad;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cpad);
@@ -219,7 +219,8 @@ __global__ void weight_prep_kernel(const float* __restrict__ src, void* __restri
         const int r = (int)(i / ((int64_t)cpad * ntaps));
         float v = 0.f;
         if (r < nr && c < nc) v = src[r * s_r + c * s_c + tapoff[t]];
-        ((unsigned short*)dst)[i] = f2b16(v, dst_dtype);
+        const int64_t col = chunked ? ((int64_t)((c >> 6) * ntaps + t) * 64 + (c & 63)) : ((int64_t)t * cpad + c);
+        ((unsigned short*)dst)[(int64_t)r * ntaps * cpad + col] = f2b16(v, dst_dtype);
     }
 }
 
@@ -258,7 +259,8 @@ extern "C" int rnr_conv_plan_create(const rnr_conv_problem_t* prob, int impl, rn
     if (e != cudaSuccess) { rnr_set_error("rnr_conv_plan_create: %s", cudaGetErrorString(e)); delete pl; return (int)e; }
     p.ksteps = pl->d_ksteps;
     if (impl == 1) {
-        int rc = rnr_conv_tc_prepare(pl, prob);
+        int rc = rnr_conv_halo_prepare(pl, prob);            // shared-memory halo reuse when the problem fits ...
+        if (rc == 0 && !pl->halo) rc = rnr_conv_tc_prepare(pl, prob);   // ... else one A tile per tap
         if (rc != 0) { cudaFree(pl->d_ksteps); delete pl; return rc; }
     }
     *out = pl;
@@ -268,14 +270,22 @@ extern "C" int rnr_conv_plan_create(const rnr_conv_problem_t* prob, int impl, rn
 extern "C" void rnr_conv_plan_destroy(rnr_conv_plan_t* plan) {
     if (!plan) return;
     cudaFree(plan->d_ksteps);
+    if (plan->d_groups) cudaFree(plan->d_groups);
+    if (plan->d_taps) cudaFree(plan->d_taps);
     delete plan;
+}
+
+/* rows of the BatchNorm partial-sum buffer this plan writes: one per M tile (SIMT / per-tap kernel) or one per CTA (halo kernel) */
+extern "C" int rnr_conv_plan_stat_rows(const rnr_conv_plan_t* plan) {
+    if (!plan) return 0;
+    return (plan->impl == 1 && plan->halo) ? plan->grid : plan->p.tiles_m;
 }
 
 extern "C" int rnr_conv_plan_tiles_m(const rnr_conv_plan_t* plan) { return plan ? plan->p.tiles_m : 0; }
 
 extern "C" int rnr_conv_run(const rnr_conv_plan_t* plan, void* stream) {
     RNR_REQUIRE(plan, "rnr_conv_run: null plan");
-    if (plan->impl == 1) return rnr_conv_tc_run(plan, (cudaStream_t)stream);
+    if (plan->impl == 1) return plan->halo ? rnr_conv_halo_run(plan, (cudaStream_t)stream) : rnr_conv_tc_run(plan, (cudaStream_t)stream);
     dim3 grid(plan->p.tiles_m, rnr_cdiv(plan->p.cout, SBN));
     conv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan->p);
     RNR_LAUNCH_CHECK();
@@ -343,12 +353,13 @@ extern "C" int rnr_wgrad_run(const rnr_wgrad_plan_t* plan, void* stream) {
 }
 
 extern "C" int rnr_weight_prep(const float* src, void* dst, int dst_dtype, int nr, int nr_pad, int nc, int cpad,
-                               int ntaps, int64_t s_r, int64_t s_c, const int32_t* tapoff_dev, void* stream) {
+                               int ntaps, int64_t s_r, int64_t s_c, const int32_t* tapoff_dev, int chunked, void* stream) {
+    RNR_REQUIRE(!chunked || cpad % 64 == 0, "rnr_weight_prep: chunk-major layout needs cpad %% 64 == 0");
     RNR_REQUIRE(dst_dtype == RNR_F16 || dst_dtype == RNR_BF16, "rnr_weight_prep: dst must be 16-bit");
     const int64_t total = (int64_t)nr_pad * ntaps * cpad;
     int blocks = rnr_cdiv(total, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    weight_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, dst_dtype, nr, nr_pad, nc, cpad, ntaps, s_r, s_c, tapoff_dev);
+    weight_prep_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, dst_dtype, nr, nr_pad, nc, cpad, ntaps, s_r, s_c, tapoff_dev, chunked);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -7,6 +7,8 @@
 // (contiguous along whichever of row/column is the inner dimension of the parameter tensor) and the 16-bit
 // destination (contiguous along the column = input-channel dimension) move in full sectors.
 //   dst[r*ntaps*cpad + t*cpad + c] = src[r*s_r + c*s_c + tapoff[t]]     (0 for r >= nr or c >= nc)
+// or, chunk-major (all taps of a 64-channel chunk adjacent in K, the order the halo kernel consumes):
+//   dst[r*ntaps*cpad + ((c/64)*ntaps + t)*64 + c%64]
 // Replaces the per-layer weight reshapes that cuDNN does inside nn.Conv2d / nn.ConvTranspose2d
 // (pytorch_prototyping/pytorch_prototyping.py:112-115,155-160,242-264).
 #include "common.cuh"
@@ -19,45 +21,46 @@ constexpr int RB = 8, CB = 64, MAXT = 16;
 struct WJob {
     const float* src;
     void* dst;
-    int32_t dtype, nr, nr_pad, nc, cpad, ntaps, ts, tiles_c;
+    int32_t dtype, nr, nr_pad, nc, cpad, ntaps, ts, tiles_c, chunked;
     int64_t s_r, s_c;
     int32_t tapoff[MAXT];
     int32_t blk0, nblk;
 };
 
-__global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict__ jobs, int njobs) {
-    __shared__ float tile[RB * CB * (MAXT + 1)];
-    __shared__ WJob J;
-    // locate the job of this block (block offsets are ascending)
-    if (threadIdx.x == 0) {
-        int lo = 0, hi = njobs - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].blk0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-        }
-        J = jobs[lo];
-    }
-    __syncthreads();
+__global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict__ jobs, const int* __restrict__ blk2job) {
+    __shared__ float tile[RB * CB * MAXT];
+    const WJob& J = jobs[blk2job[blockIdx.x]];      // every thread reads the (L1-broadcast) job record directly
     const int local = blockIdx.x - J.blk0;
     const int r0 = (local / J.tiles_c) * RB, c0 = (local % J.tiles_c) * CB;
-    const int ts = J.ts, tsp = ts + 1;
+    const int ts = J.ts;
+    const bool pow2 = (ts == 16);                                        // 4x4 kernels: XOR-swizzle the tap index (bank conflicts)
+    const unsigned magic = (65536u + ts - 1) / ts;                        // j / ts for j < 4096 without an integer division
     const int nrt = min(RB, J.nr - r0), nct = min(CB, J.nc - c0);       // valid rows / cols of this tile (may be <= 0)
+    // smem element (rr, cc, tt) lives at (rr*CB + cc)*ts + (pow2 ? tt ^ (cc & 15) : tt)
     if (nrt > 0 && nct > 0) {
         if (J.s_c < J.s_r) {
-            // columns are the inner dimension: for each row, [nct * ts] floats are contiguous
+            // columns are the inner dimension: for each row, [nct * ts] floats are contiguous -> straight copy
             const int run = nct * ts;
-            for (int i = threadIdx.x; i < nrt * run; i += 256) {
-                const int rr = i / run, j = i - rr * run;
-                const int cc = j / ts, tt = j - cc * ts;
-                tile[(rr * CB + cc) * tsp + tt] = J.src[(int64_t)(r0 + rr) * J.s_r + (int64_t)c0 * J.s_c + j];
+            for (int rr = 0; rr < nrt; rr++) {
+                const float* sp = J.src + (int64_t)(r0 + rr) * J.s_r + (int64_t)c0 * J.s_c;
+                float* tp = tile + rr * CB * ts;
+                for (int j = threadIdx.x; j < run; j += 256) {
+                    int d = j;
+                    if (pow2) { const int cc = j >> 4; d = (cc << 4) | ((j & 15) ^ (cc & 15)); }
+                    tp[d] = sp[j];
+                }
             }
         } else {
             // rows are the inner dimension: for each column, [nrt * ts] floats are contiguous
             const int run = nrt * ts;
-            for (int i = threadIdx.x; i < nct * run; i += 256) {
-                const int cc = i / run, j = i - cc * run;
-                const int rr = j / ts, tt = j - rr * ts;
-                tile[(rr * CB + cc) * tsp + tt] = J.src[(int64_t)(c0 + cc) * J.s_c + (int64_t)r0 * J.s_r + j];
+            for (int cc = threadIdx.x >> 5; cc < nct; cc += 8) {
+                const float* sp = J.src + (int64_t)(c0 + cc) * J.s_c + (int64_t)r0 * J.s_r;
+                for (int j = threadIdx.x & 31; j < run; j += 32) {
+                    const int rr = pow2 ? (j >> 4) : (int)(((unsigned)j * magic) >> 16);
+                    int tt = j - rr * ts;
+                    if (pow2) tt ^= (cc & 15);
+                    tile[(rr * CB + cc) * ts + tt] = sp[j];
+                }
             }
         }
     }
@@ -65,14 +68,21 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict
     const int ncw = min(CB, J.cpad - c0);
     const int nrw = min(RB, J.nr_pad - r0);
     unsigned short* dst = (unsigned short*)J.dst;
-    for (int i = threadIdx.x; i < nrw * J.ntaps * CB; i += 256) {
-        const int cc = i % CB;
-        const int rt = i / CB;
-        const int t = rt % J.ntaps, rr = rt / J.ntaps;
-        if (cc >= ncw) continue;
-        float v = 0.f;
-        if (rr < nrt && cc < nct) v = tile[(rr * CB + cc) * tsp + J.tapoff[t]];
-        dst[((int64_t)(r0 + rr) * J.ntaps + t) * J.cpad + c0 + cc] = f2b16(v, J.dtype);
+    const int cc = threadIdx.x & (CB - 1), q = threadIdx.x >> 6;          // 64 columns x 4 tap lanes
+    if (cc < ncw) {
+        for (int rr = 0; rr < nrw; rr++) {
+            for (int t = q; t < J.ntaps; t += 4) {
+                float v = 0.f;
+                if (rr < nrt && cc < nct) {
+                    int tt = J.tapoff[t];
+                    if (pow2) tt ^= (cc & 15);
+                    v = tile[(rr * CB + cc) * ts + tt];
+                }
+                const int c = c0 + cc;
+                const int64_t col = J.chunked ? ((int64_t)((c >> 6) * J.ntaps + t) * 64 + (c & 63)) : ((int64_t)t * J.cpad + c);
+                dst[(int64_t)(r0 + rr) * J.ntaps * J.cpad + col] = f2b16(v, J.dtype);
+            }
+        }
     }
 }
 
@@ -80,6 +90,7 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict
 
 struct rnr_wprep_plan {
     WJob* d_jobs = nullptr;
+    int* d_blk2job = nullptr;
     int njobs = 0;
     int nblocks = 0;
 };
@@ -97,7 +108,8 @@ extern "C" int rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr
         WJob& d = h[i];
         d.src = s.src; d.dst = s.dst; d.dtype = s.dst_dtype;
         d.nr = s.nr; d.nr_pad = s.nr_pad; d.nc = s.nc; d.cpad = s.cpad; d.ntaps = s.ntaps; d.ts = (int)ts;
-        d.s_r = s.s_r; d.s_c = s.s_c;
+        d.s_r = s.s_r; d.s_c = s.s_c; d.chunked = s.chunked;
+        RNR_REQUIRE(!s.chunked || s.cpad % 64 == 0, "weight prep: chunk-major layout needs cpad %% 64 == 0 (got %d)", s.cpad);
         for (int t = 0; t < s.ntaps; t++) {
             RNR_REQUIRE(s.tapoff[t] >= 0 && s.tapoff[t] < ts, "weight prep: tap offset %d outside [0,%lld)", s.tapoff[t], (long long)ts);
             d.tapoff[t] = s.tapoff[t];
@@ -112,6 +124,11 @@ extern "C" int rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr
     p->nblocks = blk;
     RNR_CHECK(cudaMalloc(&p->d_jobs, sizeof(WJob) * njobs));
     RNR_CHECK(cudaMemcpy(p->d_jobs, h.data(), sizeof(WJob) * njobs, cudaMemcpyHostToDevice));
+    std::vector<int> b2j(blk);
+    for (int i = 0; i < njobs; i++)
+        for (int b = 0; b < h[i].nblk; b++) b2j[h[i].blk0 + b] = i;
+    RNR_CHECK(cudaMalloc(&p->d_blk2job, sizeof(int) * blk));
+    RNR_CHECK(cudaMemcpy(p->d_blk2job, b2j.data(), sizeof(int) * blk, cudaMemcpyHostToDevice));
     *out = p;
     return 0;
 }
@@ -119,12 +136,13 @@ extern "C" int rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr
 extern "C" void rnr_wprep_plan_destroy(rnr_wprep_plan_t* p) {
     if (!p) return;
     cudaFree(p->d_jobs);
+    cudaFree(p->d_blk2job);
     delete p;
 }
 
 extern "C" int rnr_wprep_run(const rnr_wprep_plan_t* p, void* stream) {
     RNR_REQUIRE(p, "rnr_wprep_run: null plan");
-    wprep_batch_kernel<<<p->nblocks, 256, 0, (cudaStream_t)stream>>>(p->d_jobs, p->njobs);
+    wprep_batch_kernel<<<p->nblocks, 256, 0, (cudaStream_t)stream>>>(p->d_jobs, p->d_blk2job);
     RNR_LAUNCH_CHECK();
     return 0;
 }

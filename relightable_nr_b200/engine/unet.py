@@ -137,6 +137,7 @@ class _WPrep:
     s_c: int
     tapoff: torch.Tensor    # int32 device
     tapoff_host: Tuple[int, ...] = ()
+    chunked: int = 0        # 1: Wmat columns are [chunk of 64 channels][tap][64] (halo-kernel order)
 
 
 @dataclass
@@ -151,6 +152,7 @@ class _LayerState:
     shift: Optional[torch.Tensor] = None
     c1: Optional[torch.Tensor] = None
     c2: Optional[torch.Tensor] = None
+    coef: Optional[torch.Tensor] = None
     bwd_partials: Optional[torch.Tensor] = None
     fwd_plans: List[_Plan] = field(default_factory=list)
     dgrad_plans: List[_Plan] = field(default_factory=list)
@@ -232,6 +234,7 @@ class UNetEngine:
                     self.acts_w[sp.dst] = HaloTensor(N, Ho, Wo, sp.cout, gdt, dev, zero=True)
                 for nm in ('mean', 'invstd', 'scale', 'shift', 'c1', 'c2'):
                     setattr(st, nm, self._alloc((sp.cout,), torch.float32, zero=True))
+                st.coef = self._alloc((3 * sp.cout,), torch.float32, zero=True)
                 st.invstd.fill_(1.0)
                 st.scale.fill_(1.0)
             if self.need_backward:
@@ -291,6 +294,13 @@ class UNetEngine:
                 return bk
         raise ValueError('channel counts %s must be multiples of 16' % (channel_counts,))
 
+    @staticmethod
+    def _order_ksteps(taps, C, bk, chunked):
+        """K-steps of a single-source problem: taps = [(view, dx, dy)]; chunk-major when ``chunked`` else tap-major."""
+        if chunked:
+            return [(v, c0, dx, dy) for c0 in range(0, C, bk) for (v, dx, dy) in taps]
+        return [(v, c0, dx, dy) for (v, dx, dy) in taps for c0 in range(0, C, bk)]
+
     def _tapoff(self, offs):
         t = torch.tensor(offs, dtype=torch.int32, device=self.device)
         t.host = tuple(int(o) for o in offs)
@@ -306,6 +316,7 @@ class UNetEngine:
             j.dst = w.dst.data_ptr()
             j.dst_dtype, j.nr, j.nr_pad, j.nc, j.cpad, j.ntaps = w.dtype, w.nr, w.nr_pad, w.nc, w.cpad, w.ntaps
             j.s_r, j.s_c = w.s_r, w.s_c
+            j.chunked = w.chunked
             for t, o in enumerate(w.tapoff.host):
                 j.tapoff[t] = o
         h = C.c_void_p()
@@ -336,9 +347,19 @@ class UNetEngine:
         elif sp.bn_key is not None:
             epi = EPI_STATS
 
+        chunked = 1 if bk == 64 else 0
+
         def ksteps_for(taps):
-            """taps: list of (view index per source -> list, dx, dy)"""
+            """taps: list of (view index per source -> list, dx, dy).  K-step j multiplies Wmat columns [j*bk, (j+1)*bk).
+            bk == 64: chunk-major order (all taps of a 64-channel chunk adjacent -- the halo kernel loads that chunk's
+            input tile once and walks the taps inside shared memory); otherwise tap-major."""
             ks = []
+            if chunked:
+                for si in range(len(srcs)):
+                    for c0 in range(0, cpads[si], bk):
+                        for (vidx, dx, dy) in taps:
+                            ks.append((vidx[si], c0, dx, dy))
+                return ks
             for (vidx, dx, dy) in taps:
                 for si in range(len(srcs)):
                     for c0 in range(0, cpads[si], bk):
@@ -352,45 +373,48 @@ class UNetEngine:
             tapoffs = [kh * 3 + kw for kh in range(3) for kw in range(3)]
             wm = self._alloc((n_rows, 9 * cpad_tot), adt_t, zero=True)
             st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 9,
-                                       cin_tot * 9, 9, self._tapoff(tapoffs)))
+                                       cin_tot * 9, 9, self._tapoff(tapoffs), chunked=chunked))
             th, tw = tile_shape(Wo)
-            tiles = N * -(-Ho // th) * -(-Wo // tw)
+            tiles = max(N * -(-Ho // th) * -(-Wo // tw), 148)      # rows of the partial-sum buffer: one per tile or per CTA
             if epi & EPI_STATS:
                 st.stats = self._alloc((tiles, 2, cout), torch.float32, zero=True)
-                st.n_stat_tiles = tiles
             st.fwd_plans.append(self._conv_problem(
                 views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32,
                 (Ho * Wo * ld_out, Wo * ld_out, ld_out), (1, 1, 0, 0), epi, bias_t, st.stats, cout, self.impl))
+            st.n_stat_tiles = self.L.rnr_conv_plan_stat_rows(st.fwd_plans[-1].h)
         elif sp.kind == 'c4s2':
             views = []
             for t in srcs:
                 views += [t.parity(p, q) for p in range(2) for q in range(2)]
             taps, tapoffs = [], []
-            for kh in range(4):
-                for kw in range(4):
-                    a, p, b, q = kh // 2, kh % 2, kw // 2, kw % 2
-                    taps.append(([si * 4 + p * 2 + q for si in range(len(srcs))], b, a))
-                    tapoffs.append(kh * 4 + kw)
+            for p in range(2):                      # parity-major: the 4 taps reading one parity view are adjacent
+                for q in range(2):
+                    for a in range(2):
+                        for b in range(2):
+                            kh, kw = 2 * a + p, 2 * b + q
+                            taps.append(([si * 4 + p * 2 + q for si in range(len(srcs))], b, a))
+                            tapoffs.append(kh * 4 + kw)
             wm = self._alloc((n_rows, 16 * cpad_tot), adt_t, zero=True)
             st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 16,
-                                       cin_tot * 16, 16, self._tapoff(tapoffs)))
+                                       cin_tot * 16, 16, self._tapoff(tapoffs), chunked=chunked))
             th, tw = tile_shape(Wo)
-            tiles = N * -(-Ho // th) * -(-Wo // tw)
+            tiles = max(N * -(-Ho // th) * -(-Wo // tw), 148)
             if epi & EPI_STATS:
                 st.stats = self._alloc((tiles, 2, cout), torch.float32, zero=True)
-                st.n_stat_tiles = tiles
             st.fwd_plans.append(self._conv_problem(
                 views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32,
                 (Ho * Wo * ld_out, Wo * ld_out, ld_out), (1, 1, 0, 0), epi, bias_t, st.stats, cout, self.impl))
+            st.n_stat_tiles = self.L.rnr_conv_plan_stat_rows(st.fwd_plans[-1].h)
         else:  # ConvTranspose 4x4 s2 p1: four parity sub-problems, each a 2x2 conv over the un-padded input
             views = [t.interior() for t in srcs]
             Hi, Wi = sp.H, sp.W
             th, tw = tile_shape(Wi)
-            tiles = N * -(-Hi // th) * -(-Wi // tw)
+            tiles = max(N * -(-Hi // th) * -(-Wi // tw), 148)      # rows reserved per parity sub-problem (unused rows stay zero)
             if epi & EPI_STATS:
                 st.stats = self._alloc((4 * tiles, 2, cout), torch.float32, zero=True)
                 st.n_stat_tiles = 4 * tiles
             sel = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}      # parity -> [(k index, input offset)]
+            rows_pp = 0
             for ph in range(2):
                 for pw in range(2):
                     taps, tapoffs = [], []
@@ -401,13 +425,18 @@ class UNetEngine:
                     wm = self._alloc((n_rows, 4 * cpad_tot), adt_t, zero=True)
                     # weight [Cin, Cout, 4, 4]: rows = co (stride 16), cols = ci (stride Cout*16)
                     st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 4,
-                                               16, cout * 16, self._tapoff(tapoffs)))
+                                               16, cout * 16, self._tapoff(tapoffs), chunked=chunked))
                     stats_ptr = None
                     if st.stats is not None:
-                        stats_ptr = st.stats.data_ptr() + (ph * 2 + pw) * tiles * 2 * cout * 4
+                        stats_ptr = st.stats.data_ptr() + (ph * 2 + pw) * rows_pp * 2 * cout * 4
                     st.fwd_plans.append(self._conv_problem(
                         views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Hi, Wi, st.raw, F32,
                         (Ho * Wo * ld_out, Wo * ld_out, ld_out), (2, 2, ph, pw), epi, bias_t, stats_ptr, cout, self.impl))
+                    if ph == 0 and pw == 0:
+                        # the four parity sub-problems have identical shapes: each writes `rows_pp` consecutive partial-sum rows
+                        rows_pp = self.L.rnr_conv_plan_stat_rows(st.fwd_plans[-1].h)
+                        if st.stats is not None:
+                            st.n_stat_tiles = 4 * rows_pp
         if not self.need_backward:
             return
 
@@ -499,16 +528,14 @@ class UNetEngine:
             Hp, Wp = Hi + 2, Wi + 2
             st.gx = self._alloc((N, Hp, Wp, nci_pad), gdt_t, zero=True)
             st.gx_fold, st.gx_ld = True, nci_pad
-            ks, tapoffs = [], []
-            for kh in range(3):
-                for kw in range(3):
-                    for c0 in range(0, gC, gbk):
-                        ks.append((0, c0, 1 - kw, 1 - kh))
-                    tapoffs.append(kh * 3 + kw)
+            gch = 1 if gbk == 64 else 0
+            tapl = [(1 - kw, 1 - kh, kh * 3 + kw) for kh in range(3) for kw in range(3)]
+            ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gC, gbk, gch)
+            tapoffs = [o for (_, _, o) in tapl]
             wm = self._alloc((nci_pad, 9 * gC), gdt_t, zero=True)
             # rows = ci (stride 9), cols = co (stride Cin*9)
             st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 9, wm, self.grad_dt, nci, nci_pad, cout, gC, 9, 9, cin_tot * 9,
-                                         self._tapoff(tapoffs)))
+                                         self._tapoff(tapoffs), chunked=gch))
             st.dgrad_plans.append(self._conv_problem(
                 [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp, Wp, st.gx, self.grad_dt,
                 (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
@@ -518,15 +545,13 @@ class UNetEngine:
             st.gx_fold, st.gx_ld = True, nci_pad
             for ph in range(2):
                 for pw in range(2):
-                    ks, tapoffs = [], []
-                    for a in range(2):
-                        for b in range(2):
-                            for c0 in range(0, gC, gbk):
-                                ks.append((0, c0, 1 - b, 1 - a))
-                            tapoffs.append((2 * a + ph) * 4 + (2 * b + pw))
+                    gch = 1 if gbk == 64 else 0
+                    tapl = [(1 - b, 1 - a, (2 * a + ph) * 4 + (2 * b + pw)) for a in range(2) for b in range(2)]
+                    ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gC, gbk, gch)
+                    tapoffs = [o for (_, _, o) in tapl]
                     wm = self._alloc((nci_pad, 4 * gC), gdt_t, zero=True)
                     st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 16, wm, self.grad_dt, nci, nci_pad, cout, gC, 4, 16,
-                                                 cin_tot * 16, self._tapoff(tapoffs)))
+                                                 cin_tot * 16, self._tapoff(tapoffs), chunked=gch))
                     st.dgrad_plans.append(self._conv_problem(
                         [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp // 2, Wp // 2, st.gx, self.grad_dt,
                         (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (2, 2, ph, pw), 0, None, None, 0, self.impl))
@@ -535,17 +560,15 @@ class UNetEngine:
             st.gx = self._alloc((N, Hi, Wi, nci_pad), gdt_t, zero=True)
             st.gx_fold, st.gx_ld = False, nci_pad
             gviews = [G.parity(p, q) for p in range(2) for q in range(2)]
-            ks, tapoffs = [], []
-            for kh in range(4):
-                for kw in range(4):
-                    a, p, b, q = kh // 2, kh % 2, kw // 2, kw % 2
-                    for c0 in range(0, gC, gbk):
-                        ks.append((p * 2 + q, c0, b, a))
-                    tapoffs.append(kh * 4 + kw)
+            gch = 1 if gbk == 64 else 0
+            # parity-major tap order: the 4 taps reading one parity view of G are adjacent
+            tapl = [(p * 2 + q, b, a, (2 * a + p) * 4 + (2 * b + q)) for p in range(2) for q in range(2) for a in range(2) for b in range(2)]
+            ks = self._order_ksteps([(v, dx, dy) for (v, dx, dy, _) in tapl], gC, gbk, gch)
+            tapoffs = [o for (_, _, _, o) in tapl]
             wm = self._alloc((nci_pad, 16 * gC), gdt_t, zero=True)
             # weight [Cin, Cout, 4,4]: rows = ci (stride Cout*16), cols = co (stride 16)
             st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * cout * 16, wm, self.grad_dt, nci, nci_pad, cout, gC, 16, cout * 16, 16,
-                                         self._tapoff(tapoffs)))
+                                         self._tapoff(tapoffs), chunked=gch))
             st.dgrad_plans.append(self._conv_problem(
                 gviews, ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hi, Wi, st.gx, self.grad_dt,
                 (Hi * Wi * nci_pad, Wi * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
@@ -580,7 +603,7 @@ class UNetEngine:
         for w in items:
             src = self.params[w.src_key]
             _lib.check(self.L.rnr_weight_prep(src.data_ptr() + 4 * w.src_off, w.dst.data_ptr(), w.dtype, w.nr, w.nr_pad,
-                                              w.nc, w.cpad, w.ntaps, w.s_r, w.s_c, w.tapoff.data_ptr(), s), 'rnr_weight_prep')
+                                              w.nc, w.cpad, w.ntaps, w.s_r, w.s_c, w.tapoff.data_ptr(), w.chunked, s), 'rnr_weight_prep')
             self.gpu_launches += 1
 
     def prepare_weights(self, backward=False):
@@ -729,13 +752,14 @@ class UNetEngine:
                     dbet = self.grad_view(sp.bn_key + '.bias').data_ptr()
                 else:
                     dgam, dbet = None, self.grad_view(sp.b_key).data_ptr()
+                gam = self.params[sp.bn_key + '.weight'].data_ptr() if has_bn else None
                 _lib.check(L.rnr_bn_bwd_finalize(st.bwd_partials.data_ptr(), T.value, Cc, float(N * Ho * Wo), dgam, dbet,
-                                                 st.c1.data_ptr(), st.c2.data_ptr(), s), 'rnr_bn_bwd_finalize')
+                                                 st.c1.data_ptr(), st.c2.data_ptr(), gam, st.mean.data_ptr() if has_bn else None,
+                                                 st.invstd.data_ptr() if has_bn else None, st.coef.data_ptr() if has_bn else None, s),
+                           'rnr_bn_bwd_finalize')
                 self.gpu_launches += 2
                 if has_bn:
-                    _lib.check(L.rnr_bn_bwd_apply(self.gz[sp.name].ptr, st.raw.data_ptr(),
-                                                  self.params[sp.bn_key + '.weight'].data_ptr(), st.mean.data_ptr(),
-                                                  st.invstd.data_ptr(), st.c1.data_ptr(), st.c2.data_ptr(), N, Ho, Wo, Cc, s),
+                    _lib.check(L.rnr_bn_bwd_apply(self.gz[sp.name].ptr, st.raw.data_ptr(), st.coef.data_ptr(), N, Ho, Wo, Cc, s),
                                'rnr_bn_bwd_apply')
                     self.gpu_launches += 1
             t0 = self._mark()

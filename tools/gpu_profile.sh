@@ -1,8 +1,14 @@
 #!/bin/bash
-# ncu launch list of a short bench run + one full capture of the conv kernel.  Outputs under gpurun_out/.
+# ncu launch list of exactly 2 eager training steps (+ optionally one full capture of a kernel).  Outputs under gpurun_out/.
+#   TAG=r01_v1 KERNEL=conv_tc_kernel bash tools/gpu_profile.sh
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-1500} -c ${COUNT:-900} --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:${KERNEL:-conv_tc_kernel} -s ${KSKIP:-100} -c 3 -f -o gpurun_out/prof_conv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu2.log 2>&1
-ls -la gpurun_out | tail -8
+TAG=${TAG:-cur}
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python bench.py --profile-steps 2 --no-graph > gpurun_out/bench_ncu_${TAG}.log 2>&1
+python tools/launch_summary.py gpurun_out/launches_${TAG}.csv 2 > gpurun_out/launches_${TAG}_summary.txt
+head -45 gpurun_out/launches_${TAG}_summary.txt
+if [ -n "$KERNEL" ]; then
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${KERNEL} -s ${KSKIP:-0} -c ${KCOUNT:-3} -f -o gpurun_out/prof_${TAG} \
+    python bench.py --profile-steps 1 --no-graph > gpurun_out/bench_ncu2_${TAG}.log 2>&1
+fi
+ls -la gpurun_out | tail -6

@@ -61,7 +61,10 @@ def main():
     tot_f = tot_d = tot_w = 0.0
     tot_flop = 0.0
     print('%-10s %-5s %5s->%-4s %4s | fwd ms  TF/s | dgrad ms TF/s | wgrad ms TF/s' % ('layer', 'kind', 'cin', 'cout', 'Ho'))
+    only = os.environ.get('PERF_LAYERS')
     for sp in specs:
+        if only and sp.name not in only.split(','):
+            continue
         st = eng.layers[sp.name]
         fl = layer_flops(sp, N)
         tf = timeit(lambda: [L.rnr_conv_run(p.h, s) for p in st.fwd_plans])
