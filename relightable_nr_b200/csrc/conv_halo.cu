@@ -23,7 +23,15 @@
 
 namespace {
 
-constexpr int kThreads = 384;          // warps 0-3: TMA / MMA / TMEM / idle; warps 4-11: epilogue
+constexpr int kThreads = 640;
+// Warp roles.  The warp scheduler prefers the HIGHEST warp id of an SM sub-partition, so the two latency-critical single-issuer
+// roles sit on top (warps 10, 11) and the 8 ALU-heavy epilogue warps below them (a tcgen05.mma issuer that shares its
+// scheduler with two higher-numbered epilogue warps was measured at ~90 cycles per MMA issue instead of <= 64).
+constexpr int kEpiWarps = 16;          // warps 0-15: TMEM lane group = warp % 4 (hardware rule), 16-column quarter = warp / 4
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kAllocWarp = 16;         // TMEM allocate / free
+constexpr int kProducerWarp = 18;      // TMA
+constexpr int kMmaWarp = 19;           // tcgen05.mma issue
 constexpr int TH = 16, TW = 8;          // output tile (pixels): M = 128, one 8-row UMMA group per image row
 constexpr int kMaxGroups = 64;
 constexpr int kMaxTaps = 512;
@@ -81,6 +89,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     float* s_acc = (float*)(s_taps + kMaxTaps);                      // [2][512] per-CTA BatchNorm sums
     float* s_stage = s_acc + 1024;                                   // [128][68] epilogue staging slab (16-byte aligned)
     int64_t* s_rowoff = (int64_t*)(s_stage + 128 * 68);              // [128] output offset of each tile row
+    float* s_colp = (float*)(s_rowoff + 128);                        // [2][8][64] per-pass column partial sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // cluster of `cs` CTAs: same N tile, `cs` adjacent M tiles (rank r takes M tile mg*cs + r); the B (weight) stage is loaded once
@@ -98,25 +107,25 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     for (int i = threadIdx.x; i < n_taps; i += kThreads) s_taps[i] = taps[i];
     for (int i = threadIdx.x; i < 1024; i += kThreads) s_acc[i] = 0.f;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kProducerWarp && lane == 0) {
         for (int v = 0; v < RNR_MAX_VIEWS; v++)
             if (p.views[v].ptr) tma_prefetch_desc(&maps.a[v]);
         tma_prefetch_desc(&maps.b);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < kAStages; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < b_stages; s++) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], (uint32_t)cs); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == kAllocWarp) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync_all();          // peers' barriers must exist before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
@@ -139,7 +148,9 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 if (++as == kAStages) { as = 0; aph ^= 1; }
                 for (int k = 0; k < gtaps; k += T) {
                     const int kblk = g * gtaps + k;
+                    if ((dbg & 128) && lane == 0) trace(tr, 0, ti);
                     mbar_wait(&bempty[bs], bph ^ 1);
+                    if ((dbg & 128) && lane == 0) trace(tr, 0, ti);
                     if (elect_one_sync()) {
                         if (dbg & 4) mbar_arrive(&bfull[bs]);
                         else {
@@ -159,7 +170,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             }
             if (lane == 0) trace(tr, 0, ti);
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
         const uint32_t idesc = make_idesc(128, bn, p.ab_dtype, p.ab_dtype, 0, 0);
         const uint32_t sbo = (uint32_t)pitch * 128u;
@@ -182,8 +193,10 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 if (g == 0 && lane == 0) trace(tr, 1, ti);
                 const uint32_t a_base = a_smem0 + (uint32_t)as * (uint32_t)a_stage_bytes;
                 for (int k = 0; k < gtaps; k += T) {
+                    if ((dbg & 128) && lane == 0) trace(tr, 1, ti);
                     mbar_wait(&bfull[bs], bph);
                     tc_fence_after();
+                    if ((dbg & 128) && lane == 0) trace(tr, 1, ti);
                     const uint32_t b_base = b_smem0 + (uint32_t)bs * (uint32_t)b_stage_bytes;
                     if (elect_one_sync()) {
                         if (!(dbg & 8)) {
@@ -211,7 +224,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             __syncwarp();
             if (lane == 0) trace(tr, 1, ti);
         }
-    } else if (warp >= 4) {
+    } else if (warp < kEpiWarps) {
         // ================= epilogue (8 warps) =================
         // A lone warp per scheduler issues one dependent instruction every ~4 cycles, so the epilogue is spread over 8 warps:
         // warp w owns TMEM lanes 32*(w%4).. (hardware rule) and column half (w-4)/4 of each 64-column pass.
@@ -219,13 +232,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         // memory [128 rows][68 floats]; then (a) full-row coalesced global stores (16 lanes per 256-byte row) and (b) per-column
         // BatchNorm sums read column-wise from the staging tile.  The accumulator is handed back to the MMA warp as soon as
         // its last pass is in registers.
-        const int q = warp & 3, hcol = (warp - 4) >> 2;
+        const int q = warp & 3, hcol = warp >> 2;
         const int r = q * 32 + lane;
         const int ry = r / TW, rx = r % TW;
-        const int e = threadIdx.x - 128;                       // 0..255
+        const int e = threadIdx.x;                             // 0..511
         int it = 0;
         int t3 = 1;
-        const bool tr4 = (warp == 4 && lane == 0);
+        const bool tr4 = (warp == 0 && lane == 0);
         for (int t = cid; t < total_tiles; t += ncl, it++) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -243,11 +256,10 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             for (int c0 = 0; c0 < ((dbg & 32) ? 0 : bn); c0 += 64) {
                 const int pw = min(64, bn - c0);                 // pass width (multiple of 16)
-                const int mc0 = hcol * 32;                       // my first column inside the pass
-                const int mw = max(0, min(32, pw - mc0));        // my width: 0, 16 or 32
-                uint32_t rv[32];
+                const int mc0 = hcol * 16;                       // my first column inside the pass
+                const int mw = (mc0 < pw) ? 16 : 0;              // my width: 16 columns (pw is a multiple of 16) or nothing
+                uint32_t rv[16];
                 if (mw > 0) tmem_ld16(taddr + (uint32_t)(c0 + mc0), rv);
-                if (mw > 16) tmem_ld16(taddr + (uint32_t)(c0 + mc0 + 16), rv + 16);
                 tmem_ld_wait();
                 if (tr4 && it == 0) trace(tr, 3, t3);
                 if (c0 + 64 >= bn) {
@@ -258,7 +270,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 }
                 float* srow = s_stage + r * 68 + mc0;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < 4; j++) {
                     if (j * 4 < mw) {
                         float v[4];
 #pragma unroll
@@ -272,7 +284,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                         *(float4*)(srow + j * 4) = make_float4(v[0], v[1], v[2], v[3]);
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 if (tr4 && it == 0) trace(tr, 3, t3);
                 // ---- (a) coalesced stores: 256 threads sweep the [128 x pw] pass row-major ----
                 if (!(dbg & 1)) {
@@ -281,7 +293,20 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     const int epp = f32 ? 4 : 8;
                     const int npieces = 128 * ppr;
                     const int sh = (ppr == 16) ? 4 : (ppr == 8) ? 3 : (ppr == 4) ? 2 : (ppr == 2) ? 1 : -1;
-                    for (int i = e; i < npieces; i += 256) {
+                    if (f32 && pw == 64 && n0 + c0 + 64 <= p.cout) {
+                        // 512 threads x 4 rows: thread e owns the 16-byte piece (e & 15) of rows (e >> 4) + 32 k
+                        const int pc = (e & 15) * 4, r0_ = e >> 4;
+                        int64_t rb[4];
+                        float4 v[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) rb[k] = s_rowoff[r0_ + 32 * k];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) v[k] = *(const float4*)(s_stage + (r0_ + 32 * k) * 68 + pc);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (rb[k] >= 0) *(float4*)((float*)p.out + rb[k] + n0 + c0 + pc) = v[k];
+                    } else
+                    for (int i = e; i < npieces; i += kEpiThreads) {
                         const int rr = sh >= 0 ? (i >> sh) : (i / ppr);
                         const int pc = (i - rr * ppr) * epp;
                         const int64_t rb = s_rowoff[rr];
@@ -311,21 +336,35 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     }
                 }
                 if (tr4 && it == 0) trace(tr, 3, t3);
-                // ---- (b) BatchNorm partial sums: thread e sums column e%64 over rows [32*(e/64), +32) ----
-                if ((p.epi & RNR_EPI_STATS) && !(dbg & 2)) {
+                // ---- (b) BatchNorm partial sums: thread e sums column e%64 over rows [16*(e/64), +16) ----
+                // deterministic: the 8 row-slice partials of a column are parked in shared memory and added in a fixed order
+                // by one thread per column (no floating-point atomics), so two runs give bit-identical statistics
+                const bool do_stats = (p.epi & RNR_EPI_STATS) && !(dbg & 2);
+                if (do_stats) {
                     const int col = e & 63, part = e >> 6;
+                    float a1 = 0.f, a2 = 0.f;
+                    if (col < pw) {
+                        const float* sp = s_stage + (part * 16) * 68 + col;
+#pragma unroll
+                        for (int k = 0; k < 16; k++) { const float v = sp[k * 68]; a1 += v; a2 += v * v; }
+                    }
+                    s_colp[part * 64 + col] = a1;
+                    s_colp[512 + part * 64 + col] = a2;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");      // staging tile is free again
+                if (tr4 && it == 0) trace(tr, 3, t3);
+                if (do_stats && e < 128) {
+                    // threads 0..63: sum of x, threads 64..127: sum of x^2 (the next pass rewrites s_colp only after its own barrier)
+                    const int col = e & 63, which = e >> 6;
                     const int co = n0 + c0 + col;
                     if (col < pw && co < p.cout && co < 512) {
-                        float a1 = 0.f, a2 = 0.f;
-                        const float* sp = s_stage + (part * 32) * 68 + col;
-#pragma unroll 8
-                        for (int k = 0; k < 32; k++) { const float v = sp[k * 68]; a1 += v; a2 += v * v; }
-                        atomicAdd(&s_acc[co], a1);
-                        atomicAdd(&s_acc[512 + co], a2);
+                        const float* pp = s_colp + which * 512 + col;
+                        float a = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) a += pp[k * 64];
+                        s_acc[which * 512 + co] += a;
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");      // staging tile is free again
-                if (tr4 && it == 0) trace(tr, 3, t3);
             }
             if (dbg & 32) {
                 tc_fence_before();
@@ -335,8 +374,8 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             if (tr4) trace(tr, 2, ti);
         }
         if (p.epi & RNR_EPI_STATS) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int co = e; co < p.cout; co += 256) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            for (int co = e; co < p.cout; co += kEpiThreads) {
                 p.stats[((int64_t)blockIdx.x * 2 + 0) * p.ldstats + co] = s_acc[co];
                 p.stats[((int64_t)blockIdx.x * 2 + 1) * p.ldstats + co] = s_acc[512 + co];
             }
@@ -346,7 +385,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync_all();          // no CTA may exit while a peer can still arrive on its barriers
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -430,11 +469,13 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
             if (prob->n_rows_w % bn == 0) break;
     }
     int tiles_n = rnr_cdiv(prob->n_rows_w, bn);
-    while (bn > 64 && bn % 32 == 0 && p.tiles_m * tiles_n < 148) { bn /= 2; tiles_n = rnr_cdiv(prob->n_rows_w, bn); }
+    // a wider N tile reads fewer shared-memory operand bytes per FLOP (the SS-mode MMA is shared-memory-bandwidth bound below N = 256),
+    // so N is only narrowed when the launch would otherwise leave most SMs idle
+    while (bn > 64 && bn % 32 == 0 && p.tiles_m * tiles_n < (bn > 128 ? 100 : 50)) { bn /= 2; tiles_n = rnr_cdiv(prob->n_rows_w, bn); }
     pl->bn = bn;
     pl->tiles_n = tiles_n;
     const int a_stage = ((rows * pitch * 128) + 1023) / 1024 * 1024;
-    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 1024 * 4 + 128 * 68 * 4 + 128 * 8;
+    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 1024 * 4 + 128 * 68 * 4 + 128 * 8 + 1024 * 4;
     const int budget = 212 * 1024 - aux - kAStages * a_stage;
     // taps per B stage: one mbarrier hand-shake (~400 cycles of latency in the single-thread producer / issuer loops) must
     // cover enough tensor work, so a stage holds T taps = T*4 MMAs; T divides the taps of a group
@@ -445,6 +486,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
         const int stage = cand * bn * 128;
         if (stage <= 72 * 1024 && budget / stage >= 2) { T = cand; break; }
     }
+    { const char* te = getenv("RNR_CONV_T"); if (te && atoi(te) >= 1 && gtaps % atoi(te) == 0 && atoi(te) * bn * 128 <= 72 * 1024) T = atoi(te); }
     const int b_stage = T * bn * 128;                      // multiple of 1024 (bn is a multiple of 16 -> 2048 B)
     int b_stages = budget / b_stage;
     if (b_stages > 8) b_stages = 8;

@@ -64,16 +64,17 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const WorkItem wi = work[w];
-                const rnr_wtap_t tap = p.taps[wi.tap];
-                for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
-                    const int tx_ = pt % tiles_x, ty_ = (pt / tiles_x) % tiles_y, n_ = pt / (tiles_x * tiles_y);
-                    const int x0 = tx_ * tw, y0 = ty_ * th;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // TMA producer: the whole warp runs the loop, one elected lane issues (operands stay warp-uniform -> uniform registers)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const WorkItem wi = work[w];
+            const rnr_wtap_t tap = p.taps[wi.tap];
+            for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
+                const int tx_ = pt % tiles_x, ty_ = (pt / tiles_x) % tiles_y, n_ = pt / (tiles_x * tiles_y);
+                const int x0 = tx_ * tw, y0 = ty_ * th;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one_sync()) {
                     uint8_t* st = smem + (size_t)stage * kStageBytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + wi.n_ci_box) * kBoxBytes));
                     tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st, wi.co0, x0, y0, n_);
@@ -81,40 +82,46 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                     for (int b = 0; b < wi.n_ci_box; b++)
                         tma_load_4d(&maps.a[tap.view], &full_bar[stage], st + (size_t)(2 + b) * kBoxBytes,
                                     tap.c0 + wi.ci_off + 64 * b, x0 + tap.dx, y0 + tap.dy, n_);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
-                const WorkItem wi = work[w];
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                const uint32_t idesc = make_idesc(128, wi.n_ci_box * 64, p.g_dtype, p.a_dtype, 1, 1);
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // MMA issuer: same structure (see tc_ptx.cuh::elect_one_sync)
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        const uint32_t smem0 = smem_u32(smem);
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
+            const WorkItem wi = work[w];
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const uint32_t idesc = make_idesc(128, wi.n_ci_box * 64, p.g_dtype, p.a_dtype, 1, 1);
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+            uint32_t accum = 0;
+            for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
-                bool first = true;
-                for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(smem + (size_t)stage * kStageBytes);
+                const uint32_t sbase = smem0 + (uint32_t)stage * (uint32_t)kStageBytes;
+                if (elect_one_sync()) {
                     const uint64_t dg = make_mnmajor_desc(sbase, kBoxBytes);
                     const uint64_t da = make_mnmajor_desc(sbase + 2 * kBoxBytes, kBoxBytes);
 #pragma unroll
                     for (int k = 0; k < 8; k++) {     // 128 pixels = 8 MMAs of K=16 (2 KB of rows each)
-                        umma_f16(d_tmem, dg + (uint64_t)(k * (2048 >> 4)), da + (uint64_t)(k * (2048 >> 4)), idesc, first ? 0u : 1u);
-                        first = false;
+                        umma_f16(d_tmem, dg + (uint64_t)(k * (2048 >> 4)), da + (uint64_t)(k * (2048 >> 4)), idesc, accum);
+                        accum = 1;
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
+                __syncwarp();
+                accum = 1;
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         const int q = warp & 3;

@@ -225,7 +225,8 @@ class UNetEngine:
             self.producer[sp.dst] = sp.name
             Ho, Wo = sp.Ho, sp.Wo
             if sp.dst == 'out':
-                self.out_ld = _rup(sp.cout, 16)
+                # channel pitch of the final layer's output / gradient: a multiple of 64 keeps its data-gradient on the halo kernel
+                self.out_ld = _rup(sp.cout, 64) if sp.cout > 32 else _rup(sp.cout, 16)
                 st.raw = self._alloc((N, Ho, Wo, self.out_ld), torch.float32, zero=True)
             else:
                 st.raw = self._alloc((N, Ho, Wo, sp.cout), torch.float32)
