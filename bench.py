@@ -184,6 +184,7 @@ def _config(args, world):
     return {'workload': 'RNR train step (train_rnr.py:490-623), %dx%d material-sphere proxy views, 1 view/GPU/step, texture 512^2x24ch x4 mips, '
                         'U-Net 108->78 nf0=64, 26 rays, SH lmax 10 envmap 256x512' % (args.size, args.size),
             'views_per_step': max(world, 1), 'parallelism': 'dp%d (views sharded, NCCL grad all-reduce)' % max(world, 1), 'launch': 'eager' if args.no_graph else 'one CUDA graph per step',
+            'step': 'module-by-module (drop-in operator API)' if args.no_fused else 'fused head/tail kernels around the U-Net (relightable_nr_b200/fused.py)',
             'l2': 'per-step working set (~3 GB of activations/gradients) >> 126 MB L2; 4 distinct views cycled'}
 
 
@@ -224,7 +225,18 @@ def run_ours(args):
             g.copy_(flat[o:o + g.numel()].view_as(g))
             o += g.numel()
 
+    def sync_grad_buffers(bufs):
+        # fused step: the U-Net gradients already live in ONE flat buffer -> one large all-reduce + 5 small ones, no packing copies
+        if world == 1:
+            return
+        for g in bufs:
+            dist.all_reduce(g)
+            g.mul_(1.0 / world)
+
     def eager_step(view):
+        if not args.no_fused:
+            pipe.fused.grad_hook = sync_grad_buffers if world > 1 else None
+            return pipe.fused.train_step(view)[0]
         final, rays_lt, alpha_map = pipe.forward(view)
         loss, _ = pipe.losses(view, final, rays_lt, alpha_map)
         loss.backward()
@@ -237,7 +249,10 @@ def run_ours(args):
         step = eager_step
     else:
         # the whole iteration (incl. the gradient all-reduce) as one CUDA graph; per-view maps are copied into its static inputs
-        step, _static = pipe.make_graphed_step(views[0], grad_hook=(lambda ps: sync_grads()) if world > 1 else None)
+        if args.no_fused:
+            step, _static = pipe.make_graphed_step(views[0], grad_hook=(lambda ps: sync_grads()) if world > 1 else None)
+        else:
+            step, _static = pipe.make_graphed_step(views[0], grad_hook=sync_grad_buffers if world > 1 else None, fused=True)
 
     def barrier():
         if world > 1:
@@ -383,6 +398,8 @@ def main():
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-steps', type=int, default=0, help='run K eager steps between cudaProfilerStart/Stop and exit (for ncu)')
+    ap.add_argument('--no-fused', action='store_true', help='drive the step operator by operator through the drop-in modules '
+                    '(the reference script\'s call sequence) instead of the fused head/tail kernels')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying one CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':

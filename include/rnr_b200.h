@@ -195,6 +195,14 @@ int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* raw,
 int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count,
                         float* dgamma, float* dbeta, float* c1, float* c2,
                         const float* gamma, const float* mean, const float* invstd, float* coef, void* stream);
+/* pass 1 + finalize in ONE launch: as rnr_bn_bwd_reduce (<= 148 partial rows [T,2,C]); the last block to finish (ticket counter,
+ * an int32 in device memory that must be 0 before the first call; the kernel re-arms it) adds the rows in a fixed order and
+ * writes dbeta = sum(gz), dgamma = sum(gz*xhat) (either may be NULL) and, when coef != NULL, the coefficients (A, B, D).   */
+int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const float* raw,
+                          const float* scale, const float* shift, const float* mean, const float* invstd,
+                          const float* drop, float slope, void* gz, float* partials, int* ticket, double count,
+                          float* dgamma, float* dbeta, const float* gamma, float* coef,
+                          int N, int H, int W, int C, void* stream);
 /* pass 2 (in place): gz <- A*gz + B*raw + D */
 int rnr_bn_bwd_apply(void* gz, const float* raw, const float* coef, int N, int H, int W, int C, void* stream);
 
@@ -323,6 +331,35 @@ int rnr_l1_masked(const float* out, const float* gt, const float* alpha, int N, 
                   float weight, float* g_out, double* loss_sum, void* stream);
 int rnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, int step, float gscale, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Fused producers / consumers around the U-Net (csrc/fused.cu): the same operators as above,  */
+/* composed so that no intermediate crosses HBM in a layout its consumer cannot use directly.  */
+/* ------------------------------------------------------------------------------------------ */
+/* network.TextureMapper.forward (network.py:67-91) + RaySampler.forward x2 (network.py:445-472, 'reflect' with pivots_s
+ * [3,Rs] then 'diffuse' with pivots_d [3,Rd]) + the input assembly torch.cat((rays_dir, normal, view_dir, neural_img), 1)
+ * (train_rnr.py:530-533) -> `act`: the first convolution's operand, fp16 [N,H+2,W+2,Cpad] channels-last with reflect halo
+ * (channels r*3+c | normal | view_dir | texture | zero padding), optional bf16 copy, rays_uv [N,H,W,2,Rs+Rd], and
+ * albedo [N,H,W,8] = texture channels 0..7 (diffuse 0..2, specular 3..5, train_rnr.py:515-516).
+ * Rs = Rd = 0 with normal = view_dir = NULL gives the DNR input (train_dnr.py:252).                                   */
+int rnr_head_fwd(const float* const* textures, const int* sizes, int n_levels, int C, const float* uv, const float* sh,
+                 int sh_start, const float* tbn, const float* view_dir_tangent, const float* alpha, const float* normal,
+                 const float* view_dir, const float* pivots_s, int Rs, const float* pivots_d, int Rd, void* act,
+                 void* act_bf16, int Cpad, float* rays_uv, float* albedo, int N, int H, int W, void* stream);
+/* rays_lt = (raw*0.5+0.5)*2 (train_rnr.py:535-536; raw = tanh output of the last convolution, NHWC with pitch ldraw),
+ * RayRenderer.forward(seperate_albedo=True) (network.py:481-527) -> final [N,3,H,W]; RaysLTChromLoss (network.py:395-411)
+ * and the cropped alpha-masked L1 (train_rnr.py:565-585) as sums (double[3], pre-zeroed): sum(diff), sum(alpha),
+ * sum|final*a - gt*a|.  aux [N,H,W,12] keeps what the backward re-uses.                                               */
+int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+                 const float* alpha, const float* img_gt, int Rs, int Rd, int N, int H, int W, int crop, float* final_img,
+                 float* aux, double* sums, void* stream);
+/* backward of rnr_tail_fwd for loss = w_l1*L1 + w_chrom*chrom: gz (bf16 [N,H+2,W+2,ldg], zero halo) = d loss / d (pre-tanh
+ * output), dbias[3R] += its per-channel sums (bias gradient of the last convolution), g_alb [N,6,H,W] = d loss / d texture
+ * channels 0..5, g_lp4 [Hl*Wl,4] += d loss / d envmap (rgb + one unused lane: 128-bit vector reductions).               */
+int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+                 const float* alpha, const float* img_gt, int Rs, int Rd, int N, int H, int W, int crop, const float* aux,
+                 const double* sums, float w_l1, float w_chrom, void* gz, int ldg, float* dbias, float* g_alb,
+                 float* g_lp4, void* stream);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,7 @@ def lib():
         "rnr_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp],
         "rnr_bn_act_fwd": [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
+        "rnr_bn_bwd_reduce_fin": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, f64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_finalize": [vp, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "rnr_bn_bwd_apply": [vp, vp, vp, i32, i32, i32, i32, vp],
         "rnr_pack_nchw_to_act": [vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -1,0 +1,462 @@
+// Fused producers / consumers around the U-Net of the RNR step: the per-pixel stages of train_rnr.py:512-585 written so
+// that nothing crosses HBM in a layout the next kernel cannot use directly.
+//
+//   rnr_head_fwd : TextureMapper.forward (network.py:67-91) + 2x RaySampler.forward (network.py:445-472) + the
+//                  torch.cat input assembly (train_rnr.py:530-533) -> the first convolution's operand, i.e. the fp16
+//                  channels-last tile with reflect halo that the TMA box loads of conv 'in' read (plus the bf16 copy for
+//                  the weight-gradient MMA), the ray uv's and the 6 albedo channels for the tail.  Replaces 3 kernels +
+//                  6 permute/cat copies + the NCHW->NHWC pack (436 B/pixel fp32 written and re-read) by one pass.
+//   rnr_tail_fwd : rays_lt = (tanh*0.5+0.5)*2 (train_rnr.py:535-536), RayRenderer.forward (network.py:481-527),
+//                  RaysLTChromLoss (network.py:395-411) and the cropped masked L1 (train_rnr.py:565-585), read straight
+//                  from the last convolution's NHWC output.
+//   rnr_tail_bwd : backward of all of the above down to d loss / d (pre-tanh output) in the data-gradient kernel's
+//                  operand layout (bf16, zero halo), the last layer's bias gradient, the albedo gradients (planar, for the
+//                  texture scatter) and the envmap gradient (one 128-bit vector red per tap).
+// The arithmetic of every stage is the one of the module-level kernels (texture.cu, rays.cu, loss.cu), statement by
+// statement, so the fused step and the drop-in modules agree to fp32 rounding.
+#include "pixel.cuh"
+
+namespace {
+
+constexpr int kHeadPx = 32;
+constexpr int kHeadThreads = 256;
+constexpr int kMaxRays = 32;
+
+struct HeadParams {
+    const float* tex[8];
+    int size[8];
+    int n_levels, C, sh_start;
+    const float* uv;         // [P,2]
+    const float* sh;         // [P,9] or null
+    const float* tbn;        // [P,9]
+    const float* vdt;        // [P,3]
+    const float* alpha;      // [P]
+    const float* normal;     // [P,3] or null
+    const float* view_dir;   // [P,3] or null
+    const float* piv_s;      // [3,Rs]
+    const float* piv_d;      // [3,Rd]
+    int Rs, Rd;
+    __half* act;             // [N,H+2,W+2,Cpad]
+    __nv_bfloat16* act_b;    // same or null
+    int Cpad;
+    float* rays_uv;          // [P,2,R] or null
+    float* albedo;           // [P,8] or null
+    int N, H, W;
+};
+
+__global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(const HeadParams q) {
+    extern __shared__ float sm[];
+    const int R = q.Rs + q.Rd;
+    float* s_out = sm;                                   // [kHeadPx][Cpad]
+    float* s_uv = s_out + kHeadPx * q.Cpad;              // [kHeadPx][2R]
+    float* s_in = s_uv + kHeadPx * 2 * kMaxRays;         // [kHeadPx][13]: TBN 9, vdt 3, alpha
+    float* s_piv = s_in + kHeadPx * 13;                  // [2][3*kMaxRays]
+    const int tid = threadIdx.x;
+    const int64_t P = (int64_t)q.N * q.H * q.W;
+    const int64_t p0 = (int64_t)blockIdx.x * kHeadPx;
+    const int np = (int)((P - p0) < kHeadPx ? (P - p0) : kHeadPx);
+
+    for (int i = tid; i < kHeadPx * q.Cpad; i += kHeadThreads) s_out[i] = 0.f;
+    for (int i = tid; i < 3 * q.Rs; i += kHeadThreads) s_piv[i] = q.piv_s[i];
+    for (int i = tid; i < 3 * q.Rd; i += kHeadThreads) s_piv[3 * kMaxRays + i] = q.piv_d[i];
+    if (R > 0) {
+        for (int i = tid; i < np * 9; i += kHeadThreads) s_in[(i / 9) * 13 + (i % 9)] = q.tbn[p0 * 9 + i];
+        for (int i = tid; i < np * 3; i += kHeadThreads) s_in[(i / 3) * 13 + 9 + (i % 3)] = q.vdt[p0 * 3 + i];
+        for (int i = tid; i < np; i += kHeadThreads) s_in[i * 13 + 12] = q.alpha[p0 + i];
+    }
+    __syncthreads();
+
+    // ---- rays: item = (pixel, ray) ----
+    for (int i = tid; i < np * R; i += kHeadThreads) {
+        const int px = i / R, r = i - px * R;
+        const float* T = s_in + px * 13;
+        const float a = T[12];
+        const bool reflect = r < q.Rs;
+        const float* pv = reflect ? s_piv : s_piv + 3 * kMaxRays;
+        const int Rm = reflect ? q.Rs : q.Rd, rr = reflect ? r : r - q.Rs;
+        const float px_ = pv[rr], py_ = pv[Rm + rr], pz_ = pv[2 * Rm + rr];
+        float tx, ty, tz;
+        if (reflect) {
+            const float vx = T[9], vy = T[10], vz = T[11];
+            const float d = (px_ * vx + py_ * vy + pz_ * vz) * 2.0f;
+            tx = d * px_ - vx; ty = d * py_ - vy; tz = d * pz_ - vz;
+            normalize3(tx, ty, tz);
+            tx *= a; ty *= a; tz *= a;
+        } else {
+            tx = px_; ty = py_; tz = pz_;
+        }
+        float wx = T[0] * tx + T[1] * ty + T[2] * tz;
+        float wy = T[3] * tx + T[4] * ty + T[5] * tz;
+        float wz = T[6] * tx + T[7] * ty + T[8] * tz;
+        normalize3(wx, wy, wz);
+        float* o = s_out + px * q.Cpad + r * 3;
+        o[0] = wx; o[1] = wy; o[2] = wz;
+        float u, v;
+        spherical_uv(wx, wy, wz, u, v);
+        const float bg = (a == 0.f) ? 1.f : 0.f;
+        s_uv[px * 2 * R + r] = u * a - bg;
+        s_uv[px * 2 * R + R + r] = v * a - bg;
+    }
+    // ---- normal / view direction ----
+    int cbase = 3 * R;
+    if (q.normal) {
+        for (int i = tid; i < np * 3; i += kHeadThreads) s_out[(i / 3) * q.Cpad + cbase + (i % 3)] = q.normal[p0 * 3 + i];
+        cbase += 3;
+    }
+    if (q.view_dir) {
+        for (int i = tid; i < np * 3; i += kHeadThreads) s_out[(i / 3) * q.Cpad + cbase + (i % 3)] = q.view_dir[p0 * 3 + i];
+        cbase += 3;
+    }
+    // ---- neural texture: item = (pixel, group of 4 channels) ----
+    const int ng = q.C >> 2;
+    for (int i = tid; i < np * ng; i += kHeadThreads) {
+        const int px = i / ng, c = (i - px * ng) * 4;
+        const int64_t pix = p0 + px;
+        const float u = q.uv[pix * 2 + 0], v = q.uv[pix * 2 + 1];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int l = 0; l < q.n_levels; l++) {
+            const int S = q.size[l];
+            const float x = u * (float)(S - 1);
+            const float y = (float)(S - 1) - v * (float)(S - 1);
+            const Bilin b = bilinear_setup(x, y, S, S);
+            const float* Tx = q.tex[l];
+            const float4 a = *(const float4*)(Tx + (int64_t)b.i00 * q.C + c), bb = *(const float4*)(Tx + (int64_t)b.i10 * q.C + c);
+            const float4 cc = *(const float4*)(Tx + (int64_t)b.i01 * q.C + c), d = *(const float4*)(Tx + (int64_t)b.i11 * q.C + c);
+            acc[0] += a.x * b.w00 + bb.x * b.w10 + cc.x * b.w01 + d.x * b.w11;
+            acc[1] += a.y * b.w00 + bb.y * b.w10 + cc.y * b.w01 + d.y * b.w11;
+            acc[2] += a.z * b.w00 + bb.z * b.w10 + cc.z * b.w01 + d.z * b.w11;
+            acc[3] += a.w * b.w00 + bb.w * b.w10 + cc.w * b.w01 + d.w * b.w11;
+        }
+        if (q.sh) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = c + e - q.sh_start;
+                if (k >= 0 && k < 9) acc[e] *= q.sh[pix * 9 + k];
+            }
+        }
+        float* o = s_out + px * q.Cpad + cbase + c;
+        o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+        if (q.albedo && c < 8) *(float4*)(q.albedo + pix * 8 + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+    __syncthreads();
+
+    // ---- write-out: fp16 (+ bf16) rows of Cpad channels with the reflect halo; rays_uv rows ----
+    const int vpp = q.Cpad >> 3;
+    const int Hp = q.H + 2, Wp = q.W + 2;
+    for (int i = tid; i < np * vpp; i += kHeadThreads) {
+        const int px = i / vpp, c = (i - px * vpp) * 8;
+        const int64_t pix = p0 + px;
+        const int w = (int)(pix % q.W), h = (int)((pix / q.W) % q.H), n = (int)(pix / ((int64_t)q.W * q.H));
+        const float* sv = s_out + px * q.Cpad + c;
+        __align__(16) __half o[8];
+        __align__(16) __nv_bfloat16 ob[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { o[e] = __float2half_rn(sv[e]); ob[e] = __float2bfloat16_rn(sv[e]); }
+        const uint4 ov = *(const uint4*)o, ovb = *(const uint4*)ob;
+        int rows[3], cols[3], nr = 0, nc = 0;
+        rows[nr++] = h + 1;
+        if (h == 1) rows[nr++] = 0;
+        if (h == q.H - 2) rows[nr++] = q.H + 1;
+        cols[nc++] = w + 1;
+        if (w == 1) cols[nc++] = 0;
+        if (w == q.W - 2) cols[nc++] = q.W + 1;
+        for (int a = 0; a < nr; a++)
+            for (int b = 0; b < nc; b++) {
+                const int64_t o_ = (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * q.Cpad + c;
+                *(uint4*)(q.act + o_) = ov;
+                if (q.act_b) *(uint4*)(q.act_b + o_) = ovb;
+            }
+    }
+    if (q.rays_uv)
+        for (int i = tid; i < np * 2 * R; i += kHeadThreads) q.rays_uv[p0 * 2 * R + i] = s_uv[i];
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// tail
+// -------------------------------------------------------------------------------------------------------------------
+struct TailParams {
+    const float* raw;        // [P, ldraw] tanh output of the last convolution (channels r*3+c)
+    int ldraw;
+    const float* rays_uv;    // [P,2,R]
+    const float* albedo;     // [P,8]: diffuse 0..2, specular 3..5
+    const float* lp;         // [Hl,Wl,3]
+    int Hl, Wl;
+    const float* alpha;      // [P]
+    const float* img;        // [N,3,H,W]
+    int R, Rs, Rd;
+    int N, H, W, crop;
+    float* final_img;        // [N,3,H,W]
+    float* aux;              // [P,12]: ltt_s 0..2, ltt_d 3..5, chrom mean 6..8, image weight 9
+    double* sums;            // [0] sum diff, [1] sum alpha, [2] sum |out*a - gt*a| over the crop
+};
+
+__device__ __forceinline__ float block_sum128(float v, float* s_tmp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_tmp[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+        r = lane < (blockDim.x >> 5) ? s_tmp[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void env_taps(const TailParams& q, int64_t pix, int r, Bilin& b) {
+    const float u = q.rays_uv[pix * 2 * q.R + r], v = q.rays_uv[pix * 2 * q.R + q.R + r];
+    const float x = fminf(u * (float)q.Wl, (float)(q.Wl - 1));
+    const float y = fminf(v * (float)q.Hl, (float)(q.Hl - 1));
+    b = bilinear_setup(x, y, q.Wl, q.Hl);
+}
+
+__global__ void __launch_bounds__(128) tail_fwd_kernel(const TailParams q) {
+    __shared__ float s_tmp[8];
+    const int64_t HW = (int64_t)q.H * q.W;
+    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float dsum = 0.f, asum = 0.f, lsum = 0.f;
+    if (pix < HW * q.N) {
+        const int n = (int)(pix / HW);
+        const int64_t p = pix % HW;
+        const float a = q.alpha[pix];
+        float wi = 1.f;
+        float gt[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) gt[c] = q.img[((int64_t)n * 3 + c) * HW + p];
+        wi = fminf(sqrtf(gt[0] * gt[0] + gt[1] * gt[1] + gt[2] * gt[2]) * 20.f, 1.0f);
+        const float* t = q.raw + pix * q.ldraw;
+        float ss[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        for (int r = 0; r < q.R; r++) {
+            Bilin b;
+            env_taps(q, pix, r, b);
+            float lt[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                lt[c] = (t[r * 3 + c] * 0.5f + 0.5f) * 2.0f;
+                const float col = q.lp[b.i00 * 3 + c] * b.w00 + q.lp[b.i10 * 3 + c] * b.w10 + q.lp[b.i01 * 3 + c] * b.w01 +
+                                  q.lp[b.i11 * 3 + c] * b.w11;
+                const float tt = lt[c] * col;
+                if (r < q.Rs) ss[c] += tt; else sd[c] += tt;
+            }
+            float x = lt[0], y = lt[1], z = lt[2];
+            normalize3(x, y, z);
+            m0 += x; m1 += y; m2 += z;
+        }
+        m0 /= (float)q.R; m1 /= (float)q.R; m2 /= (float)q.R;
+        normalize3(m0, m1, m2);
+        for (int r = 0; r < q.R; r++) {
+            float x = (t[r * 3 + 0] * 0.5f + 0.5f) * 2.0f, y = (t[r * 3 + 1] * 0.5f + 0.5f) * 2.0f, z = (t[r * 3 + 2] * 0.5f + 0.5f) * 2.0f;
+            normalize3(x, y, z);
+            dsum += (1.f - (x * m0 + y * m1 + z * m2)) * a * wi;
+        }
+        asum = a;
+        const int w = (int)(p % q.W), h = (int)(p / q.W);
+        const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
+        float* ax = q.aux + pix * 12;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float ls = ss[c] / (float)q.Rs;
+            const float os = q.albedo[pix * 8 + 3 + c] * ls;
+            float ld = 0.f, od = 0.f;
+            if (q.Rd > 0) { ld = sd[c] / (float)q.Rd; od = q.albedo[pix * 8 + c] * ld; }
+            const float out = os + od;
+            q.final_img[((int64_t)n * 3 + c) * HW + p] = out;
+            ax[c] = ls; ax[3 + c] = ld;
+            if (inside) lsum += fabsf(out * a - gt[c] * a);
+        }
+        ax[6] = m0; ax[7] = m1; ax[8] = m2; ax[9] = wi;
+    }
+    const float bd = block_sum128(dsum, s_tmp);
+    const float ba = block_sum128(asum, s_tmp);
+    const float bl = block_sum128(lsum, s_tmp);
+    if (threadIdx.x == 0) {
+        if (bd != 0.f) atomicAdd(&q.sums[0], (double)bd);
+        if (ba != 0.f) atomicAdd(&q.sums[1], (double)ba);
+        if (bl != 0.f) atomicAdd(&q.sums[2], (double)bl);
+    }
+}
+
+struct TailBwdParams {
+    TailParams f;
+    float w_l1, w_chrom;     // loss weights (upstream gradient folded in)
+    __nv_bfloat16* gz;       // [N,H+2,W+2,ldg] zero halo; channels [0, 3R) of the interior are written
+    int ldg;
+    float* dbias;            // [3R] += sum over pixels of dz
+    float* g_alb;            // [N,6,H,W]: d loss / d neural_img channels 0..5
+    float4* g_lp4;           // [Hl*Wl] (r,g,b,unused) += envmap gradient, or null
+};
+
+constexpr int kTailPitch = 97;          // >= 3R + 1, odd: conflict-free column sums (R <= 32)
+
+__global__ void __launch_bounds__(128) tail_bwd_kernel(const TailBwdParams qq) {
+    extern __shared__ float s_dz[];      // [128][kTailPitch]
+    const TailParams& q = qq.f;
+    const int64_t HW = (int64_t)q.H * q.W;
+    const int64_t p0 = (int64_t)blockIdx.x * 128;
+    const int64_t pix = p0 + threadIdx.x;
+    const int nch = 3 * q.R;
+    float* mine = s_dz + threadIdx.x * kTailPitch;
+    if (pix < HW * q.N) {
+        const int n = (int)(pix / HW);
+        const int64_t p = pix % HW;
+        const float a = q.alpha[pix];
+        const float* ax = q.aux + pix * 12;
+        const int w = (int)(p % q.W), h = (int)(p / q.W);
+        const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
+        const double cnt = (double)q.N * 3 * (q.H - 2 * q.crop) * (q.W - 2 * q.crop);
+        float Gls[3], Gld[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float as = q.albedo[pix * 8 + 3 + c], ad = q.albedo[pix * 8 + c];
+            const float ls = ax[c], ld = ax[3 + c];
+            const float os = as * ls;
+            const float od = (q.Rd > 0) ? ad * ld : 0.f;
+            const float out = os + od;
+            float go = 0.f;
+            if (inside) {
+                const float d = out * a - q.img[((int64_t)n * 3 + c) * HW + p] * a;
+                go = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * a * (float)((double)qq.w_l1 / cnt);
+            }
+            Gls[c] = go * as / (float)q.Rs;
+            Gld[c] = (q.Rd > 0) ? go * ad / (float)q.Rd : 0.f;
+            qq.g_alb[((int64_t)n * 6 + 3 + c) * HW + p] = go * ls;
+            qq.g_alb[((int64_t)n * 6 + c) * HW + p] = (q.Rd > 0) ? go * ld : 0.f;
+        }
+        const float m0 = ax[6], m1 = ax[7], m2 = ax[8];
+        const float s = qq.w_chrom * a * ax[9] / ((float)q.sums[1] * (float)q.R);
+        const float* t = q.raw + pix * q.ldraw;
+        for (int r = 0; r < q.R; r++) {
+            Bilin b;
+            env_taps(q, pix, r, b);
+            float th[3], lt[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { th[c] = t[r * 3 + c]; lt[c] = (th[c] * 0.5f + 0.5f) * 2.0f; }
+            const float nr = fmaxf(sqrtf(lt[0] * lt[0] + lt[1] * lt[1] + lt[2] * lt[2]), 1e-12f);
+            const float x = lt[0] / nr, y = lt[1] / nr, z = lt[2] / nr;
+            const float cm = x * m0 + y * m1 + z * m2;
+            const float gch[3] = {-s * (m0 - x * cm) / nr, -s * (m1 - y * cm) / nr, -s * (m2 - z * cm) / nr};
+            float gc[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float G = (r < q.Rs) ? Gls[c] : Gld[c];
+                const float col = q.lp[b.i00 * 3 + c] * b.w00 + q.lp[b.i10 * 3 + c] * b.w10 + q.lp[b.i01 * 3 + c] * b.w01 +
+                                  q.lp[b.i11 * 3 + c] * b.w11;
+                const float glt = G * col + gch[c];
+                mine[r * 3 + c] = glt * (1.f - th[c] * th[c]);
+                gc[c] = G * lt[c];
+            }
+            if (qq.g_lp4 && (gc[0] != 0.f || gc[1] != 0.f || gc[2] != 0.f)) {
+                if (b.w00 != 0.f) atomicAdd(qq.g_lp4 + b.i00, make_float4(gc[0] * b.w00, gc[1] * b.w00, gc[2] * b.w00, 0.f));
+                if (b.w10 != 0.f) atomicAdd(qq.g_lp4 + b.i10, make_float4(gc[0] * b.w10, gc[1] * b.w10, gc[2] * b.w10, 0.f));
+                if (b.w01 != 0.f) atomicAdd(qq.g_lp4 + b.i01, make_float4(gc[0] * b.w01, gc[1] * b.w01, gc[2] * b.w01, 0.f));
+                if (b.w11 != 0.f) atomicAdd(qq.g_lp4 + b.i11, make_float4(gc[0] * b.w11, gc[1] * b.w11, gc[2] * b.w11, 0.f));
+            }
+        }
+        for (int c = nch; c < kTailPitch; c++) mine[c] = 0.f;
+    } else {
+        for (int c = 0; c < kTailPitch; c++) mine[c] = 0.f;
+    }
+    __syncthreads();
+    // ---- gz rows: bf16, 8 channels per 16-byte store, channels [0, roundup8(3R)) ----
+    const int vpp = (nch + 7) >> 3;
+    const int Hp = q.H + 2, Wp = q.W + 2;
+    for (int i = threadIdx.x; i < 128 * vpp; i += 128) {
+        const int px = i / vpp, c = (i - px * vpp) * 8;
+        const int64_t pp = p0 + px;
+        if (pp >= HW * q.N) break;
+        const int w = (int)(pp % q.W), h = (int)((pp / q.W) % q.H), n = (int)(pp / HW);
+        __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[e] = __float2bfloat16_rn(s_dz[px * kTailPitch + c + e]);     // (columns >= 3R are zero)
+        *(uint4*)(qq.gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * qq.ldg + c) = *(const uint4*)o;
+    }
+    // ---- bias gradient of the last convolution: column sums of the block, one red per channel ----
+    if (threadIdx.x < nch) {
+        float acc = 0.f;
+        for (int px = 0; px < 128; px++) acc += s_dz[px * kTailPitch + threadIdx.x];
+        if (acc != 0.f) atomicAdd(qq.dbias + threadIdx.x, acc);
+    }
+}
+
+}  // namespace
+
+extern "C" int rnr_head_fwd(const float* const* tex, const int* sizes, int n_levels, int C, const float* uv, const float* sh,
+                            int sh_start, const float* tbn, const float* vdt, const float* alpha, const float* normal,
+                            const float* view_dir, const float* pivots_s, int Rs, const float* pivots_d, int Rd, void* act,
+                            void* act_bf16, int Cpad, float* rays_uv, float* albedo, int N, int H, int W, void* stream) {
+    RNR_REQUIRE(n_levels >= 1 && n_levels <= 8, "head: 1..8 mip levels supported, got %d", n_levels);
+    RNR_REQUIRE(C >= 4 && C % 4 == 0 && C <= 64, "head: texture channels must be a multiple of 4 (got %d)", C);
+    RNR_REQUIRE(Rs >= 0 && Rd >= 0 && Rs + Rd <= kMaxRays, "head: at most %d rays (got %d + %d)", kMaxRays, Rs, Rd);
+    RNR_REQUIRE(!sh || (sh_start >= 0 && sh_start + 9 <= C), "head: SH channels [%d,%d) exceed C=%d", sh_start, sh_start + 9, C);
+    const int used = 3 * (Rs + Rd) + (normal ? 3 : 0) + (view_dir ? 3 : 0) + C;
+    RNR_REQUIRE(Cpad % 8 == 0 && used <= Cpad && Cpad <= 256, "head: %d channels do not fit the operand pitch %d", used, Cpad);
+    RNR_REQUIRE(H >= 2 && W >= 2, "head: reflect halo needs H, W >= 2");
+    RNR_REQUIRE(Rs + Rd == 0 || (tbn && vdt && alpha && pivots_s && (Rd == 0 || pivots_d)), "head: ray inputs missing");
+    HeadParams q;
+    memset(&q, 0, sizeof(q));
+    for (int i = 0; i < n_levels; i++) { q.tex[i] = tex[i]; q.size[i] = sizes[i]; }
+    q.n_levels = n_levels; q.C = C; q.sh_start = sh_start;
+    q.uv = uv; q.sh = sh; q.tbn = tbn; q.vdt = vdt; q.alpha = alpha; q.normal = normal; q.view_dir = view_dir;
+    q.piv_s = pivots_s; q.piv_d = pivots_d; q.Rs = Rs; q.Rd = Rd;
+    q.act = (__half*)act; q.act_b = (__nv_bfloat16*)act_bf16; q.Cpad = Cpad;
+    q.rays_uv = rays_uv; q.albedo = albedo; q.N = N; q.H = H; q.W = W;
+    const size_t smem = ((size_t)kHeadPx * Cpad + kHeadPx * 2 * kMaxRays + kHeadPx * 13 + 6 * kMaxRays) * sizeof(float);
+    static bool attr = false;
+    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    RNR_REQUIRE(smem <= 64 * 1024, "head: shared memory %zu too large", smem);
+    const int64_t P = (int64_t)N * H * W;
+    head_fwd_kernel<<<rnr_cdiv(P, kHeadPx), kHeadThreads, smem, (cudaStream_t)stream>>>(q);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+static int fill_tail(TailParams& q, const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp,
+                     int Hl, int Wl, const float* alpha, const float* img, int Rs, int Rd, int N, int H, int W, int crop,
+                     float* final_img, float* aux, double* sums) {
+    RNR_REQUIRE(Rs >= 1 && Rd >= 0 && Rs + Rd <= kMaxRays, "tail: 1..%d rays supported (got %d + %d)", kMaxRays, Rs, Rd);
+    RNR_REQUIRE(ldraw >= 3 * (Rs + Rd), "tail: output pitch %d < %d channels", ldraw, 3 * (Rs + Rd));
+    RNR_REQUIRE(H > 2 * crop && W > 2 * crop, "tail: crop too large");
+    RNR_REQUIRE(raw && rays_uv && albedo && lp && alpha && img && aux && sums, "tail: null argument");
+    q.raw = raw; q.ldraw = ldraw; q.rays_uv = rays_uv; q.albedo = albedo; q.lp = lp; q.Hl = Hl; q.Wl = Wl; q.alpha = alpha;
+    q.img = img; q.R = Rs + Rd; q.Rs = Rs; q.Rd = Rd; q.N = N; q.H = H; q.W = W; q.crop = crop; q.final_img = final_img;
+    q.aux = aux; q.sums = sums;
+    return 0;
+}
+
+extern "C" int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+                            const float* alpha, const float* img, int Rs, int Rd, int N, int H, int W, int crop, float* final_img,
+                            float* aux, double* sums, void* stream) {
+    TailParams q;
+    int rc = fill_tail(q, raw, ldraw, rays_uv, albedo, lp, Hl, Wl, alpha, img, Rs, Rd, N, H, W, crop, final_img, aux, sums);
+    if (rc) return rc;
+    RNR_REQUIRE(final_img, "tail: null output");
+    tail_fwd_kernel<<<rnr_cdiv((int64_t)N * H * W, 128), 128, 0, (cudaStream_t)stream>>>(q);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+                            const float* alpha, const float* img, int Rs, int Rd, int N, int H, int W, int crop, const float* aux,
+                            const double* sums, float w_l1, float w_chrom, void* gz, int ldg, float* dbias, float* g_alb,
+                            float* g_lp4, void* stream) {
+    TailBwdParams qq;
+    int rc = fill_tail(qq.f, raw, ldraw, rays_uv, albedo, lp, Hl, Wl, alpha, img, Rs, Rd, N, H, W, crop, nullptr,
+                       const_cast<float*>(aux), const_cast<double*>(sums));
+    if (rc) return rc;
+    RNR_REQUIRE(gz && dbias && g_alb, "tail bwd: null output");
+    RNR_REQUIRE(ldg % 8 == 0 && ldg >= (3 * (Rs + Rd) + 7) / 8 * 8, "tail bwd: gradient pitch %d too small", ldg);
+    RNR_REQUIRE(3 * (Rs + Rd) + 1 <= kTailPitch, "tail bwd: too many rays");
+    RNR_REQUIRE(!g_lp4 || ((uintptr_t)g_lp4 & 15) == 0, "tail bwd: envmap gradient must be 16-byte aligned");
+    qq.w_l1 = w_l1; qq.w_chrom = w_chrom; qq.gz = (__nv_bfloat16*)gz; qq.ldg = ldg; qq.dbias = dbias; qq.g_alb = g_alb;
+    qq.g_lp4 = (float4*)g_lp4;
+    const size_t smem = (size_t)128 * kTailPitch * sizeof(float);
+    static bool attr = false;
+    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    tail_bwd_kernel<<<rnr_cdiv((int64_t)N * H * W, 128), 128, smem, (cudaStream_t)stream>>>(qq);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}

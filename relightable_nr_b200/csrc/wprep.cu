@@ -37,29 +37,52 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict
     const unsigned magic = (65536u + ts - 1) / ts;                        // j / ts for j < 4096 without an integer division
     const int nrt = min(RB, J.nr - r0), nct = min(CB, J.nc - c0);       // valid rows / cols of this tile (may be <= 0)
     // smem element (rr, cc, tt) lives at (rr*CB + cc)*ts + (pow2 ? tt ^ (cc & 15) : tt)
+    // The kernel is a pure HBM stream (fp32 in, 16 bit out): all loads of a thread are issued before the first shared-memory
+    // store (8 independent 4-byte loads in flight per thread) -- with one load in flight it ran at 1/5 of the copy bandwidth.
     if (nrt > 0 && nct > 0) {
         if (J.s_c < J.s_r) {
             // columns are the inner dimension: for each row, [nct * ts] floats are contiguous -> straight copy
             const int run = nct * ts;
-            for (int rr = 0; rr < nrt; rr++) {
-                const float* sp = J.src + (int64_t)(r0 + rr) * J.s_r + (int64_t)c0 * J.s_c;
-                float* tp = tile + rr * CB * ts;
-                for (int j = threadIdx.x; j < run; j += 256) {
-                    int d = j;
-                    if (pow2) { const int cc = j >> 4; d = (cc << 4) | ((j & 15) ^ (cc & 15)); }
-                    tp[d] = sp[j];
-                }
+            const float* sp0 = J.src + (int64_t)r0 * J.s_r + (int64_t)c0 * J.s_c;
+            for (int j = threadIdx.x; j < run; j += 256) {
+                float v[RB];
+#pragma unroll
+                for (int rr = 0; rr < RB; rr++) v[rr] = (rr < nrt) ? __ldcs(sp0 + (int64_t)rr * J.s_r + j) : 0.f;
+                int d = j;
+                if (pow2) { const int cc = j >> 4; d = (cc << 4) | ((j & 15) ^ (cc & 15)); }
+#pragma unroll
+                for (int rr = 0; rr < RB; rr++) tile[rr * CB * ts + d] = v[rr];
             }
         } else {
-            // rows are the inner dimension: for each column, [nrt * ts] floats are contiguous
+            // rows are the inner dimension: for each column, [nrt * ts] (<= 128) floats are contiguous; a warp owns 8 columns
             const int run = nrt * ts;
-            for (int cc = threadIdx.x >> 5; cc < nct; cc += 8) {
-                const float* sp = J.src + (int64_t)(c0 + cc) * J.s_c + (int64_t)r0 * J.s_r;
-                for (int j = threadIdx.x & 31; j < run; j += 32) {
-                    const int rr = pow2 ? (j >> 4) : (int)(((unsigned)j * magic) >> 16);
-                    int tt = j - rr * ts;
-                    if (pow2) tt ^= (cc & 15);
-                    tile[(rr * CB + cc) * ts + tt] = sp[j];
+            const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+            const float* sp0 = J.src + (int64_t)c0 * J.s_c + (int64_t)r0 * J.s_r;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                float v[4][4];
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) {
+                    const int cc = wq + 8 * (half * 4 + ci);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = lane + 32 * u;
+                        v[ci][u] = (cc < nct && j < run) ? __ldcs(sp0 + (int64_t)cc * J.s_c + j) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) {
+                    const int cc = wq + 8 * (half * 4 + ci);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = lane + 32 * u;
+                        if (cc < nct && j < run) {
+                            const int rr = pow2 ? (j >> 4) : (int)(((unsigned)j * magic) >> 16);
+                            int tt = j - rr * ts;
+                            if (pow2) tt ^= (cc & 15);
+                            tile[(rr * CB + cc) * ts + tt] = v[ci][u];
+                        }
+                    }
                 }
             }
         }
@@ -68,20 +91,22 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict
     const int ncw = min(CB, J.cpad - c0);
     const int nrw = min(RB, J.nr_pad - r0);
     unsigned short* dst = (unsigned short*)J.dst;
-    const int cc = threadIdx.x & (CB - 1), q = threadIdx.x >> 6;          // 64 columns x 4 tap lanes
-    if (cc < ncw) {
-        for (int rr = 0; rr < nrw; rr++) {
-            for (int t = q; t < J.ntaps; t += 4) {
+    // thread = (8-column group cg, tap lane tl, row lane rl): one 16-byte store per (row, tap, column group)
+    const int cg = threadIdx.x & 7, tl = (threadIdx.x >> 3) & 15, rl = threadIdx.x >> 7;     // 8 x 16 x 2
+    if (cg * 8 < ncw && tl < J.ntaps) {
+        const int tsel = J.tapoff[tl];
+        for (int rr = rl; rr < nrw; rr += 2) {
+            __align__(16) unsigned short o[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int cc = cg * 8 + e;
                 float v = 0.f;
-                if (rr < nrt && cc < nct) {
-                    int tt = J.tapoff[t];
-                    if (pow2) tt ^= (cc & 15);
-                    v = tile[(rr * CB + cc) * ts + tt];
-                }
-                const int c = c0 + cc;
-                const int64_t col = J.chunked ? ((int64_t)((c >> 6) * J.ntaps + t) * 64 + (c & 63)) : ((int64_t)t * J.cpad + c);
-                dst[(int64_t)(r0 + rr) * J.ntaps * J.cpad + col] = f2b16(v, J.dtype);
+                if (rr < nrt && cc < nct) v = tile[(rr * CB + cc) * ts + (pow2 ? (tsel ^ (cc & 15)) : tsel)];
+                o[e] = f2b16(v, J.dtype);
             }
+            const int c = c0 + cg * 8;
+            const int64_t col = J.chunked ? ((int64_t)((c >> 6) * J.ntaps + tl) * 64 + (c & 63)) : ((int64_t)tl * J.cpad + c);
+            *(uint4*)(dst + (int64_t)(r0 + rr) * J.ntaps * J.cpad + col) = *(const uint4*)o;
         }
     }
 }
@@ -109,6 +134,7 @@ extern "C" int rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr
         d.src = s.src; d.dst = s.dst; d.dtype = s.dst_dtype;
         d.nr = s.nr; d.nr_pad = s.nr_pad; d.nc = s.nc; d.cpad = s.cpad; d.ntaps = s.ntaps; d.ts = (int)ts;
         d.s_r = s.s_r; d.s_c = s.s_c; d.chunked = s.chunked;
+        RNR_REQUIRE(s.cpad % 8 == 0 && ((uintptr_t)s.dst & 15) == 0, "weight prep: cpad %% 8 == 0 and a 16-byte aligned destination required (cpad %d)", s.cpad);
         RNR_REQUIRE(!s.chunked || s.cpad % 64 == 0, "weight prep: chunk-major layout needs cpad %% 64 == 0 (got %d)", s.cpad);
         for (int t = 0; t < s.ntaps; t++) {
             RNR_REQUIRE(s.tapoff[t] >= 0 && s.tapoff[t] < ts, "weight prep: tap offset %d outside [0,%lld)", s.tapoff[t], (long long)ts);

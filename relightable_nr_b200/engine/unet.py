@@ -163,6 +163,7 @@ class _LayerState:
     gx_fold: bool = False
     gx_ld: int = 0
     drop: Optional[torch.Tensor] = None
+    ticket: Optional[torch.Tensor] = None
 
 
 class UNetEngine:
@@ -242,6 +243,7 @@ class UNetEngine:
                 ld = self.out_ld if sp.dst == 'out' else sp.cout
                 self.gz[sp.name] = HaloTensor(N, Ho, Wo, ld, gdt, dev, zero=True)
                 st.bwd_partials = self._alloc((148 * 8 * 2 * max(ld, 8),), torch.float32)
+                st.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
             # flat gradient storage
             for key in (sp.w_key, sp.b_key, (sp.bn_key + '.weight') if sp.bn_key else None,
                         (sp.bn_key + '.bias') if sp.bn_key else None):
@@ -256,6 +258,7 @@ class UNetEngine:
         all_items = fwd_items + [w for sp in self.specs for w in self.layers[sp.name].wprep_dgrad]
         self.wprep_fwd_plan = self._wprep_plan(fwd_items)
         self.wprep_all_plan = self._wprep_plan(all_items) if len(all_items) > len(fwd_items) else self.wprep_fwd_plan
+        self.wprep_dgrad_plan = self._wprep_plan(all_items[len(fwd_items):]) if len(all_items) > len(fwd_items) else None
 
     # ---- problem builders ---------------------------------------------------------------------
     def _conv_problem(self, views, ksteps, ab_dtype, bk, wmat, n_rows_w, cout, mN, mY, mX, out_t, out_dtype,
@@ -613,6 +616,15 @@ class UNetEngine:
         _lib.check(self.L.rnr_wprep_run(plan.h, self._stream()), 'rnr_wprep_run')
         self.gpu_launches += 1
 
+    def prepare_weights_split(self, part):
+        """'fwd' or 'dgrad' half of prepare_weights(backward=True) as its own launch: the fused step runs the data-gradient
+        half on a side stream underneath the forward pass."""
+        plan = self.wprep_fwd_plan if part == 'fwd' else self.wprep_dgrad_plan
+        if plan is None:
+            return
+        _lib.check(self.L.rnr_wprep_run(plan.h, self._stream()), 'rnr_wprep_run')
+        self.gpu_launches += 1
+
     def prepare_weights_per_layer(self, backward=False):
         """Same result through the single-matrix entry point (kept as the cross-check of the batched kernel)."""
         s = self._stream()
@@ -740,25 +752,22 @@ class UNetEngine:
                 srcs = self._gsrcs_for(sp.dst)
                 assert 1 <= len(srcs) <= 2, (sp.name, len(srcs))
                 arr = (GSrc * len(srcs))(*srcs)
-                T = C.c_int(0)
                 has_bn = sp.bn_key is not None
                 shift = st.shift if has_bn else self.params[sp.b_key]
-                _lib.check(L.rnr_bn_bwd_reduce(arr, len(srcs), st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
-                                               st.mean.data_ptr(), st.invstd.data_ptr(),
-                                               st.drop.data_ptr() if st.drop is not None else None, sp.slope,
-                                               self.gz[sp.name].ptr, st.bwd_partials.data_ptr(), C.byref(T), N, Ho, Wo, Cc, s),
-                           'rnr_bn_bwd_reduce')
                 if has_bn:
                     dgam = self.grad_view(sp.bn_key + '.weight').data_ptr()
                     dbet = self.grad_view(sp.bn_key + '.bias').data_ptr()
                 else:
                     dgam, dbet = None, self.grad_view(sp.b_key).data_ptr()
                 gam = self.params[sp.bn_key + '.weight'].data_ptr() if has_bn else None
-                _lib.check(L.rnr_bn_bwd_finalize(st.bwd_partials.data_ptr(), T.value, Cc, float(N * Ho * Wo), dgam, dbet,
-                                                 st.c1.data_ptr(), st.c2.data_ptr(), gam, st.mean.data_ptr() if has_bn else None,
-                                                 st.invstd.data_ptr() if has_bn else None, st.coef.data_ptr() if has_bn else None, s),
-                           'rnr_bn_bwd_finalize')
-                self.gpu_launches += 2
+                # pass 1 (activation' / dropout gate, per-channel sums) with the finalize fused into its last block
+                _lib.check(L.rnr_bn_bwd_reduce_fin(arr, len(srcs), st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
+                                                   st.mean.data_ptr(), st.invstd.data_ptr(),
+                                                   st.drop.data_ptr() if st.drop is not None else None, sp.slope,
+                                                   self.gz[sp.name].ptr, st.bwd_partials.data_ptr(), st.ticket.data_ptr(),
+                                                   float(N * Ho * Wo), dgam, dbet, gam, st.coef.data_ptr() if has_bn else None,
+                                                   N, Ho, Wo, Cc, s), 'rnr_bn_bwd_reduce_fin')
+                self.gpu_launches += 1
                 if has_bn:
                     _lib.check(L.rnr_bn_bwd_apply(self.gz[sp.name].ptr, st.raw.data_ptr(), st.coef.data_ptr(), N, Ho, Wo, Cc, s),
                                'rnr_bn_bwd_apply')

@@ -77,7 +77,16 @@ class UnetRunner:
         rng = self.input_grad_range if (need_backward and x.requires_grad) else None
         if need_backward and x.requires_grad and rng is None:
             rng = (0, Cin)
-        key = (x.device, N, H, W, need_backward, apply_tanh, rng)
+        return self.engine_for(x.device, N, H, W, need_backward, apply_tanh, rng)
+
+    def engine_for(self, device, N, H, W, need_backward, apply_tanh, rng):
+        """The (cached) engine for an input shape.  Also the entry point of the fused step (relightable_nr_b200/fused.py),
+        whose producer kernel writes the first convolution's operand in place instead of handing over an NCHW tensor."""
+        unet = self._unet()
+        cfg = unet._cfg
+        Cin = cfg['in_channels']
+        device = torch.device(device)
+        key = (device, N, H, W, need_backward, apply_tanh, rng)
         params, bufs = _live_params(unet)
         eng = self._engines.get(key)
         if eng is not None:
@@ -98,7 +107,7 @@ class UnetRunner:
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                 raise TypeError('U-Net parameter %s must be a contiguous fp32 CUDA tensor (librnr_b200 has no CPU path)' % k)
         live_bufs = {k: v for k, v in bufs.items() if 'running' in k}
-        eng = UNetEngine(specs, live, live_bufs, N, Cin, x.device, impl='tc', input_grad_range=rng,
+        eng = UNetEngine(specs, live, live_bufs, N, Cin, device, impl='tc', input_grad_range=rng,
                          need_backward=need_backward, final_tanh=apply_tanh)
         eng.version = 0
         # bound memory: keep at most 4 shapes alive
@@ -125,6 +134,13 @@ class UnetRunner:
         plist = [params[k] for k in self.param_keys]
         need_backward = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plist))
         eng = self._engine(x, need_backward, apply_tanh)
+        training_bn, drop_masks = self.step_state(eng)
+        return _UnetFn.apply(self, eng, training_bn, drop_masks, x, *plist)
+
+    def step_state(self, eng):
+        """Per-forward host work of the nn.Module semantics: (BatchNorm in training mode?, Dropout2d channel masks or None);
+        bumps ``num_batches_tracked`` like nn.BatchNorm2d.forward does."""
+        unet = self._unet()
         bn_mod = unet.in_layer[1]
         drop_mod = unet.in_layer[3]
         training_bn = bool(bn_mod.training)
@@ -133,13 +149,13 @@ class UnetRunner:
             p = float(drop_mod.p)
             names = [sp.name for sp in eng.specs if sp.drop and sp.dst != 'out']
             chans = [eng.layers[n].spec.cout for n in names]
-            r = (torch.rand((eng.N, sum(chans)), device=x.device) >= p).float() * (1.0 / (1.0 - p))
+            r = (torch.rand((eng.N, sum(chans)), device=eng.device) >= p).float() * (1.0 / (1.0 - p))
             drop_masks, o = {}, 0
             for n, c in zip(names, chans):
                 drop_masks[n] = r[:, o:o + c].contiguous()
                 o += c
         if training_bn:
-            nbt = [b for k, b in bufs.items() if k.endswith('num_batches_tracked') and '.fuse.' not in k]
+            nbt = [b for k, b in unet.named_buffers() if k.endswith('num_batches_tracked') and '.fuse.' not in k]
             if nbt:
                 torch._foreach_add_(nbt, 1)
-        return _UnetFn.apply(self, eng, training_bn, drop_masks, x, *plist)
+        return training_bn, drop_masks

@@ -163,7 +163,18 @@ class RNRPipeline:
         loss_alb = loss_alb * self.w['alb']
         return loss_lighting + loss_rn + loss_chrom + loss_alb, dict(lighting=loss_lighting, rn=loss_rn, chrom=loss_chrom, alb=loss_alb)
 
-    def train_step(self, view, step_optimizer=True):
+    @property
+    def fused(self):
+        """The same iteration with its per-pixel stages fused around the U-Net (relightable_nr_b200/fused.py)."""
+        if getattr(self, '_fused', None) is None:
+            from .fused import FusedRNRStep
+            self._fused = FusedRNRStep(self)
+        return self._fused
+
+    def train_step(self, view, step_optimizer=True, fused=False):
+        if fused:
+            loss, final = self.fused.train_step(view, step_optimizer=step_optimizer)
+            return loss.detach(), final
         final, rays_lt, alpha_map = self.forward(view)
         loss, parts = self.losses(view, final, rays_lt, alpha_map)
         loss.backward()
@@ -172,7 +183,7 @@ class RNRPipeline:
             self.optimizer.zero_grad()
         return loss.detach(), final.detach()
 
-    def make_graphed_step(self, example_view, grad_hook=None, warmup=3):
+    def make_graphed_step(self, example_view, grad_hook=None, warmup=3, fused=False):
         """Capture ``train_step`` (forward, four losses, backward, [grad_hook], Adam) into ONE CUDA graph.
 
         Returns ``(step, static_view)``: ``step(view)`` copies the per-view maps into the static input buffers, replays the
@@ -184,7 +195,15 @@ class RNRPipeline:
         static_view = {k: v.detach().clone() for k, v in example_view.items()}
         params = [p for grp in self.optimizer.param_groups for p in grp['params']]
 
+        def body_fused():
+            # grad_hook receives the step's gradient buffers (engine flat buffer, texture levels, SH coefficients)
+            self.fused.grad_hook = (lambda gs: grad_hook(gs)) if grad_hook is not None else None
+            loss, _ = self.fused.train_step(static_view)
+            return loss.detach()
+
         def body():
+            if fused:
+                return body_fused()
             self.optimizer.zero_grad(set_to_none=True)
             final, rays_lt, alpha_map = self.forward(static_view)
             loss, _ = self.losses(static_view, final, rays_lt, alpha_map)
@@ -219,7 +238,9 @@ class RNRPipeline:
         return step, static_view
 
     @torch.no_grad()
-    def render(self, view):
+    def render(self, view, fused=False):
+        if fused:
+            return self.fused.render(view)
         return self.forward(view)[0]
 
 
