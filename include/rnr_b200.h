@@ -195,12 +195,13 @@ int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* raw,
 int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count,
                         float* dgamma, float* dbeta, float* c1, float* c2,
                         const float* gamma, const float* mean, const float* invstd, float* coef, void* stream);
-/* pass 1 + finalize in ONE launch: as rnr_bn_bwd_reduce (<= 148 partial rows [T,2,C]); the last block to finish (ticket counter,
- * an int32 in device memory that must be 0 before the first call; the kernel re-arms it) adds the rows in a fixed order and
- * writes dbeta = sum(gz), dgamma = sum(gz*xhat) (either may be NULL) and, when coef != NULL, the coefficients (A, B, D).   */
+/* pass 1 + finalize in ONE launch: as rnr_bn_bwd_reduce, but the block partial sums are added (fp64 atomics) into
+ * totals [2,C] (double, must be 0 before the first call; the kernel re-zeroes it) and the last block to finish (ticket: an
+ * int32 in device memory, 0 before the first call, re-armed by the kernel) writes dbeta = sum(gz), dgamma = sum(gz*xhat)
+ * (either may be NULL) and, when coef != NULL, the coefficients (A, B, D) of rnr_bn_bwd_apply.                          */
 int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const float* raw,
                           const float* scale, const float* shift, const float* mean, const float* invstd,
-                          const float* drop, float slope, void* gz, float* partials, int* ticket, double count,
+                          const float* drop, float slope, void* gz, double* totals, int* ticket, double count,
                           float* dgamma, float* dbeta, const float* gamma, float* coef,
                           int N, int H, int W, int C, void* stream);
 /* pass 2 (in place): gz <- A*gz + B*raw + D */
@@ -349,14 +350,14 @@ int rnr_head_fwd(const float* const* textures, const int* sizes, int n_levels, i
 /* rays_lt = (raw*0.5+0.5)*2 (train_rnr.py:535-536; raw = tanh output of the last convolution, NHWC with pitch ldraw),
  * RayRenderer.forward(seperate_albedo=True) (network.py:481-527) -> final [N,3,H,W]; RaysLTChromLoss (network.py:395-411)
  * and the cropped alpha-masked L1 (train_rnr.py:565-585) as sums (double[3], pre-zeroed): sum(diff), sum(alpha),
- * sum|final*a - gt*a|.  aux [N,H,W,12] keeps what the backward re-uses.                                               */
-int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+ * sum|final*a - gt*a|.  aux [N,H,W,12] keeps what the backward re-uses; lp4 [Hl*Wl,4] = envmap texels (r,g,b,unused).                                             */
+int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp4, int Hl, int Wl,
                  const float* alpha, const float* img_gt, int Rs, int Rd, int N, int H, int W, int crop, float* final_img,
                  float* aux, double* sums, void* stream);
 /* backward of rnr_tail_fwd for loss = w_l1*L1 + w_chrom*chrom: gz (bf16 [N,H+2,W+2,ldg], zero halo) = d loss / d (pre-tanh
  * output), dbias[3R] += its per-channel sums (bias gradient of the last convolution), g_alb [N,6,H,W] = d loss / d texture
  * channels 0..5, g_lp4 [Hl*Wl,4] += d loss / d envmap (rgb + one unused lane: 128-bit vector reductions).               */
-int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp4, int Hl, int Wl,
                  const float* alpha, const float* img_gt, int Rs, int Rd, int N, int H, int W, int crop, const float* aux,
                  const double* sums, float w_l1, float w_chrom, void* gz, int ldg, float* dbias, float* g_alb,
                  float* g_lp4, void* stream);

@@ -216,19 +216,52 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const GSrcs srcs,
     }
 }
 
-// Same pass with the finalize step fused in: one 1024-thread block per SM (T <= 148 partial rows instead of 592), warp-shuffle
-// pre-reduction over the pixel lanes that share a warp, and the LAST block to finish (threadfence + ticket counter) adds the T
-// partial rows in a fixed order (fp64, deterministic) and writes dgamma / dbeta / the fused apply coefficients -- the separate
-// finalize launch (10-14 us of latency-bound work per layer, 21 layers) disappears.
-__global__ void __launch_bounds__(1024, 1) bn_bwd_reduce_fin_kernel(const GSrcs srcs, const float* __restrict__ raw,
+// Same pass with the finalize step fused in and 4 pixels in flight per thread.
+//   * one 512-thread block per SM; every thread owns an 8-channel vector and issues the loads of FOUR pixels (raw fp32 + the
+//     packed 16-bit gradient sources) before touching any of them: ~100 KB in flight per SM instead of ~25 KB (the one-pixel
+//     version ran at 40 % of the HBM roofline, latency-bound);
+//   * block partial sums go to a [2C] fp64 accumulator with atomicAdd(double) (148 adds per address; fp64 accumulation of
+//     fp32 partials is order-independent to ~1e-16, far below the fp32 result's rounding);
+//   * the LAST block to finish (threadfence + ticket) turns the totals into dgamma / dbeta / the fused apply coefficients,
+//     re-zeroes the accumulator and re-arms the ticket -- the separate finalize launch disappears.
+constexpr int kRU = 4;
+
+__device__ __forceinline__ void acc_packed(const uint4& u, int dtype, float* out) {
+    const unsigned short* us = (const unsigned short*)&u;
+#pragma unroll
+    for (int e = 0; e < 8; e++) out[e] += cvt16(us[e], dtype);
+}
+
+// reflect-halo fold of one gradient source at a border pixel (rare: 4 rows / columns of the image) -- kept out of line so
+// that its address arithmetic does not inflate the register budget of the streaming loop
+__device__ __noinline__ void fold_border(const rnr_gsrc_t s, int64_t center, int h, int w, int H, int W, int Wp, float* g) {
+    const int dr = (h == 1) ? -(h + 1) : ((h == H - 2) ? 2 : 0);       // padded row offset of the mirrored copy
+    const int dc = (w == 1) ? -(w + 1) : ((w == W - 2) ? 2 : 0);
+    if (dr) load8(s.ptr, center + (int64_t)dr * Wp * s.ld, s.dtype, g);
+    if (dc) load8(s.ptr, center + (int64_t)dc * s.ld, s.dtype, g);
+    if (dr && dc) load8(s.ptr, center + ((int64_t)dr * Wp + dc) * s.ld, s.dtype, g);
+    // (an image of height/width 3 has h == 1 == H-2: both halo rows mirror the same row)
+    if (h == 1 && h == H - 2) {
+        load8(s.ptr, center + (int64_t)2 * Wp * s.ld, s.dtype, g);
+        if (dc) load8(s.ptr, center + ((int64_t)2 * Wp + dc) * s.ld, s.dtype, g);
+    }
+    if (w == 1 && w == W - 2) {
+        load8(s.ptr, center + (int64_t)2 * s.ld, s.dtype, g);
+        if (dr) load8(s.ptr, center + ((int64_t)dr * Wp + 2) * s.ld, s.dtype, g);
+        if (h == 1 && h == H - 2) load8(s.ptr, center + ((int64_t)2 * Wp + 2) * s.ld, s.dtype, g);
+    }
+}
+
+template <int NSRC>
+__global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs srcs, const float* __restrict__ raw,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ drop, float slope,
-                                     __nv_bfloat16* __restrict__ gz, float* __restrict__ partials, int* __restrict__ ticket,
+                                     __nv_bfloat16* __restrict__ gz, double* __restrict__ totals, int* __restrict__ ticket,
                                      double count, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      const float* __restrict__ gamma, float* __restrict__ coef,
                                      int N, int H, int W, int C, int ppb, int prow) {
-    extern __shared__ float smem[];    // [3][C] scale / shift / mean, then [prow][2C] partial rows (reused as fp64 scratch)
+    extern __shared__ float smem[];    // [3][C] scale / shift / mean, then [prow][2C] partial rows
     __shared__ int s_last;
     float* s_sc = smem;
     float* s_sh = s_sc + C;
@@ -240,59 +273,68 @@ __global__ void __launch_bounds__(1024, 1) bn_bwd_reduce_fin_kernel(const GSrcs 
     for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; s_mu[i] = mean[i]; }
     __syncthreads();
     const int Hp = H + 2, Wp = W + 2;
+    const int HW = H * W;
+    const int P = N * HW;
     float sg[8], sgx[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) { sg[e] = 0.f; sgx[e] = 0.f; }
-    const int segs_per_row = (W + ppb - 1) / ppb;
-    const int nseg = N * H * segs_per_row;
+    const int units = (P + ppb - 1) / ppb;
+    const rnr_gsrc_t S0 = srcs.s[0];
+    const rnr_gsrc_t S1 = srcs.s[NSRC - 1];
+    const bool pre0 = S0.dtype != RNR_F32;                              // 16-bit sources are prefetched as packed vectors
+    const bool pre1 = NSRC > 1 && S1.dtype != RNR_F32;
     if (pl < ppb)
-    for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-        const int row = seg / segs_per_row;
-        const int w = (seg - row * segs_per_row) * ppb + pl;
-        if (w >= W) continue;
-        const int n = row / H, h = row - n * H;
-        const int64_t pix = (int64_t)row * W + w;
-        const float4 r0 = __ldcs((const float4*)(raw + pix * C + c));
-        const float4 r1 = __ldcs((const float4*)(raw + pix * C + c + 4));
-        float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const bool border = (h == 1) | (h == H - 2) | (w == 1) | (w == W - 2);
-        for (int si = 0; si < srcs.n; si++) {
-            const rnr_gsrc_t& s = srcs.s[si];
-            if (s.fold) {
-                const int64_t center = (((int64_t)n * Hp + h + 1) * Wp + w + 1) * s.ld + s.c0 + c;
-                load8(s.ptr, center, s.dtype, g);
-                if (border) {
-                    const int dr = (h == 1) ? -(h + 1) : ((h == H - 2) ? 2 : 0);
-                    const int dc = (w == 1) ? -(w + 1) : ((w == W - 2) ? 2 : 0);
-                    if (dr) load8(s.ptr, center + (int64_t)dr * Wp * s.ld, s.dtype, g);
-                    if (dc) load8(s.ptr, center + (int64_t)dc * s.ld, s.dtype, g);
-                    if (dr && dc) load8(s.ptr, center + ((int64_t)dr * Wp + dc) * s.ld, s.dtype, g);
-                    if (h == 1 && h == H - 2) {
-                        load8(s.ptr, center + (int64_t)2 * Wp * s.ld, s.dtype, g);
-                        if (dc) load8(s.ptr, center + ((int64_t)2 * Wp + dc) * s.ld, s.dtype, g);
-                    }
-                    if (w == 1 && w == W - 2) {
-                        load8(s.ptr, center + (int64_t)2 * s.ld, s.dtype, g);
-                        if (dr) load8(s.ptr, center + ((int64_t)dr * Wp + 2) * s.ld, s.dtype, g);
-                        if (h == 1 && h == H - 2) load8(s.ptr, center + ((int64_t)2 * Wp + 2) * s.ld, s.dtype, g);
-                    }
-                }
-            } else {
-                load8(s.ptr, pix * s.ld + s.c0 + c, s.dtype, g);
+    for (int u0 = blockIdx.x; u0 < units; u0 += kRU * gridDim.x) {
+        float4 r0[kRU], r1[kRU];
+        uint4 q0[kRU], q1[NSRC > 1 ? kRU : 1];
+        int pixv[kRU];
+        // ---- load phase: everything a pixel needs from HBM, for kRU pixels ----
+#pragma unroll
+        for (int j = 0; j < kRU; j++) {
+            const int u = u0 + j * gridDim.x;
+            const int pix = u * ppb + pl;
+            pixv[j] = (u < units && pix < P) ? pix : -1;
+            if (pixv[j] >= 0) {
+                r0[j] = __ldcs((const float4*)(raw + (int64_t)pix * C + c));
+                r1[j] = __ldcs((const float4*)(raw + (int64_t)pix * C + c + 4));
+                const int n = pix / HW, rem = pix - n * HW, h = rem / W, w = rem - h * W;
+                const int64_t ctr = ((int64_t)n * Hp + h + 1) * Wp + w + 1;
+                if (pre0) q0[j] = *(const uint4*)((const unsigned short*)S0.ptr + (S0.fold ? ctr : (int64_t)pix) * S0.ld + S0.c0 + c);
+                if (NSRC > 1 && pre1) q1[j] = *(const uint4*)((const unsigned short*)S1.ptr + (S1.fold ? ctr : (int64_t)pix) * S1.ld + S1.c0 + c);
             }
         }
-        const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-        __align__(16) __nv_bfloat16 o[8];
+        // ---- compute phase ----
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const float z = r[e] * s_sc[c + e] + s_sh[c + e];
-            float gg = g[e] * (z > 0.f ? 1.f : slope);
-            if (drop) gg *= drop[n * C + c + e];
-            sg[e] += gg;
-            sgx[e] += gg * (r[e] - s_mu[c + e]);
-            o[e] = __float2bfloat16_rn(gg);
+        for (int j = 0; j < kRU; j++) {
+            const int pix = pixv[j];
+            if (pix < 0) continue;
+            const int n = pix / HW, rem = pix - n * HW, h = rem / W, w = rem - h * W;
+            const int64_t ctr = ((int64_t)n * Hp + h + 1) * Wp + w + 1;
+            float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const bool border = (h == 1) | (h == H - 2) | (w == 1) | (w == W - 2);
+            {
+                const int64_t o = (S0.fold ? ctr : (int64_t)pix) * S0.ld + S0.c0 + c;
+                if (pre0) acc_packed(q0[j], S0.dtype, g); else load8(S0.ptr, o, S0.dtype, g);
+                if (S0.fold && border) fold_border(S0, o, h, w, H, W, Wp, g);
+            }
+            if (NSRC > 1) {
+                const int64_t o = (S1.fold ? ctr : (int64_t)pix) * S1.ld + S1.c0 + c;
+                if (pre1) acc_packed(q1[j], S1.dtype, g); else load8(S1.ptr, o, S1.dtype, g);
+                if (S1.fold && border) fold_border(S1, o, h, w, H, W, Wp, g);
+            }
+            const float r[8] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w, r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+            __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float z = r[e] * s_sc[c + e] + s_sh[c + e];
+                float gg = g[e] * (z > 0.f ? 1.f : slope);
+                if (drop) gg *= drop[n * C + c + e];
+                sg[e] += gg;
+                sgx[e] += gg * (r[e] - s_mu[c + e]);
+                o[e] = __float2bfloat16_rn(gg);
+            }
+            *(uint4*)(gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c) = *(const uint4*)o;
         }
-        *(uint4*)(gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c) = *(const uint4*)o;
     }
     // pixel lanes that share a warp (vpp < 32, a power of two there): butterfly over lane bits >= log2(vpp)
     if (vpp < 32 && (vpp & (vpp - 1)) == 0) {
@@ -318,7 +360,7 @@ __global__ void __launch_bounds__(1024, 1) bn_bwd_reduce_fin_kernel(const GSrcs 
         float a = 0.f;
         for (int q = 0; q < prow; q++) a += s_part[q * 2 * C + i];
         if (i >= C) a *= invstd[i - C];
-        partials[(int64_t)blockIdx.x * 2 * C + i] = a;
+        if (a != 0.f) atomicAdd(totals + i, (double)a);
     }
     // ---- ticket: the last block to arrive finalizes ----
     __threadfence();
@@ -327,31 +369,10 @@ __global__ void __launch_bounds__(1024, 1) bn_bwd_reduce_fin_kernel(const GSrcs 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int T = gridDim.x;
-    const int cols = 2 * C;
-    double* s_red = (double*)s_part;                        // [nsl][ncol] fp64 slice sums (<= 1024 doubles)
-    double* s_tot = s_red + 1024;                           // [2C] column totals
-    const int nt = blockDim.x;                              // 64 .. 1024 threads (narrow layers launch fewer)
-    for (int base = 0; base < cols; base += nt) {
-        const int ncol = min(nt, cols - base);
-        const int nsl = max(1, nt / ncol);
-        const int sl = threadIdx.x / ncol, col = threadIdx.x - sl * ncol;
-        __syncthreads();
-        if (sl < nsl) {
-            double a = 0.0;
-            for (int t = sl; t < T; t += nsl) a += (double)__ldcg(partials + (int64_t)t * cols + base + col);
-            s_red[sl * ncol + col] = a;
-        }
-        __syncthreads();
-        if (threadIdx.x < ncol) {
-            double a = 0.0;
-            for (int q = 0; q < nsl; q++) a += s_red[q * ncol + threadIdx.x];
-            s_tot[base + threadIdx.x] = a;
-        }
-    }
-    __syncthreads();
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-        const double sv = s_tot[ch], qv = s_tot[C + ch];
+        const double sv = __ldcg(totals + ch), qv = __ldcg(totals + C + ch);
+        totals[ch] = 0.0;                                   // re-arm for the next launch (stream order / graph replay)
+        totals[C + ch] = 0.0;
         if (dbeta) dbeta[ch] = (float)sv;
         if (dgamma) dgamma[ch] = (float)qv;
         if (coef) {
@@ -363,7 +384,7 @@ __global__ void __launch_bounds__(1024, 1) bn_bwd_reduce_fin_kernel(const GSrcs 
             coef[2 * C + ch] = (float)(gi * ((double)mean[ch] * (double)invstd[ch] * k2 - k1));
         }
     }
-    if (threadIdx.x == 0) *ticket = 0;                      // re-arm for the next launch (stream order / graph replay)
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __restrict__ partials, int T, int C, double count,
@@ -474,44 +495,47 @@ extern "C" int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* 
 
 extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const float* raw, const float* scale, const float* shift,
                                      const float* mean, const float* invstd, const float* drop, float slope, void* gz,
-                                     float* partials, int* ticket, double count, float* dgamma, float* dbeta, const float* gamma,
+                                     double* totals, int* ticket, double count, float* dgamma, float* dbeta, const float* gamma,
                                      float* coef, int N, int H, int W, int C, void* stream) {
     RNR_REQUIRE(C % 8 == 0 && C <= 2048, "rnr_bn_bwd_reduce_fin: bad C=%d", C);
     RNR_REQUIRE(nsrc >= 1 && nsrc <= 2, "rnr_bn_bwd_reduce_fin: nsrc must be 1 or 2");
-    RNR_REQUIRE(ticket && partials, "rnr_bn_bwd_reduce_fin: ticket / partials required");
+    RNR_REQUIRE(ticket && totals, "rnr_bn_bwd_reduce_fin: ticket / totals required");
     RNR_REQUIRE(!coef || gamma, "rnr_bn_bwd_reduce_fin: coef needs gamma");
+    RNR_REQUIRE((int64_t)N * H * W < (1ll << 31), "rnr_bn_bwd_reduce_fin: too many pixels");
     GSrcs gs;
     gs.n = nsrc;
     for (int i = 0; i < nsrc; i++) gs.s[i] = srcs[i];
     const int vpp = C / 8;
-    int ppb = 1024 / vpp;
+    const int64_t P = (int64_t)N * H * W;
+    int ppb = 512 / vpp;
     if (ppb < 1) ppb = 1;
-    if (ppb > W) {                      // narrow images: do not waste pixel lanes (keeps ppb a power of two when vpp is)
-        int p2 = 1;
-        while (p2 * 2 <= W) p2 *= 2;
-        if ((vpp & (vpp - 1)) == 0) ppb = p2 < ppb ? p2 : ppb; else ppb = W;
-    }
+    const bool pow2 = (vpp & (vpp - 1)) == 0;
+    while (ppb > 1 && (int64_t)(ppb / 2) >= P && pow2) ppb /= 2;        // tiny layers: do not launch idle pixel lanes
+    if (!pow2 && ppb > P) ppb = (int)P;
     int threads = vpp * ppb;
     threads = (threads + 31) / 32 * 32;
-    if (threads > 1024) threads = 1024;
-    const bool shuffle = vpp < 32 && (vpp & (vpp - 1)) == 0;
+    RNR_REQUIRE(threads <= 512, "rnr_bn_bwd_reduce_fin: C=%d needs %d threads", C, threads);
+    const bool shuffle = vpp < 32 && pow2;
     const int prow = shuffle ? threads / 32 : ppb;
-    const int64_t nseg = (int64_t)N * H * rnr_cdiv(W, ppb);
-    int T = (int)(nseg < 148 ? nseg : 148);
+    const int64_t units = (P + ppb - 1) / ppb;
+    int T = (int)(units < 148 ? units : 148);
     if (T < 1) T = 1;
-    size_t smem_part = (size_t)prow * 2 * C * sizeof(float);
-    const size_t smem_fin = 1024 * sizeof(double) + (size_t)2 * C * sizeof(double);
-    if (smem_part < smem_fin) smem_part = smem_fin;
-    const size_t smem = 3 * (size_t)C * sizeof(float) + smem_part + 16;
+    const size_t smem = 3 * (size_t)C * sizeof(float) + (size_t)prow * 2 * C * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
     }
     RNR_REQUIRE(smem <= 160 * 1024, "rnr_bn_bwd_reduce_fin: C=%d needs %zu bytes of shared memory", C, smem);
-    bn_bwd_reduce_fin_kernel<<<T, threads, smem, (cudaStream_t)stream>>>(
-        gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, partials, ticket, count, dgamma, dbeta, gamma, coef,
-        N, H, W, C, ppb, prow);
+    if (nsrc == 1)
+        bn_bwd_reduce_fin_kernel<1><<<T, threads, smem, (cudaStream_t)stream>>>(
+            gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
+            N, H, W, C, ppb, prow);
+    else
+        bn_bwd_reduce_fin_kernel<2><<<T, threads, smem, (cudaStream_t)stream>>>(
+            gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
+            N, H, W, C, ppb, prow);
     RNR_LAUNCH_CHECK();
     return 0;
 }

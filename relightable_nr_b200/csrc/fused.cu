@@ -72,6 +72,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(const HeadParams
         const float* T = s_in + px * 13;
         const float a = T[12];
         const bool reflect = r < q.Rs;
+        // background pixel (alpha == 0): the reflected direction is scaled by alpha, so dir = 0 and uv = 0.5 * 0 - 1 exactly; the
+        // diffuse pivots give the same when TBN is zero (how the rasterizer / precompute.py leave uncovered pixels).  Skips the
+        // two normalisations and atan2 / acos for typically half of the image without changing a bit of the result.
+        if (a == 0.f && (reflect || (T[0] == 0.f && T[1] == 0.f && T[2] == 0.f && T[3] == 0.f && T[4] == 0.f && T[5] == 0.f &&
+                                     T[6] == 0.f && T[7] == 0.f && T[8] == 0.f))) {
+            s_uv[px * 2 * R + r] = -1.f;
+            s_uv[px * 2 * R + R + r] = -1.f;
+            continue;                                   // (s_out is pre-zeroed)
+        }
         const float* pv = reflect ? s_piv : s_piv + 3 * kMaxRays;
         const int Rm = reflect ? q.Rs : q.Rd, rr = reflect ? r : r - q.Rs;
         const float px_ = pv[rr], py_ = pv[Rm + rr], pz_ = pv[2 * Rm + rr];
@@ -179,7 +188,7 @@ struct TailParams {
     int ldraw;
     const float* rays_uv;    // [P,2,R]
     const float* albedo;     // [P,8]: diffuse 0..2, specular 3..5
-    const float* lp;         // [Hl,Wl,3]
+    const float4* lp4;       // [Hl*Wl] envmap texels (r, g, b, unused): one 16-byte load per bilinear tap
     int Hl, Wl;
     const float* alpha;      // [P]
     const float* img;        // [N,3,H,W]
@@ -206,17 +215,56 @@ __device__ __forceinline__ float block_sum128(float v, float* s_tmp) {
     return r;
 }
 
-__device__ __forceinline__ void env_taps(const TailParams& q, int64_t pix, int r, Bilin& b) {
-    const float u = q.rays_uv[pix * 2 * q.R + r], v = q.rays_uv[pix * 2 * q.R + q.R + r];
+constexpr int kTailPx = 128;            // pixels (= threads) per block
+// row pitches in shared memory: smallest odd numbers > 3R resp. 2R (thread-per-row access without bank conflicts)
+__host__ __device__ __forceinline__ int raw_pitch(int R) { return (3 * R + 1) | 1; }
+__host__ __device__ __forceinline__ int uv_pitch(int R) { return (2 * R + 1) | 1; }
+
+// Coalesced staging of the block's rows of the last convolution's output ([P, ldraw], 3R used) and of rays_uv ([P, 2R]) into
+// shared memory: the per-pixel threads then walk their own row.  (Reading the rows straight from global memory, one thread
+// per 312-byte row, moved 6x the useful bytes through L1: profiles/r01_tail_v0.)
+__device__ __forceinline__ void stage_rows(const TailParams& q, int64_t p0, int np, float* s_raw, float* s_uv) {
+    const int kRawPitch = raw_pitch(q.R), kUvPitch = uv_pitch(q.R);
+    const int nch = 3 * q.R, nv = (nch + 3) >> 2;
+    for (int i = threadIdx.x; i < np * nv; i += kTailPx) {
+        const int px = i / nv, k = (i - px * nv) * 4;
+        const float4 v = *(const float4*)(q.raw + (p0 + px) * q.ldraw + k);
+        float* d = s_raw + px * kRawPitch + k;
+        d[0] = v.x; if (k + 1 < kRawPitch) d[1] = v.y; if (k + 2 < kRawPitch) d[2] = v.z; if (k + 3 < kRawPitch) d[3] = v.w;
+    }
+    const int nuv = 2 * q.R;
+    for (int i = threadIdx.x; i < np * nuv; i += kTailPx) {
+        const int px = i / nuv, k = i - px * nuv;
+        s_uv[px * kUvPitch + k] = q.rays_uv[p0 * nuv + i];
+    }
+}
+
+__device__ __forceinline__ void env_taps(const TailParams& q, const float* uvrow, int r, Bilin& b) {
+    const float u = uvrow[r], v = uvrow[q.R + r];
     const float x = fminf(u * (float)q.Wl, (float)(q.Wl - 1));
     const float y = fminf(v * (float)q.Hl, (float)(q.Hl - 1));
     b = bilinear_setup(x, y, q.Wl, q.Hl);
 }
 
-__global__ void __launch_bounds__(128) tail_fwd_kernel(const TailParams q) {
+__device__ __forceinline__ void env_color(const TailParams& q, const Bilin& b, float* col) {
+    const float4 t00 = q.lp4[b.i00], t10 = q.lp4[b.i10], t01 = q.lp4[b.i01], t11 = q.lp4[b.i11];
+    col[0] = t00.x * b.w00 + t10.x * b.w10 + t01.x * b.w01 + t11.x * b.w11;
+    col[1] = t00.y * b.w00 + t10.y * b.w10 + t01.y * b.w01 + t11.y * b.w11;
+    col[2] = t00.z * b.w00 + t10.z * b.w10 + t01.z * b.w01 + t11.z * b.w11;
+}
+
+__global__ void __launch_bounds__(kTailPx) tail_fwd_kernel(const TailParams q) {
+    extern __shared__ float s_dyn[];
+    const int kRawPitch = raw_pitch(q.R), kUvPitch = uv_pitch(q.R);
+    float* s_raw = s_dyn;                              // [128][kRawPitch]
+    float* s_uv = s_raw + kTailPx * kRawPitch;         // [128][kUvPitch]
     __shared__ float s_tmp[8];
     const int64_t HW = (int64_t)q.H * q.W;
-    const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * kTailPx;
+    const int64_t pix = p0 + threadIdx.x;
+    const int np = (int)((HW * q.N - p0) < kTailPx ? (HW * q.N - p0) : kTailPx);
+    stage_rows(q, p0, np, s_raw, s_uv);
+    __syncthreads();
     float dsum = 0.f, asum = 0.f, lsum = 0.f;
     if (pix < HW * q.N) {
         const int n = (int)(pix / HW);
@@ -227,19 +275,19 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(const TailParams q) {
 #pragma unroll
         for (int c = 0; c < 3; c++) gt[c] = q.img[((int64_t)n * 3 + c) * HW + p];
         wi = fminf(sqrtf(gt[0] * gt[0] + gt[1] * gt[1] + gt[2] * gt[2]) * 20.f, 1.0f);
-        const float* t = q.raw + pix * q.ldraw;
+        const float* t = s_raw + threadIdx.x * kRawPitch;
+        const float* uvrow = s_uv + threadIdx.x * kUvPitch;
         float ss[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
         for (int r = 0; r < q.R; r++) {
             Bilin b;
-            env_taps(q, pix, r, b);
-            float lt[3];
+            env_taps(q, uvrow, r, b);
+            float col[3], lt[3];
+            env_color(q, b, col);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 lt[c] = (t[r * 3 + c] * 0.5f + 0.5f) * 2.0f;
-                const float col = q.lp[b.i00 * 3 + c] * b.w00 + q.lp[b.i10 * 3 + c] * b.w10 + q.lp[b.i01 * 3 + c] * b.w01 +
-                                  q.lp[b.i11 * 3 + c] * b.w11;
-                const float tt = lt[c] * col;
+                const float tt = lt[c] * col[c];
                 if (r < q.Rs) ss[c] += tt; else sd[c] += tt;
             }
             float x = lt[0], y = lt[1], z = lt[2];
@@ -257,6 +305,7 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(const TailParams q) {
         const int w = (int)(p % q.W), h = (int)(p / q.W);
         const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
         float* ax = q.aux + pix * 12;
+        float axv[12];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float ls = ss[c] / (float)q.Rs;
@@ -265,10 +314,13 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(const TailParams q) {
             if (q.Rd > 0) { ld = sd[c] / (float)q.Rd; od = q.albedo[pix * 8 + c] * ld; }
             const float out = os + od;
             q.final_img[((int64_t)n * 3 + c) * HW + p] = out;
-            ax[c] = ls; ax[3 + c] = ld;
+            axv[c] = ls; axv[3 + c] = ld;
             if (inside) lsum += fabsf(out * a - gt[c] * a);
         }
-        ax[6] = m0; ax[7] = m1; ax[8] = m2; ax[9] = wi;
+        axv[6] = m0; axv[7] = m1; axv[8] = m2; axv[9] = wi; axv[10] = 0.f; axv[11] = 0.f;
+        *(float4*)(ax + 0) = make_float4(axv[0], axv[1], axv[2], axv[3]);
+        *(float4*)(ax + 4) = make_float4(axv[4], axv[5], axv[6], axv[7]);
+        *(float4*)(ax + 8) = make_float4(axv[8], axv[9], axv[10], axv[11]);
     }
     const float bd = block_sum128(dsum, s_tmp);
     const float ba = block_sum128(asum, s_tmp);
@@ -290,29 +342,37 @@ struct TailBwdParams {
     float4* g_lp4;           // [Hl*Wl] (r,g,b,unused) += envmap gradient, or null
 };
 
-constexpr int kTailPitch = 97;          // >= 3R + 1, odd: conflict-free column sums (R <= 32)
-
-__global__ void __launch_bounds__(128) tail_bwd_kernel(const TailBwdParams qq) {
-    extern __shared__ float s_dz[];      // [128][kTailPitch]
+__global__ void __launch_bounds__(kTailPx) tail_bwd_kernel(const TailBwdParams qq) {
+    extern __shared__ float s_dyn[];
+    const int kRawPitch = raw_pitch(qq.f.R), kUvPitch = uv_pitch(qq.f.R);
+    float* s_raw = s_dyn;                              // [128][kRawPitch]: tanh outputs, overwritten in place by dz
+    float* s_uv = s_raw + kTailPx * kRawPitch;         // [128][kUvPitch]
     const TailParams& q = qq.f;
     const int64_t HW = (int64_t)q.H * q.W;
-    const int64_t p0 = (int64_t)blockIdx.x * 128;
+    const int64_t p0 = (int64_t)blockIdx.x * kTailPx;
     const int64_t pix = p0 + threadIdx.x;
+    const int np = (int)((HW * q.N - p0) < kTailPx ? (HW * q.N - p0) : kTailPx);
     const int nch = 3 * q.R;
-    float* mine = s_dz + threadIdx.x * kTailPitch;
+    stage_rows(q, p0, np, s_raw, s_uv);
+    __syncthreads();
+    float* mine = s_raw + threadIdx.x * kRawPitch;
     if (pix < HW * q.N) {
         const int n = (int)(pix / HW);
         const int64_t p = pix % HW;
         const float a = q.alpha[pix];
-        const float* ax = q.aux + pix * 12;
+        const float4 ax0 = *(const float4*)(q.aux + pix * 12), ax1 = *(const float4*)(q.aux + pix * 12 + 4), ax2 = *(const float4*)(q.aux + pix * 12 + 8);
+        const float lsv[3] = {ax0.x, ax0.y, ax0.z}, ldv[3] = {ax0.w, ax1.x, ax1.y};
+        const float m0 = ax1.z, m1 = ax1.w, m2 = ax2.x, wi = ax2.y;
+        const float4 al0 = *(const float4*)(q.albedo + pix * 8), al1 = *(const float4*)(q.albedo + pix * 8 + 4);
+        const float adv[3] = {al0.x, al0.y, al0.z}, asv[3] = {al0.w, al1.x, al1.y};
         const int w = (int)(p % q.W), h = (int)(p / q.W);
         const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
         const double cnt = (double)q.N * 3 * (q.H - 2 * q.crop) * (q.W - 2 * q.crop);
         float Gls[3], Gld[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const float as = q.albedo[pix * 8 + 3 + c], ad = q.albedo[pix * 8 + c];
-            const float ls = ax[c], ld = ax[3 + c];
+            const float as = asv[c], ad = adv[c];
+            const float ls = lsv[c], ld = ldv[c];
             const float os = as * ls;
             const float od = (q.Rd > 0) ? ad * ld : 0.f;
             const float out = os + od;
@@ -326,15 +386,16 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(const TailBwdParams qq) {
             qq.g_alb[((int64_t)n * 6 + 3 + c) * HW + p] = go * ls;
             qq.g_alb[((int64_t)n * 6 + c) * HW + p] = (q.Rd > 0) ? go * ld : 0.f;
         }
-        const float m0 = ax[6], m1 = ax[7], m2 = ax[8];
-        const float s = qq.w_chrom * a * ax[9] / ((float)q.sums[1] * (float)q.R);
-        const float* t = q.raw + pix * q.ldraw;
+        const float s = qq.w_chrom * a * wi / ((float)q.sums[1] * (float)q.R);
+        const float* uvrow = s_uv + threadIdx.x * kUvPitch;
         for (int r = 0; r < q.R; r++) {
             Bilin b;
-            env_taps(q, pix, r, b);
+            env_taps(q, uvrow, r, b);
+            float col[3];
+            env_color(q, b, col);
             float th[3], lt[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) { th[c] = t[r * 3 + c]; lt[c] = (th[c] * 0.5f + 0.5f) * 2.0f; }
+            for (int c = 0; c < 3; c++) { th[c] = mine[r * 3 + c]; lt[c] = (th[c] * 0.5f + 0.5f) * 2.0f; }
             const float nr = fmaxf(sqrtf(lt[0] * lt[0] + lt[1] * lt[1] + lt[2] * lt[2]), 1e-12f);
             const float x = lt[0] / nr, y = lt[1] / nr, z = lt[2] / nr;
             const float cm = x * m0 + y * m1 + z * m2;
@@ -343,9 +404,7 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(const TailBwdParams qq) {
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const float G = (r < q.Rs) ? Gls[c] : Gld[c];
-                const float col = q.lp[b.i00 * 3 + c] * b.w00 + q.lp[b.i10 * 3 + c] * b.w10 + q.lp[b.i01 * 3 + c] * b.w01 +
-                                  q.lp[b.i11 * 3 + c] * b.w11;
-                const float glt = G * col + gch[c];
+                const float glt = G * col[c] + gch[c];
                 mine[r * 3 + c] = glt * (1.f - th[c] * th[c]);
                 gc[c] = G * lt[c];
             }
@@ -356,28 +415,28 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(const TailBwdParams qq) {
                 if (b.w11 != 0.f) atomicAdd(qq.g_lp4 + b.i11, make_float4(gc[0] * b.w11, gc[1] * b.w11, gc[2] * b.w11, 0.f));
             }
         }
-        for (int c = nch; c < kTailPitch; c++) mine[c] = 0.f;
+        for (int c = nch; c < kRawPitch; c++) mine[c] = 0.f;
     } else {
-        for (int c = 0; c < kTailPitch; c++) mine[c] = 0.f;
+        for (int c = 0; c < kRawPitch; c++) mine[c] = 0.f;
     }
     __syncthreads();
     // ---- gz rows: bf16, 8 channels per 16-byte store, channels [0, roundup8(3R)) ----
     const int vpp = (nch + 7) >> 3;
     const int Hp = q.H + 2, Wp = q.W + 2;
-    for (int i = threadIdx.x; i < 128 * vpp; i += 128) {
+    for (int i = threadIdx.x; i < kTailPx * vpp; i += kTailPx) {
         const int px = i / vpp, c = (i - px * vpp) * 8;
         const int64_t pp = p0 + px;
         if (pp >= HW * q.N) break;
         const int w = (int)(pp % q.W), h = (int)((pp / q.W) % q.H), n = (int)(pp / HW);
         __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = __float2bfloat16_rn(s_dz[px * kTailPitch + c + e]);     // (columns >= 3R are zero)
+        for (int e = 0; e < 8; e++) o[e] = __float2bfloat16_rn(c + e < nch ? s_raw[px * kRawPitch + c + e] : 0.f);
         *(uint4*)(qq.gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * qq.ldg + c) = *(const uint4*)o;
     }
     // ---- bias gradient of the last convolution: column sums of the block, one red per channel ----
     if (threadIdx.x < nch) {
         float acc = 0.f;
-        for (int px = 0; px < 128; px++) acc += s_dz[px * kTailPitch + threadIdx.x];
+        for (int px = 0; px < kTailPx; px++) acc += s_raw[px * kRawPitch + threadIdx.x];
         if (acc != 0.f) atomicAdd(qq.dbias + threadIdx.x, acc);
     }
 }
@@ -414,49 +473,52 @@ extern "C" int rnr_head_fwd(const float* const* tex, const int* sizes, int n_lev
     return 0;
 }
 
-static int fill_tail(TailParams& q, const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp,
+static int fill_tail(TailParams& q, const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp4,
                      int Hl, int Wl, const float* alpha, const float* img, int Rs, int Rd, int N, int H, int W, int crop,
                      float* final_img, float* aux, double* sums) {
     RNR_REQUIRE(Rs >= 1 && Rd >= 0 && Rs + Rd <= kMaxRays, "tail: 1..%d rays supported (got %d + %d)", kMaxRays, Rs, Rd);
-    RNR_REQUIRE(ldraw >= 3 * (Rs + Rd), "tail: output pitch %d < %d channels", ldraw, 3 * (Rs + Rd));
+    RNR_REQUIRE(ldraw >= (3 * (Rs + Rd) + 3) / 4 * 4, "tail: output pitch %d < %d channels", ldraw, 3 * (Rs + Rd));
     RNR_REQUIRE(H > 2 * crop && W > 2 * crop, "tail: crop too large");
-    RNR_REQUIRE(raw && rays_uv && albedo && lp && alpha && img && aux && sums, "tail: null argument");
-    q.raw = raw; q.ldraw = ldraw; q.rays_uv = rays_uv; q.albedo = albedo; q.lp = lp; q.Hl = Hl; q.Wl = Wl; q.alpha = alpha;
+    RNR_REQUIRE(raw && rays_uv && albedo && lp4 && alpha && img && aux && sums, "tail: null argument");
+    RNR_REQUIRE(ldraw % 4 == 0 && (((uintptr_t)raw | (uintptr_t)lp4 | (uintptr_t)aux | (uintptr_t)albedo) & 15) == 0, "tail: 16-byte alignment required");
+    q.raw = raw; q.ldraw = ldraw; q.rays_uv = rays_uv; q.albedo = albedo; q.lp4 = (const float4*)lp4; q.Hl = Hl; q.Wl = Wl; q.alpha = alpha;
     q.img = img; q.R = Rs + Rd; q.Rs = Rs; q.Rd = Rd; q.N = N; q.H = H; q.W = W; q.crop = crop; q.final_img = final_img;
     q.aux = aux; q.sums = sums;
     return 0;
 }
 
-extern "C" int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+extern "C" int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp4, int Hl, int Wl,
                             const float* alpha, const float* img, int Rs, int Rd, int N, int H, int W, int crop, float* final_img,
                             float* aux, double* sums, void* stream) {
     TailParams q;
-    int rc = fill_tail(q, raw, ldraw, rays_uv, albedo, lp, Hl, Wl, alpha, img, Rs, Rd, N, H, W, crop, final_img, aux, sums);
+    int rc = fill_tail(q, raw, ldraw, rays_uv, albedo, lp4, Hl, Wl, alpha, img, Rs, Rd, N, H, W, crop, final_img, aux, sums);
     if (rc) return rc;
     RNR_REQUIRE(final_img, "tail: null output");
-    tail_fwd_kernel<<<rnr_cdiv((int64_t)N * H * W, 128), 128, 0, (cudaStream_t)stream>>>(q);
+    const size_t smem = (size_t)kTailPx * (raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd)) * sizeof(float);
+    static bool attr = false;
+    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+    tail_fwd_kernel<<<rnr_cdiv((int64_t)N * H * W, kTailPx), kTailPx, smem, (cudaStream_t)stream>>>(q);
     RNR_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp, int Hl, int Wl,
+extern "C" int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp4, int Hl, int Wl,
                             const float* alpha, const float* img, int Rs, int Rd, int N, int H, int W, int crop, const float* aux,
                             const double* sums, float w_l1, float w_chrom, void* gz, int ldg, float* dbias, float* g_alb,
                             float* g_lp4, void* stream) {
     TailBwdParams qq;
-    int rc = fill_tail(qq.f, raw, ldraw, rays_uv, albedo, lp, Hl, Wl, alpha, img, Rs, Rd, N, H, W, crop, nullptr,
+    int rc = fill_tail(qq.f, raw, ldraw, rays_uv, albedo, lp4, Hl, Wl, alpha, img, Rs, Rd, N, H, W, crop, nullptr,
                        const_cast<float*>(aux), const_cast<double*>(sums));
     if (rc) return rc;
     RNR_REQUIRE(gz && dbias && g_alb, "tail bwd: null output");
     RNR_REQUIRE(ldg % 8 == 0 && ldg >= (3 * (Rs + Rd) + 7) / 8 * 8, "tail bwd: gradient pitch %d too small", ldg);
-    RNR_REQUIRE(3 * (Rs + Rd) + 1 <= kTailPitch, "tail bwd: too many rays");
     RNR_REQUIRE(!g_lp4 || ((uintptr_t)g_lp4 & 15) == 0, "tail bwd: envmap gradient must be 16-byte aligned");
     qq.w_l1 = w_l1; qq.w_chrom = w_chrom; qq.gz = (__nv_bfloat16*)gz; qq.ldg = ldg; qq.dbias = dbias; qq.g_alb = g_alb;
     qq.g_lp4 = (float4*)g_lp4;
-    const size_t smem = (size_t)128 * kTailPitch * sizeof(float);
+    const size_t smem = (size_t)kTailPx * (raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd)) * sizeof(float);
     static bool attr = false;
-    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
-    tail_bwd_kernel<<<rnr_cdiv((int64_t)N * H * W, 128), 128, smem, (cudaStream_t)stream>>>(qq);
+    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+    tail_bwd_kernel<<<rnr_cdiv((int64_t)N * H * W, kTailPx), kTailPx, smem, (cudaStream_t)stream>>>(qq);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -164,6 +164,7 @@ class _LayerState:
     gx_ld: int = 0
     drop: Optional[torch.Tensor] = None
     ticket: Optional[torch.Tensor] = None
+    bwd_totals: Optional[torch.Tensor] = None
 
 
 class UNetEngine:
@@ -244,6 +245,7 @@ class UNetEngine:
                 self.gz[sp.name] = HaloTensor(N, Ho, Wo, ld, gdt, dev, zero=True)
                 st.bwd_partials = self._alloc((148 * 8 * 2 * max(ld, 8),), torch.float32)
                 st.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+                st.bwd_totals = torch.zeros(2 * max(ld, 8), dtype=torch.float64, device=dev)
             # flat gradient storage
             for key in (sp.w_key, sp.b_key, (sp.bn_key + '.weight') if sp.bn_key else None,
                         (sp.bn_key + '.bias') if sp.bn_key else None):
@@ -764,7 +766,7 @@ class UNetEngine:
                 _lib.check(L.rnr_bn_bwd_reduce_fin(arr, len(srcs), st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
                                                    st.mean.data_ptr(), st.invstd.data_ptr(),
                                                    st.drop.data_ptr() if st.drop is not None else None, sp.slope,
-                                                   self.gz[sp.name].ptr, st.bwd_partials.data_ptr(), st.ticket.data_ptr(),
+                                                   self.gz[sp.name].ptr, st.bwd_totals.data_ptr(), st.ticket.data_ptr(),
                                                    float(N * Ho * Wo), dgam, dbet, gam, st.coef.data_ptr() if has_bn else None,
                                                    N, Ho, Wo, Cc, s), 'rnr_bn_bwd_reduce_fin')
                 self.gpu_launches += 1

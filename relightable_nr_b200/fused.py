@@ -121,9 +121,12 @@ class FusedRNRStep:
                                        self.sums.data_ptr(), _s()), 'rnr_tail_fwd')
 
     def _envmap(self):
+        """LightingSH.reconstruct_lp (network.py:622-627) of the current coefficients as [Hl*Wl, 4] texels (r, g, b, 0): the SH
+        coefficients get a zero fourth column, so the tail kernels fetch one 16-byte texel per bilinear tap."""
         lm = self.pipe.lighting_model
         with torch.no_grad():
-            return lm.reconstruct_lp(lm.coeff[self.pipe.lighting_idx]).contiguous()
+            coeff4 = torch.nn.functional.pad(lm.coeff[self.pipe.lighting_idx], (0, 1))
+            return _sph_harm.reconstruct_sh(coeff4, lm.basis_val_recon).contiguous()
 
     # ------------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
