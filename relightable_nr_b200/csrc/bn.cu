@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const GSrcs srcs,
 //     fp32 partials is order-independent to ~1e-16, far below the fp32 result's rounding);
 //   * the LAST block to finish (threadfence + ticket) turns the totals into dgamma / dbeta / the fused apply coefficients,
 //     re-zeroes the accumulator and re-arms the ticket -- the separate finalize launch disappears.
-constexpr int kRU = 4;
+constexpr int kRU = 2;
 
 __device__ __forceinline__ void acc_packed(const uint4& u, int dtype, float* out) {
     const unsigned short* us = (const unsigned short*)&u;
@@ -252,6 +252,21 @@ __device__ __noinline__ void fold_border(const rnr_gsrc_t s, int64_t center, int
     }
 }
 
+// pixel index -> (n, h, w); shifts when H*W and W are powers of two (every U-Net level of a 2^k image), divisions otherwise
+__device__ __forceinline__ void split_pix(int pix, int HW, int W, int lhw, int lw, int& n, int& h, int& w) {
+    if (lhw >= 0) {
+        n = pix >> lhw;
+        const int rem = pix & (HW - 1);
+        h = rem >> lw;
+        w = rem & (W - 1);
+    } else {
+        n = pix / HW;
+        const int rem = pix - n * HW;
+        h = rem / W;
+        w = rem - h * W;
+    }
+}
+
 template <int NSRC>
 __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs srcs, const float* __restrict__ raw,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -260,18 +275,27 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
                                      __nv_bfloat16* __restrict__ gz, double* __restrict__ totals, int* __restrict__ ticket,
                                      double count, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      const float* __restrict__ gamma, float* __restrict__ coef,
-                                     int N, int H, int W, int C, int ppb, int prow) {
-    extern __shared__ float smem[];    // [3][C] scale / shift / mean, then [prow][2C] partial rows
+                                     int N, int H, int W, int C, int ppb, int prow, int lhw, int lw) {
+    extern __shared__ float smem[];    // [prow][2C] partial rows
     __shared__ int s_last;
-    float* s_sc = smem;
-    float* s_sh = s_sc + C;
-    float* s_mu = s_sh + C;
-    float* s_part = s_mu + C;
+    float* s_part = smem;
     const int vpp = C >> 3;
     const int cv = threadIdx.x % vpp, pl = threadIdx.x / vpp;
     const int c = cv * 8;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) { s_sc[i] = scale[i]; s_sh[i] = shift[i]; s_mu[i] = mean[i]; }
-    __syncthreads();
+    // per-channel constants of this thread's 8 channels stay in registers for the whole kernel (the profile of the version that
+    // re-read them from shared memory per pixel was issue-bound: 350 instructions per pixel vector at 16 warps / SM)
+    float sc[8], sh[8], mu[8], dr[8];
+    {
+        const float4 a0 = *(const float4*)(scale + c), a1 = *(const float4*)(scale + c + 4);
+        const float4 b0 = *(const float4*)(shift + c), b1 = *(const float4*)(shift + c + 4);
+        const float4 m0 = *(const float4*)(mean + c), m1 = *(const float4*)(mean + c + 4);
+        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+        mu[0] = m0.x; mu[1] = m0.y; mu[2] = m0.z; mu[3] = m0.w; mu[4] = m1.x; mu[5] = m1.y; mu[6] = m1.z; mu[7] = m1.w;
+#pragma unroll
+        for (int e = 0; e < 8; e++) dr[e] = (drop && N == 1) ? drop[c + e] : 1.f;
+    }
+    const bool drop_per_pixel = drop && N > 1;
     const int Hp = H + 2, Wp = W + 2;
     const int HW = H * W;
     const int P = N * HW;
@@ -297,7 +321,8 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
             if (pixv[j] >= 0) {
                 r0[j] = __ldcs((const float4*)(raw + (int64_t)pix * C + c));
                 r1[j] = __ldcs((const float4*)(raw + (int64_t)pix * C + c + 4));
-                const int n = pix / HW, rem = pix - n * HW, h = rem / W, w = rem - h * W;
+                int n, h, w;
+                split_pix(pix, HW, W, lhw, lw, n, h, w);
                 const int64_t ctr = ((int64_t)n * Hp + h + 1) * Wp + w + 1;
                 if (pre0) q0[j] = *(const uint4*)((const unsigned short*)S0.ptr + (S0.fold ? ctr : (int64_t)pix) * S0.ld + S0.c0 + c);
                 if (NSRC > 1 && pre1) q1[j] = *(const uint4*)((const unsigned short*)S1.ptr + (S1.fold ? ctr : (int64_t)pix) * S1.ld + S1.c0 + c);
@@ -308,7 +333,8 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
         for (int j = 0; j < kRU; j++) {
             const int pix = pixv[j];
             if (pix < 0) continue;
-            const int n = pix / HW, rem = pix - n * HW, h = rem / W, w = rem - h * W;
+            int n, h, w;
+            split_pix(pix, HW, W, lhw, lw, n, h, w);
             const int64_t ctr = ((int64_t)n * Hp + h + 1) * Wp + w + 1;
             float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const bool border = (h == 1) | (h == H - 2) | (w == 1) | (w == W - 2);
@@ -326,14 +352,14 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
             __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                const float z = r[e] * s_sc[c + e] + s_sh[c + e];
+                const float z = r[e] * sc[e] + sh[e];
                 float gg = g[e] * (z > 0.f ? 1.f : slope);
-                if (drop) gg *= drop[n * C + c + e];
+                gg *= drop_per_pixel ? drop[n * C + c + e] : dr[e];
                 sg[e] += gg;
-                sgx[e] += gg * (r[e] - s_mu[c + e]);
+                sgx[e] += gg * (r[e] - mu[e]);
                 o[e] = __float2bfloat16_rn(gg);
             }
-            *(uint4*)(gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c) = *(const uint4*)o;
+            *(uint4*)(gz + ctr * C + c) = *(const uint4*)o;
         }
     }
     // pixel lanes that share a warp (vpp < 32, a power of two there): butterfly over lane bits >= log2(vpp)
@@ -520,7 +546,15 @@ extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const flo
     const int64_t units = (P + ppb - 1) / ppb;
     int T = (int)(units < 148 ? units : 148);
     if (T < 1) T = 1;
-    const size_t smem = 3 * (size_t)C * sizeof(float) + (size_t)prow * 2 * C * sizeof(float);
+    const size_t smem = (size_t)prow * 2 * C * sizeof(float);
+    int lhw = -1, lw = -1;
+    {
+        const int HW = H * W;
+        if ((HW & (HW - 1)) == 0 && (W & (W - 1)) == 0) {
+            lhw = 0; while ((1 << lhw) < HW) lhw++;
+            lw = 0; while ((1 << lw) < W) lw++;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -531,11 +565,11 @@ extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const flo
     if (nsrc == 1)
         bn_bwd_reduce_fin_kernel<1><<<T, threads, smem, (cudaStream_t)stream>>>(
             gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
-            N, H, W, C, ppb, prow);
+            N, H, W, C, ppb, prow, lhw, lw);
     else
         bn_bwd_reduce_fin_kernel<2><<<T, threads, smem, (cudaStream_t)stream>>>(
             gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
-            N, H, W, C, ppb, prow);
+            N, H, W, C, ppb, prow, lhw, lw);
     RNR_LAUNCH_CHECK();
     return 0;
 }
