@@ -157,6 +157,21 @@ int  rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr_wprep_pla
 void rnr_wprep_plan_destroy(rnr_wprep_plan_t* plan);
 int  rnr_wprep_run(const rnr_wprep_plan_t* plan, void* stream);
 
+/* Weight-gradient un-transpose (one launch for all layers): the weight-gradient problem may point `dw` at a scratch buffer in
+ * GEMM order [tap][co][ci] (s_co = cin, s_ci = 1, tap offset = tap*cout*cin), which lets the tcgen05 kernel reduce with 128-bit
+ * vector atomics; this pass writes the parameter's own layout (autograd of nn.Conv2d / nn.ConvTranspose2d w.r.t. weight,
+ * pytorch_prototyping.py:112-115,155-160,242-264):   dst[co*s_co + ci*s_ci + t] = src[(t*cout + co)*cin + ci]               */
+typedef struct {
+    const float* src;          /* scratch [ntaps, cout, cin] */
+    float*       dst;          /* parameter-layout gradient */
+    int32_t      cout, cin, ntaps;
+    int64_t      s_co, s_ci;   /* element strides of co / ci in dst (taps are contiguous) */
+} rnr_wunpack_job_t;
+typedef struct rnr_wunpack_plan rnr_wunpack_plan_t;
+int  rnr_wgrad_unpack_plan_create(const rnr_wunpack_job_t* jobs, int njobs, rnr_wunpack_plan_t** plan);
+void rnr_wgrad_unpack_plan_destroy(rnr_wunpack_plan_t* plan);
+int  rnr_wgrad_unpack_run(const rnr_wunpack_plan_t* plan, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* BatchNorm2d (batch statistics) + activation + Dropout2d                                     */
 /*   replaces nn.BatchNorm2d / LeakyReLU / ReLU / Dropout2d of pytorch_prototyping.py:177-197,  */

@@ -59,6 +59,11 @@ class WPrepJob(C.Structure):
                 ("tapoff", C.c_int32 * 16), ("chunked", C.c_int32)]
 
 
+class WUnpackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("cout", C.c_int32), ("cin", C.c_int32), ("ntaps", C.c_int32),
+                ("s_co", C.c_int64), ("s_ci", C.c_int64)]
+
+
 class RnrError(RuntimeError):
     pass
 
@@ -93,6 +98,8 @@ def lib():
         "rnr_weight_prep": [vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, vp, i32, vp],
         "rnr_wprep_plan_create": [C.POINTER(WPrepJob), i32, C.POINTER(vp)],
         "rnr_wprep_run": [vp, vp],
+        "rnr_wgrad_unpack_plan_create": [C.POINTER(WUnpackJob), i32, C.POINTER(vp)],
+        "rnr_wgrad_unpack_run": [vp, vp],
         "rnr_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp],
         "rnr_bn_act_fwd": [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
@@ -114,6 +121,8 @@ def lib():
     L.rnr_wgrad_plan_destroy.restype = None
     L.rnr_wprep_plan_destroy.argtypes = [vp]
     L.rnr_wprep_plan_destroy.restype = None
+    L.rnr_wgrad_unpack_plan_destroy.argtypes = [vp]
+    L.rnr_wgrad_unpack_plan_destroy.restype = None
     _register_optional(L)
     _lib = L
     return L

@@ -79,6 +79,7 @@ struct rnr_wgrad_plan {
     int th, tw, tiles_y, tiles_x;
     int smem_bytes, grid, stages;
     int n_work;          // tc work items
+    int vec;             // 1: dW destination is ci-contiguous -> 128-bit vector reductions
     int* d_work_tab;     // [n_work, 8]
 };
 

@@ -34,7 +34,7 @@ struct WorkItem {          // 8 ints
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const WorkItem* __restrict__ work, int n_work,
-                int th, int tw, int tiles_y, int tiles_x) {
+                int th, int tw, int tiles_y, int tiles_x, int vec) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* aux = smem + (size_t)kStages * kStageBytes;
@@ -138,14 +138,31 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
             const int ncols = wi.n_ci_box * 64;
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
-                uint32_t rv[16];
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t rv[32];
                 tmem_ld16(taddr + (uint32_t)c0, rv);
+                if (c0 + 16 < ncols) tmem_ld16(taddr + (uint32_t)(c0 + 16), rv + 16);
                 tmem_ld_wait();
                 if (co < p.cout) {
+                    if (vec) {
+                        // dW scratch is ci-contiguous (s_ci == 1): one 128-bit vector reduction per 4 input channels -- 4x fewer
+                        // L2 atomic operations than the scalar form, whose lanes (co rows, s_co apart) never share a sector
 #pragma unroll
-                    for (int e = 0; e < 16; e++)
-                        if (c0 + e < wi.ci_valid) atomicAdd(dst + (int64_t)(c0 + e) * p.s_ci, __uint_as_float(rv[e]));
+                        for (int j = 0; j < 8; j++) {
+                            const int ci = c0 + 4 * j;
+                            if (ci + 3 < wi.ci_valid)
+                                atomicAdd((float4*)(dst + ci), make_float4(__uint_as_float(rv[4 * j]), __uint_as_float(rv[4 * j + 1]),
+                                                                           __uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3])));
+                            else
+#pragma unroll
+                                for (int e = 0; e < 4; e++)
+                                    if (ci + e < wi.ci_valid) atomicAdd(dst + ci + e, __uint_as_float(rv[4 * j + e]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++)
+                            if (c0 + e < wi.ci_valid) atomicAdd(dst + (int64_t)(c0 + e) * p.s_ci, __uint_as_float(rv[e]));
+                    }
                 }
             }
             tc_fence_before();
@@ -208,6 +225,10 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
             work.push_back(w);
         }
     }
+    // vector reductions need a ci-contiguous, 16-byte aligned destination for every (tap, ci chunk)
+    pl->vec = (prob->s_ci == 1 && prob->s_co % 4 == 0 && ((uintptr_t)prob->dw & 15) == 0) ? 1 : 0;
+    for (int t = 0; t < prob->n_taps && pl->vec; t++)
+        if (prob->taps[t].off % 4 != 0 || prob->taps[t].ci0 % 4 != 0) pl->vec = 0;
     pl->n_work = (int)work.size();
     RNR_CHECK(cudaMalloc(&pl->d_work_tab, work.size() * sizeof(WorkItem)));
     RNR_CHECK(cudaMemcpy(pl->d_work_tab, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
@@ -226,7 +247,7 @@ int rnr_wgrad_tc_run(const rnr_wgrad_plan* pl, cudaStream_t stream) {
     memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
     memcpy(maps.g, pl->tmap_g, sizeof(maps.g));
     wgrad_tc_kernel<<<pl->grid, kThreads, pl->smem_bytes, stream>>>(maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
-                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x);
+                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec);
     RNR_LAUNCH_CHECK();
     return 0;
 }

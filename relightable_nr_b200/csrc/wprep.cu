@@ -172,3 +172,87 @@ extern "C" int rnr_wprep_run(const rnr_wprep_plan_t* p, void* stream) {
     RNR_LAUNCH_CHECK();
     return 0;
 }
+
+// -------------------------------------------------------------------------------------------------------------------
+// Weight-gradient un-transpose.  The tcgen05 weight-gradient kernel accumulates dW in GEMM order [tap][co][ci] (ci contiguous:
+// every thread of its epilogue owns one co row and issues 128-bit vector reductions) instead of the parameter's own order
+// ([co][ci][kh][kw] for nn.Conv2d, [ci][co][kh][kw] for nn.ConvTranspose2d), where the 4-byte reductions of a warp land in 32
+// different sectors.  One batched launch per step moves every layer's gradient into the flat fp32 gradient buffer that
+// torch.optim.Adam reads:   dst[co*s_co + ci*s_ci + t] = src[(t*cout + co)*cin + ci].
+// -------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct WUnJob {
+    const float* src;
+    float* dst;
+    int32_t cout, cin, ntaps, tiles_c;
+    int64_t s_co, s_ci;
+    int32_t blk0, nblk;
+};
+
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(const WUnJob* __restrict__ jobs, const int* __restrict__ blk2job) {
+    __shared__ float tile[MAXT][CB + 1];
+    const WUnJob& J = jobs[blk2job[blockIdx.x]];
+    const int local = blockIdx.x - J.blk0;
+    const int co = local / J.tiles_c, c0 = (local - co * J.tiles_c) * CB;
+    const int nc = min(CB, J.cin - c0);
+    for (int i = threadIdx.x; i < J.ntaps * CB; i += 256) {
+        const int t = i / CB, cc = i - t * CB;
+        if (cc < nc) tile[t][cc] = __ldcs(J.src + ((int64_t)t * J.cout + co) * J.cin + c0 + cc);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc * J.ntaps; i += 256) {
+        const int cc = i / J.ntaps, t = i - cc * J.ntaps;
+        J.dst[(int64_t)co * J.s_co + (int64_t)(c0 + cc) * J.s_ci + t] = tile[t][cc];
+    }
+}
+
+}  // namespace
+
+struct rnr_wunpack_plan {
+    WUnJob* d_jobs = nullptr;
+    int* d_blk2job = nullptr;
+    int nblocks = 0;
+};
+
+extern "C" int rnr_wgrad_unpack_plan_create(const rnr_wunpack_job_t* jobs, int njobs, rnr_wunpack_plan_t** out) {
+    RNR_REQUIRE(jobs && out && njobs >= 1, "rnr_wgrad_unpack_plan_create: bad arguments");
+    std::vector<WUnJob> h(njobs);
+    int blk = 0;
+    for (int i = 0; i < njobs; i++) {
+        const rnr_wunpack_job_t& s = jobs[i];
+        RNR_REQUIRE(s.ntaps >= 1 && s.ntaps <= MAXT, "wgrad unpack: 1..%d taps, got %d", MAXT, s.ntaps);
+        WUnJob& d = h[i];
+        d.src = s.src; d.dst = s.dst; d.cout = s.cout; d.cin = s.cin; d.ntaps = s.ntaps; d.s_co = s.s_co; d.s_ci = s.s_ci;
+        d.tiles_c = rnr_cdiv(s.cin, CB);
+        d.blk0 = blk;
+        d.nblk = s.cout * d.tiles_c;
+        blk += d.nblk;
+    }
+    rnr_wunpack_plan* p = new rnr_wunpack_plan();
+    p->nblocks = blk;
+    RNR_CHECK(cudaMalloc(&p->d_jobs, sizeof(WUnJob) * njobs));
+    RNR_CHECK(cudaMemcpy(p->d_jobs, h.data(), sizeof(WUnJob) * njobs, cudaMemcpyHostToDevice));
+    std::vector<int> b2j(blk);
+    for (int i = 0; i < njobs; i++)
+        for (int b = 0; b < h[i].nblk; b++) b2j[h[i].blk0 + b] = i;
+    RNR_CHECK(cudaMalloc(&p->d_blk2job, sizeof(int) * blk));
+    RNR_CHECK(cudaMemcpy(p->d_blk2job, b2j.data(), sizeof(int) * blk, cudaMemcpyHostToDevice));
+    *out = p;
+    return 0;
+}
+
+extern "C" void rnr_wgrad_unpack_plan_destroy(rnr_wunpack_plan_t* p) {
+    if (!p) return;
+    cudaFree(p->d_jobs);
+    cudaFree(p->d_blk2job);
+    delete p;
+}
+
+extern "C" int rnr_wgrad_unpack_run(const rnr_wunpack_plan_t* p, void* stream) {
+    RNR_REQUIRE(p, "rnr_wgrad_unpack_run: null plan");
+    wgrad_unpack_kernel<<<p->nblocks, 256, 0, (cudaStream_t)stream>>>(p->d_jobs, p->d_blk2job);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+

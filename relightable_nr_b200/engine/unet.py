@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import _lib
-from .._lib import BF16, EPI_BIAS, EPI_STATS, EPI_TANH, F16, F32, ConvProblem, GSrc, KStep, WgradProblem, WPrepJob, WTap
+from .._lib import BF16, EPI_BIAS, EPI_STATS, EPI_TANH, F16, F32, ConvProblem, GSrc, KStep, WgradProblem, WPrepJob, WTap, WUnpackJob
 from .views import HaloTensor, tile_shape
 
 _TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
@@ -117,7 +117,8 @@ class _Plan:
         try:
             L = _lib.lib()
             if self.h:
-                {'conv': L.rnr_conv_plan_destroy, 'wgrad': L.rnr_wgrad_plan_destroy, 'wprep': L.rnr_wprep_plan_destroy}[self.kind](self.h)
+                {'conv': L.rnr_conv_plan_destroy, 'wgrad': L.rnr_wgrad_plan_destroy, 'wprep': L.rnr_wprep_plan_destroy,
+                 'wunpack': L.rnr_wgrad_unpack_plan_destroy}[self.kind](self.h)
         except Exception:
             pass
 
@@ -254,8 +255,30 @@ class UNetEngine:
                     self.grad_slices[key] = (grad_numel, n)
                     grad_numel += _rup(n, 4)
         self.grad_flat = self._alloc((max(grad_numel, 4),), torch.float32, zero=True) if self.need_backward else None
+        # weight gradients are accumulated in GEMM order [tap][co][ci] (vector reductions, see csrc/wprep.cu: wgrad_unpack) and
+        # moved into grad_flat by one batched launch at the end of the backward pass
+        self.wscratch = None
+        self.wscratch_slices = {}
+        self._wunpack_jobs = []
+        if self.need_backward and self.wgrad_impl == 1:
+            n = 0
+            for sp in self.specs:
+                if sum(sp.cin) % 4 == 0:
+                    k = 9 if sp.kind == 'c3' else 16
+                    self.wscratch_slices[sp.name] = (n, k * sp.cout * sum(sp.cin))
+                    n += _rup(k * sp.cout * sum(sp.cin), 4)
+            if n:
+                self.wscratch = self._alloc((n,), torch.float32, zero=True)
         for sp in self.specs:
             self._build_layer(self.layers[sp.name])
+        self.wunpack_plan = None
+        if self._wunpack_jobs:
+            arr = (WUnpackJob * len(self._wunpack_jobs))()
+            for j, (src, dst, cout, cin, ntaps, s_co, s_ci) in zip(arr, self._wunpack_jobs):
+                j.src, j.dst, j.cout, j.cin, j.ntaps, j.s_co, j.s_ci = src, dst, cout, cin, ntaps, s_co, s_ci
+            h = C.c_void_p()
+            _lib.check(self.L.rnr_wgrad_unpack_plan_create(arr, len(self._wunpack_jobs), C.byref(h)), 'rnr_wgrad_unpack_plan_create')
+            self.wunpack_plan = _Plan(h, 'wunpack')
         fwd_items = [w for sp in self.specs for w in self.layers[sp.name].wprep_fwd]
         all_items = fwd_items + [w for sp in self.specs for w in self.layers[sp.name].wprep_dgrad]
         self.wprep_fwd_plan = self._wprep_plan(fwd_items)
@@ -513,6 +536,14 @@ class UNetEngine:
         wp.cout = cout
         g0, gn = self.grad_slices[sp.w_key]
         wp.dw = self.grad_flat.data_ptr() + 4 * g0
+        if sp.name in self.wscratch_slices:
+            # scratch destination [tap][co][ci]: tap offset = kernel tap index * cout * cin
+            w0, _wn = self.wscratch_slices[sp.name]
+            self._wunpack_jobs.append((self.wscratch.data_ptr() + 4 * w0, wp.dw, cout, cin_tot, kk, int(wp.s_co), int(wp.s_ci)))
+            for i in range(len(wtaps)):
+                tarr[i].off = int(tarr[i].off) * cout * cin_tot
+            wp.dw = self.wscratch.data_ptr() + 4 * w0
+            wp.s_co, wp.s_ci = cin_tot, 1
         h = C.c_void_p()
         _lib.check(self.L.rnr_wgrad_plan_create(C.byref(wp), self.wgrad_impl, C.byref(h)), 'rnr_wgrad_plan_create')
         st.wgrad_plan = _Plan(h, 'wgrad')
@@ -723,6 +754,12 @@ class UNetEngine:
             out.append(g)
         return out
 
+    def zero_grads(self):
+        """Zero the accumulation targets of the backward pass (flat gradient buffer + weight-gradient scratch)."""
+        self.grad_flat.zero_()
+        if self.wscratch is not None:
+            self.wscratch.zero_()
+
     def backward_from_nchw(self, grad_out: torch.Tensor):
         """grad_out: d loss / d (tanh output), NCHW fp32.  Fills self.grad_flat; returns grad wrt the input
         channels ``input_grad_range`` as NCHW fp32 (or None)."""
@@ -730,8 +767,7 @@ class UNetEngine:
         L, s = self.L, self._stream()
         sp = self.specs[-1]
         st = self.layers['out']
-        self.grad_flat.zero_()
-        self.gpu_launches += 1
+        self.zero_grads()
         go = grad_out.contiguous()
         th = st.raw
         if not self.final_tanh:      # linear output: d/d raw = grad * (1 - 0^2)
@@ -783,6 +819,9 @@ class UNetEngine:
                 self.gpu_launches += 1
             if st.dgrad_plans:
                 self._mark('dgrad', sp.name, t1)
+        if self.wunpack_plan is not None:
+            _lib.check(L.rnr_wgrad_unpack_run(self.wunpack_plan.h, s), 'rnr_wgrad_unpack_run')
+            self.gpu_launches += 1
         st = self.layers['in']
         if st.gx is None:
             return None

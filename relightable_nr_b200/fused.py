@@ -184,7 +184,7 @@ class FusedRNRStep:
             eng.prepare_weights_split('fwd')
             ev_w = torch.cuda.Event()
             ev_w.record(side)
-            eng.grad_flat.zero_()
+            eng.zero_grads()
             self.g_lp4.zero_()
             for g in self.tex_grads:
                 g.zero_()
