@@ -93,6 +93,11 @@ typedef struct rnr_conv_plan rnr_conv_plan_t;   /* opaque: device k-step table +
 
 /* impl: 0 = SIMT validation kernel, 1 = tcgen05/TMA kernel */
 int  rnr_conv_plan_create(const rnr_conv_problem_t* prob, int impl, rnr_conv_plan_t** plan);
+/* n <= 4 sub-problems differing only in tap offsets (dx, dy), wmat (stacked row-wise in one buffer: sub s at byte offset
+ * s * n_rows_w * n_ksteps * bk * 2 from sub 0) and output parity (out_py, out_px) as ONE launch: the four output parities of
+ * nn.ConvTranspose2d(4, 2, 1) forward (pytorch_prototyping.py:155-160) or of the data gradient of nn.Conv2d(4, stride 2)
+ * (:242-264).  Returns cudaErrorNotSupported without a plan when they cannot be fused (create one plan per problem then). */
+int  rnr_conv_plan_create_multi(const rnr_conv_problem_t* probs, int n, int impl, rnr_conv_plan_t** plan);
 void rnr_conv_plan_destroy(rnr_conv_plan_t* plan);
 int  rnr_conv_run(const rnr_conv_plan_t* plan, void* stream);
 int  rnr_conv_plan_tiles_m(const rnr_conv_plan_t* plan);

@@ -89,6 +89,7 @@ def lib():
     L.rnr_launch_count.argtypes = []
     sigs = {
         "rnr_conv_plan_create": [C.POINTER(ConvProblem), i32, C.POINTER(vp)],
+        "rnr_conv_plan_create_multi": [C.POINTER(ConvProblem), i32, i32, C.POINTER(vp)],
         "rnr_conv_run": [vp, vp],
         "rnr_conv_plan_tiles_m": [vp],
         "rnr_conv_plan_stat_rows": [vp],

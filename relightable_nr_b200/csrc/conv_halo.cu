@@ -33,12 +33,15 @@ constexpr int kAllocWarp = 16;         // TMEM allocate / free
 constexpr int kProducerWarp = 18;      // TMA
 constexpr int kMmaWarp = 19;           // tcgen05.mma issue
 constexpr int TH = 16, TW = 8;          // output tile (pixels): M = 128, one 8-row UMMA group per image row
-constexpr int kMaxGroups = 64;
+constexpr int kMaxGroups = 128;
+constexpr int kMaxSub = 4;           // sub-problems fused into one launch (the 4 output parities of a stride-2 layer)
 constexpr int kMaxTaps = 512;
 constexpr int kAStages = 2;
 
 struct HaloCfg {           // per-problem constants of the tap pattern (kernel parameter -> constant bank -> uniform registers)
-    int a_off[16];         // byte offset of tap k inside the halo tile (identical for every group)
+    int a_off[kMaxSub][16];   // byte offset of tap k inside the halo tile (identical for every group of a sub-problem)
+    int out_py[kMaxSub], out_px[kMaxSub];
+    int nsub, sub_rows;       // sub-problem s uses Wmat rows [s*sub_rows, (s+1)*sub_rows) and groups [s*n_groups, ...)
 };
 
 struct HaloMaps {
@@ -97,13 +100,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     const int crank = cs > 1 ? (int)cluster_ctarank() : 0;
     const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
     const int m_groups = (p.tiles_m + cs - 1) / cs;
-    const int total_tiles = m_groups * tiles_n;             // cluster-level work items
+    const int per_sub = m_groups * tiles_n;
+    const int total_tiles = hc.nsub * per_sub;              // cluster-level work items: (sub-problem, M group, N tile)
     const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
     long long* tr = (g_trace && blockIdx.x < 4) ? g_trace + (size_t)blockIdx.x * 4 * 64 : nullptr;
     int ti = 0;
     if (threadIdx.x == 0) { int z = 0; trace(tr, 3, z); }
 
-    for (int i = threadIdx.x; i < n_groups; i += kThreads) s_groups[i] = groups[i];
+    for (int i = threadIdx.x; i < n_groups * hc.nsub; i += kThreads) s_groups[i] = groups[i];
     for (int i = threadIdx.x; i < n_taps; i += kThreads) s_taps[i] = taps[i];
     for (int i = threadIdx.x; i < 1024; i += kThreads) s_acc[i] = 0.f;
 
@@ -130,12 +134,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
-            const int tile_m = (t / tiles_n) * cs + crank, tile_n = t % tiles_n;
+            const int sub = t / per_sub, ts = t - sub * per_sub;
+            const int tile_m = (ts / tiles_n) * cs + crank, tile_n = ts % tiles_n;
             const int tx_ = tile_m % p.tiles_x, ty_ = (tile_m / p.tiles_x) % p.tiles_y, n_ = tile_m / (p.tiles_x * p.tiles_y);
-            const int x0 = tx_ * TW, y0 = ty_ * TH, n0 = tile_n * bn;
+            const int x0 = tx_ * TW, y0 = ty_ * TH, n0 = tile_n * bn + sub * hc.sub_rows;
             if (lane == 0) trace(tr, 0, ti);
             for (int g = 0; g < n_groups; g++) {
-                const HaloGroup G = s_groups[g];
+                const HaloGroup G = s_groups[sub * n_groups + g];
                 mbar_wait(&aempty[as], aph ^ 1);
                 if (elect_one_sync()) {
                     if (dbg & 16) mbar_arrive(&afull[as]);
@@ -182,6 +187,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         for (int t = cid; t < total_tiles; t += ncl, it++) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
+            const int sub = t / per_sub;
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             if (lane == 0) trace(tr, 1, ti);
@@ -201,7 +207,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     if (elect_one_sync()) {
                         if (!(dbg & 8)) {
                             for (int tt = 0; tt < T; tt++) {
-                                const uint64_t da = make_halo_desc(a_base + (uint32_t)hc.a_off[k + tt], sbo);
+                                const uint64_t da = make_halo_desc(a_base + (uint32_t)hc.a_off[sub][k + tt], sbo);
                                 const uint64_t db = make_kmajor_desc(b_base + (uint32_t)tt * b_tap_bytes, 64);
 #pragma unroll
                                 for (int kk = 0; kk < 4; kk++) {
@@ -242,13 +248,14 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         for (int t = cid; t < total_tiles; t += ncl, it++) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int tile_m = (t / tiles_n) * cs + crank, tile_n = t % tiles_n;
+            const int sub = t / per_sub, ts = t - sub * per_sub;
+            const int tile_m = (ts / tiles_n) * cs + crank, tile_n = ts % tiles_n;
             const int tx_ = tile_m % p.tiles_x, ty_ = (tile_m / p.tiles_x) % p.tiles_y, n_ = tile_m / (p.tiles_x * p.tiles_y);
             const int y = ty_ * TH + ry, x = tx_ * TW + rx, n0 = tile_n * bn;
             const bool valid = (y < p.mY && x < p.mX && tile_m < p.tiles_m);
             if (hcol == 0)      // output element offset of every tile row (-1: outside the image)
-                s_rowoff[r] = valid ? ((int64_t)n_ * p.out_sn + (int64_t)(y * p.out_my + p.out_py) * p.out_sy +
-                                       (int64_t)(x * p.out_mx + p.out_px) * p.out_sx) : (int64_t)-1;
+                s_rowoff[r] = valid ? ((int64_t)n_ * p.out_sn + (int64_t)(y * p.out_my + hc.out_py[sub]) * p.out_sy +
+                                       (int64_t)(x * p.out_mx + hc.out_px[sub]) * p.out_sx) : (int64_t)-1;
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -407,57 +414,95 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // Returns 0 and sets pl->halo = 1 when the problem fits the halo scheme, 0 with pl->halo = 0 when it does not
 // (the caller then uses the generic per-tap kernel), or an error code.
-int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
+// `nsub` > 1 fuses sub-problems that differ only in their taps' (dx, dy), weight matrix and output parity -- the four output
+// parities of a ConvTranspose2d(4, 2, 1) forward or of a Conv2d(4, stride 2) data gradient -- into ONE launch: the tile index
+// gets a sub-problem digit.  Their weight matrices must be stacked row-wise in one buffer (sub s at rows [s*n_rows_w, ...)).
+int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, int nsub) {
+    const rnr_conv_problem_t* prob = probs;
     pl->halo = 0;
     const char* env = getenv("RNR_CONV_HALO");
     if (env && env[0] == '0') return 0;
+    if (nsub < 1 || nsub > kMaxSub) return 0;
     if (prob->bk != 64) return 0;
     if (prob->cout > 512 && (prob->epi & RNR_EPI_STATS)) return 0;
     // ---- group the K-steps: maximal runs of consecutive K-steps on the same (view, channel chunk) ----
     // (the engine emits the K-steps chunk-major, so all taps of a chunk are adjacent in K and in Wmat)
     struct Key { int view, c0; };
-    std::vector<Key> keys;
-    std::vector<std::vector<int>> members;
-    for (int j = 0; j < prob->n_ksteps; j++) {
-        const rnr_kstep_t& ks = prob->ksteps[j];
-        if (keys.empty() || keys.back().view != ks.view || keys.back().c0 != ks.c0) { keys.push_back({ks.view, ks.c0}); members.emplace_back(); }
-        members.back().push_back(j);
-    }
-    if ((int)keys.size() > kMaxGroups || prob->n_ksteps > kMaxTaps) return 0;
-    int ex = 0, ey = 0;
-    std::vector<HaloGroup> groups(keys.size());
-    bool uniform = true;
-    for (size_t g = 0; g < keys.size(); g++) {
-        int dx0 = 1 << 20, dx1 = -(1 << 20), dy0 = 1 << 20, dy1 = -(1 << 20);
-        for (int j : members[g]) {
-            dx0 = std::min(dx0, (int)prob->ksteps[j].dx); dx1 = std::max(dx1, (int)prob->ksteps[j].dx);
-            dy0 = std::min(dy0, (int)prob->ksteps[j].dy); dy1 = std::max(dy1, (int)prob->ksteps[j].dy);
-        }
-        ex = std::max(ex, dx1 - dx0); ey = std::max(ey, dy1 - dy0);
-        groups[g].view = (int16_t)keys[g].view; groups[g].c0 = (int16_t)keys[g].c0;
-        groups[g].ox = (int16_t)dx0; groups[g].oy = (int16_t)dy0;
-        uniform &= (members[g].size() == members[0].size());
-    }
-    if (ex > 4 || ey > 4) return 0;
-    if (!uniform || members[0].size() > 16) return 0;       // every (view, chunk) group must carry the same <= 16 taps
-    const int pitch = TW + ex, rows = TH + ey;
+    std::vector<HaloGroup> groups;
     std::vector<HaloTap> taps;
-    for (size_t g = 0; g < keys.size(); g++) {
-        groups[g].first_tap = (int16_t)taps.size();
-        groups[g].n_taps = (int16_t)members[g].size();
-        for (int j : members[g]) {
-            HaloTap t;
-            t.a_off = ((prob->ksteps[j].dy - groups[g].oy) * pitch + (prob->ksteps[j].dx - groups[g].ox)) * 128;
-            t.wcol = j * 64;
-            taps.push_back(t);
+    int ex = 0, ey = 0, n_groups = 0, gtaps_all = 0;
+    std::vector<std::vector<Key>> keys_s(nsub);
+    std::vector<std::vector<std::vector<int>>> members_s(nsub);
+    for (int sb = 0; sb < nsub; sb++) {
+        const rnr_conv_problem_t* pr = probs + sb;
+        std::vector<Key>& keys = keys_s[sb];
+        std::vector<std::vector<int>>& members = members_s[sb];
+        for (int j = 0; j < pr->n_ksteps; j++) {
+            const rnr_kstep_t& ks = pr->ksteps[j];
+            if (keys.empty() || keys.back().view != ks.view || keys.back().c0 != ks.c0) { keys.push_back({ks.view, ks.c0}); members.emplace_back(); }
+            members.back().push_back(j);
+        }
+        if (sb == 0) { n_groups = (int)keys.size(); gtaps_all = (int)members[0].size(); }
+        if ((int)keys.size() != n_groups) return 0;
+        for (size_t g = 0; g < keys.size(); g++) {
+            if ((int)members[g].size() != gtaps_all) return 0;      // every (view, chunk) group must carry the same taps
+            int dx0 = 1 << 20, dx1 = -(1 << 20), dy0 = 1 << 20, dy1 = -(1 << 20);
+            for (int j : members[g]) {
+                dx0 = std::min(dx0, (int)pr->ksteps[j].dx); dx1 = std::max(dx1, (int)pr->ksteps[j].dx);
+                dy0 = std::min(dy0, (int)pr->ksteps[j].dy); dy1 = std::max(dy1, (int)pr->ksteps[j].dy);
+            }
+            ex = std::max(ex, dx1 - dx0); ey = std::max(ey, dy1 - dy0);
         }
     }
-    // the halo kernel addresses tap k of every group through one offset table: all groups must share the tap pattern
-    for (size_t g = 0; g < keys.size(); g++)
-        for (size_t k = 0; k < members[g].size(); k++)
-            if (taps[groups[g].first_tap + k].a_off != taps[k].a_off) return 0;
-    for (size_t k = 0; k < 16; k++) pl->halo_a_off[k] = k < members[0].size() ? taps[k].a_off : 0;
-    pl->halo_gtaps = (int)members[0].size();
+    if (n_groups * nsub > kMaxGroups || prob->n_ksteps > kMaxTaps) return 0;
+    if (ex > 4 || ey > 4) return 0;
+    if (gtaps_all > 16) return 0;
+    const int pitch = TW + ex, rows = TH + ey;
+    memset(pl->halo_a_off, 0, sizeof(pl->halo_a_off));
+    for (int sb = 0; sb < nsub; sb++) {
+        const rnr_conv_problem_t* pr = probs + sb;
+        const std::vector<Key>& keys = keys_s[sb];
+        const std::vector<std::vector<int>>& members = members_s[sb];
+        const size_t tap0 = taps.size();
+        for (size_t g = 0; g < keys.size(); g++) {
+            int dx0 = 1 << 20, dy0 = 1 << 20;
+            for (int j : members[g]) { dx0 = std::min(dx0, (int)pr->ksteps[j].dx); dy0 = std::min(dy0, (int)pr->ksteps[j].dy); }
+            HaloGroup G;
+            G.view = (int16_t)keys[g].view; G.c0 = (int16_t)keys[g].c0; G.ox = (int16_t)dx0; G.oy = (int16_t)dy0;
+            G.first_tap = (int16_t)taps.size(); G.n_taps = (int16_t)members[g].size();
+            for (int j : members[g]) {
+                HaloTap t;
+                t.a_off = ((pr->ksteps[j].dy - dy0) * pitch + (pr->ksteps[j].dx - dx0)) * 128;
+                t.wcol = j * 64;
+                taps.push_back(t);
+            }
+            groups.push_back(G);
+        }
+        // the halo kernel addresses tap k of every group through one offset table: all groups must share the tap pattern
+        for (size_t g = 0; g < keys.size(); g++)
+            for (int k = 0; k < gtaps_all; k++)
+                if (taps[tap0 + g * gtaps_all + k].a_off != taps[tap0 + k].a_off) return 0;
+        for (int k = 0; k < gtaps_all; k++) pl->halo_a_off[sb][k] = taps[tap0 + k].a_off;
+        pl->halo_out_py[sb] = pr->out_py; pl->halo_out_px[sb] = pr->out_px;
+        // sub-problems must agree on everything the kernel takes from sub-problem 0
+        if (sb > 0) {
+            const rnr_conv_problem_t* p0 = probs;
+            if (pr->n_views != p0->n_views || pr->bk != p0->bk || pr->n_ksteps != p0->n_ksteps || pr->n_rows_w != p0->n_rows_w ||
+                pr->cout != p0->cout || pr->mN != p0->mN || pr->mY != p0->mY || pr->mX != p0->mX || pr->out != p0->out ||
+                pr->out_dtype != p0->out_dtype || pr->out_sn != p0->out_sn || pr->out_sy != p0->out_sy || pr->out_sx != p0->out_sx ||
+                pr->out_my != p0->out_my || pr->out_mx != p0->out_mx || pr->epi != p0->epi || pr->bias != p0->bias ||
+                pr->ab_dtype != p0->ab_dtype || pr->ldstats != p0->ldstats)
+                return 0;
+            for (int v = 0; v < p0->n_views; v++)
+                if (memcmp(&pr->views[v], &p0->views[v], sizeof(rnr_view_t)) != 0) return 0;
+            const size_t sub_bytes = (size_t)p0->n_rows_w * p0->n_ksteps * p0->bk * 2;
+            if ((const char*)pr->wmat != (const char*)p0->wmat + sb * sub_bytes) return 0;
+        }
+    }
+    pl->halo_nsub = nsub;
+    pl->halo_gtaps = gtaps_all;
+    const bool uniform = true;
+    std::vector<std::vector<int>> members(1, std::vector<int>(gtaps_all));
     // ---- tiling ----
     ConvParams& p = pl->p;
     p.th = TH; p.tw = TW;
@@ -471,7 +516,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
     int tiles_n = rnr_cdiv(prob->n_rows_w, bn);
     // a wider N tile reads fewer shared-memory operand bytes per FLOP (the SS-mode MMA is shared-memory-bandwidth bound below N = 256),
     // so N is only narrowed when the launch would otherwise leave most SMs idle
-    while (bn > 64 && bn % 32 == 0 && p.tiles_m * tiles_n < (bn > 128 ? 100 : 50)) { bn /= 2; tiles_n = rnr_cdiv(prob->n_rows_w, bn); }
+    while (bn > 64 && bn % 32 == 0 && p.tiles_m * tiles_n * nsub < (bn > 128 ? 100 : 50)) { bn /= 2; tiles_n = rnr_cdiv(prob->n_rows_w, bn); }
     pl->bn = bn;
     pl->tiles_n = tiles_n;
     const int a_stage = ((rows * pitch * 128) + 1023) / 1024 * 1024;
@@ -508,7 +553,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
     pl->halo_a_bytes = rows * pitch * 128;
     pl->smem_bytes = kAStages * a_stage + b_stages * b_stage + aux + 1024;
     {
-        const int groups_total = rnr_cdiv(p.tiles_m, cs) * tiles_n;
+        const int groups_total = rnr_cdiv(p.tiles_m, cs) * tiles_n * nsub;
         const int max_clusters = 148 / cs;
         pl->grid = (groups_total < max_clusters ? groups_total : max_clusters) * cs;
     }
@@ -521,7 +566,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
     }
     {
         // Wmat [n_rows, ldw] viewed as (64 channels, n rows, K blocks): one box = T consecutive K blocks = T [bn x 64] tiles
-        cuuint64_t gdim[3] = {64, (cuuint64_t)prob->n_rows_w, (cuuint64_t)(p.ldw / 64)};
+        cuuint64_t gdim[3] = {64, (cuuint64_t)prob->n_rows_w * nsub, (cuuint64_t)(p.ldw / 64)};
         cuuint64_t gstr[2] = {(cuuint64_t)p.ldw * 2, 128};
         cuuint32_t box[3] = {64u, (cuuint32_t)bn, (cuuint32_t)T};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -532,7 +577,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
         RNR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(Wmat 3-D) failed with CUresult %d", (int)r);
     }
     if (cs > 1) {
-        cuuint64_t gdim[2] = {(cuuint64_t)p.ldw, (cuuint64_t)prob->n_rows_w};
+        cuuint64_t gdim[2] = {(cuuint64_t)p.ldw, (cuuint64_t)prob->n_rows_w * nsub};
         cuuint64_t gstr[1] = {(cuuint64_t)p.ldw * 2};
         cuuint32_t box[2] = {64u, (cuuint32_t)(bn / cs)};
         cuuint32_t estr[2] = {1, 1};
@@ -548,7 +593,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
     RNR_CHECK(cudaMemcpy(pl->d_groups, groups.data(), sizeof(HaloGroup) * groups.size(), cudaMemcpyHostToDevice));
     RNR_CHECK(cudaMalloc(&pl->d_taps, sizeof(HaloTap) * taps.size()));
     RNR_CHECK(cudaMemcpy(pl->d_taps, taps.data(), sizeof(HaloTap) * taps.size(), cudaMemcpyHostToDevice));
-    pl->n_groups = (int)groups.size();
+    pl->n_groups = n_groups;
     pl->n_taps = (int)taps.size();
     static bool attr_set = false;
     if (!attr_set) {
@@ -572,6 +617,10 @@ int rnr_conv_halo_run(const rnr_conv_plan* pl, cudaStream_t stream) {
     maps.b2 = pl->tmap_b2;
     HaloCfg hc;
     memcpy(hc.a_off, pl->halo_a_off, sizeof(hc.a_off));
+    memcpy(hc.out_py, pl->halo_out_py, sizeof(hc.out_py));
+    memcpy(hc.out_px, pl->halo_out_px, sizeof(hc.out_px));
+    hc.nsub = pl->halo_nsub;
+    hc.sub_rows = pl->p.n_rows_w;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(pl->grid);

@@ -46,7 +46,9 @@ struct rnr_conv_plan {
     int halo_a_stage, halo_b_stage, halo_pitch, halo_a_bytes, halo_T, halo_cs;
     CUtensorMap tmap_b2;
     int halo_gtaps;
-    int halo_a_off[16];
+    int halo_a_off[4][16];
+    int halo_out_py[4], halo_out_px[4];
+    int halo_nsub;
     HaloGroup* d_groups;
     HaloTap* d_taps;
     int n_groups, n_taps;
@@ -86,7 +88,7 @@ struct rnr_wgrad_plan {
 int rnr_encode_view_map(CUtensorMap* map, const rnr_view_t& v, int dtype, int box_c, int box_x, int box_y);
 int rnr_conv_tc_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* prob);
 int rnr_conv_tc_run(const rnr_conv_plan* plan, cudaStream_t stream);
-int rnr_conv_halo_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* prob);
+int rnr_conv_halo_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* probs, int nsub);
 int rnr_conv_halo_run(const rnr_conv_plan* plan, cudaStream_t stream);
 int rnr_wgrad_tc_prepare(rnr_wgrad_plan* plan, const rnr_wgrad_problem_t* prob);
 int rnr_wgrad_tc_run(const rnr_wgrad_plan* plan, cudaStream_t stream);

@@ -234,7 +234,22 @@ void copy_view(ViewD& d, const rnr_view_t& s) {
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+static int conv_plan_create(const rnr_conv_problem_t* prob, int nsub, int impl, rnr_conv_plan_t** out);
+
 extern "C" int rnr_conv_plan_create(const rnr_conv_problem_t* prob, int impl, rnr_conv_plan_t** out) {
+    return conv_plan_create(prob, 1, impl, out);
+}
+
+/* `n` sub-problems that differ only in tap offsets, weight matrix (stacked row-wise in one buffer) and output parity, run as ONE
+ * launch of the tcgen05 halo kernel.  Returns cudaErrorNotSupported (and no plan) when the problems cannot be fused -- the caller
+ * then creates one plan per problem. */
+extern "C" int rnr_conv_plan_create_multi(const rnr_conv_problem_t* probs, int n, int impl, rnr_conv_plan_t** out) {
+    RNR_REQUIRE(probs && out && n >= 1 && n <= 4, "rnr_conv_plan_create_multi: 1..4 sub-problems");
+    if (n > 1 && impl != 1) { rnr_set_error("rnr_conv_plan_create_multi: only the tcgen05 implementation fuses sub-problems"); return (int)cudaErrorNotSupported; }
+    return conv_plan_create(probs, n, impl, out);
+}
+
+static int conv_plan_create(const rnr_conv_problem_t* prob, int nsub, int impl, rnr_conv_plan_t** out) {
     RNR_REQUIRE(prob && out, "rnr_conv_plan_create: null argument");
     RNR_REQUIRE(prob->th * prob->tw == 128, "rnr_conv_plan_create: tile must hold 128 pixels (th=%d tw=%d)", prob->th, prob->tw);
     RNR_REQUIRE(prob->bk == 16 || prob->bk == 32 || prob->bk == 64, "rnr_conv_plan_create: bk must be 16/32/64");
@@ -259,9 +274,13 @@ extern "C" int rnr_conv_plan_create(const rnr_conv_problem_t* prob, int impl, rn
     if (e != cudaSuccess) { rnr_set_error("rnr_conv_plan_create: %s", cudaGetErrorString(e)); delete pl; return (int)e; }
     p.ksteps = pl->d_ksteps;
     if (impl == 1) {
-        int rc = rnr_conv_halo_prepare(pl, prob);            // shared-memory halo reuse when the problem fits ...
+        int rc = rnr_conv_halo_prepare(pl, prob, nsub);      // shared-memory halo reuse when the problem fits ...
+        if (rc == 0 && !pl->halo && nsub > 1) {
+            rnr_set_error("rnr_conv_plan_create_multi: sub-problems cannot be fused by the halo kernel");
+            rc = (int)cudaErrorNotSupported;
+        }
         if (rc == 0 && !pl->halo) rc = rnr_conv_tc_prepare(pl, prob);   // ... else one A tile per tap
-        if (rc != 0) { cudaFree(pl->d_ksteps); delete pl; return rc; }
+        if (rc != 0) { cudaFree(pl->d_ksteps); if (pl->d_groups) cudaFree(pl->d_groups); if (pl->d_taps) cudaFree(pl->d_taps); delete pl; return rc; }
     }
     *out = pl;
     return 0;

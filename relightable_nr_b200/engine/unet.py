@@ -287,7 +287,7 @@ class UNetEngine:
 
     # ---- problem builders ---------------------------------------------------------------------
     def _conv_problem(self, views, ksteps, ab_dtype, bk, wmat, n_rows_w, cout, mN, mY, mX, out_t, out_dtype,
-                      out_strides, out_mp, epi, bias, stats, ldstats, impl):
+                      out_strides, out_mp, epi, bias, stats, ldstats, impl, defer=False):
         prob = ConvProblem()
         for i, v in enumerate(views):
             prob.views[i] = v
@@ -299,7 +299,7 @@ class UNetEngine:
             arr[i].view, arr[i].c0, arr[i].dx, arr[i].dy = v, c0, dx, dy
         prob.n_ksteps = len(ksteps)
         prob.ksteps = C.cast(arr, C.POINTER(KStep))
-        prob.wmat = wmat.data_ptr()
+        prob.wmat = wmat if isinstance(wmat, int) else wmat.data_ptr()
         prob.n_rows_w = n_rows_w
         prob.cout = cout
         prob.mN, prob.mY, prob.mX = mN, mY, mX
@@ -312,6 +312,28 @@ class UNetEngine:
         prob.bias = bias.data_ptr() if bias is not None else None
         prob.stats = stats if isinstance(stats, int) or stats is None else stats.data_ptr()
         prob.ldstats = ldstats
+        prob._keep = arr
+        if defer:
+            return prob
+        h = C.c_void_p()
+        _lib.check(self.L.rnr_conv_plan_create(C.byref(prob), impl, C.byref(h)), 'rnr_conv_plan_create')
+        return _Plan(h, 'conv')
+
+    def _fused_plan(self, probs, impl):
+        """One plan (one launch) for sub-problems that differ only in taps / weights / output parity; None when the library
+        cannot fuse them (SIMT validation path, per-tap kernel)."""
+        if impl != 1 or len(probs) < 2:
+            return None
+        arr = (ConvProblem * len(probs))()
+        for i, pr in enumerate(probs):
+            C.memmove(C.byref(arr[i]), C.byref(pr), C.sizeof(ConvProblem))
+        h = C.c_void_p()
+        rc = self.L.rnr_conv_plan_create_multi(arr, len(probs), impl, C.byref(h))
+        if rc != 0:
+            return None
+        return _Plan(h, 'conv')
+
+    def _single_plan(self, prob, impl):
         h = C.c_void_p()
         _lib.check(self.L.rnr_conv_plan_create(C.byref(prob), impl, C.byref(h)), 'rnr_conv_plan_create')
         return _Plan(h, 'conv')
@@ -443,7 +465,10 @@ class UNetEngine:
                 st.stats = self._alloc((4 * tiles, 2, cout), torch.float32, zero=True)
                 st.n_stat_tiles = 4 * tiles
             sel = {0: [(1, 0), (3, -1)], 1: [(0, 1), (2, 0)]}      # parity -> [(k index, input offset)]
-            rows_pp = 0
+            # the four parity sub-problems share one weight buffer (sub s at rows [s*n_rows, (s+1)*n_rows)) so that they can
+            # run as ONE launch (rnr_conv_plan_create_multi): 4x the tiles per launch instead of four half-empty grids
+            wm_all = self._alloc((4 * n_rows, 4 * cpad_tot), adt_t, zero=True)
+            probs = []
             for ph in range(2):
                 for pw in range(2):
                     taps, tapoffs = [], []
@@ -451,17 +476,27 @@ class UNetEngine:
                         for (kw, dx) in sel[pw]:
                             taps.append(([si for si in range(len(srcs))], dx, dy))
                             tapoffs.append(kh * 4 + kw)
-                    wm = self._alloc((n_rows, 4 * cpad_tot), adt_t, zero=True)
+                    sidx = ph * 2 + pw
+                    wm = wm_all[sidx * n_rows:(sidx + 1) * n_rows]
                     # weight [Cin, Cout, 4, 4]: rows = co (stride 16), cols = ci (stride Cout*16)
                     st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 4,
                                                16, cout * 16, self._tapoff(tapoffs), chunked=chunked))
-                    stats_ptr = None
-                    if st.stats is not None:
-                        stats_ptr = st.stats.data_ptr() + (ph * 2 + pw) * rows_pp * 2 * cout * 4
-                    st.fwd_plans.append(self._conv_problem(
+                    probs.append(self._conv_problem(
                         views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Hi, Wi, st.raw, F32,
-                        (Ho * Wo * ld_out, Wo * ld_out, ld_out), (2, 2, ph, pw), epi, bias_t, stats_ptr, cout, self.impl))
-                    if ph == 0 and pw == 0:
+                        (Ho * Wo * ld_out, Wo * ld_out, ld_out), (2, 2, ph, pw), epi, bias_t, st.stats, cout, self.impl, defer=True))
+            self.keep.append(probs)
+            fused = self._fused_plan(probs, self.impl)
+            if fused is not None:
+                st.fwd_plans.append(fused)
+                if st.stats is not None:
+                    st.n_stat_tiles = self.L.rnr_conv_plan_stat_rows(fused.h)
+            else:
+                rows_pp = 0
+                for sidx, pr in enumerate(probs):
+                    if st.stats is not None:
+                        pr.stats = st.stats.data_ptr() + sidx * rows_pp * 2 * cout * 4
+                    st.fwd_plans.append(self._single_plan(pr, self.impl))
+                    if sidx == 0:
                         # the four parity sub-problems have identical shapes: each writes `rows_pp` consecutive partial-sum rows
                         rows_pp = self.L.rnr_conv_plan_stat_rows(st.fwd_plans[-1].h)
                         if st.stats is not None:
@@ -580,18 +615,27 @@ class UNetEngine:
             Hp, Wp = Hi + 2, Wi + 2
             st.gx = self._alloc((N, Hp, Wp, nci_pad), gdt_t, zero=True)
             st.gx_fold, st.gx_ld = True, nci_pad
+            wm_all = self._alloc((4 * nci_pad, 4 * gC), gdt_t, zero=True)
+            probs = []
             for ph in range(2):
                 for pw in range(2):
                     gch = 1 if gbk == 64 else 0
                     tapl = [(1 - b, 1 - a, (2 * a + ph) * 4 + (2 * b + pw)) for a in range(2) for b in range(2)]
                     ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gC, gbk, gch)
                     tapoffs = [o for (_, _, o) in tapl]
-                    wm = self._alloc((nci_pad, 4 * gC), gdt_t, zero=True)
+                    sidx = ph * 2 + pw
+                    wm = wm_all[sidx * nci_pad:(sidx + 1) * nci_pad]
                     st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 16, wm, self.grad_dt, nci, nci_pad, cout, gC, 4, 16,
                                                  cin_tot * 16, self._tapoff(tapoffs), chunked=gch))
-                    st.dgrad_plans.append(self._conv_problem(
+                    probs.append(self._conv_problem(
                         [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp // 2, Wp // 2, st.gx, self.grad_dt,
-                        (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (2, 2, ph, pw), 0, None, None, 0, self.impl))
+                        (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (2, 2, ph, pw), 0, None, None, 0, self.impl, defer=True))
+            self.keep.append(probs)
+            fused = self._fused_plan(probs, self.impl)
+            if fused is not None:
+                st.dgrad_plans.append(fused)
+            else:
+                st.dgrad_plans.extend(self._single_plan(pr, self.impl) for pr in probs)
         else:
             # gX[ih,iw,ci] = sum_{kh,kw,co} Gp[2ih+kh, 2iw+kw, co] W[ci,co,kh,kw]
             st.gx = self._alloc((N, Hi, Wi, nci_pad), gdt_t, zero=True)
