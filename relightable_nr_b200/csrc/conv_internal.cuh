@@ -82,6 +82,7 @@ struct rnr_wgrad_plan {
     int smem_bytes, grid, stages;
     int n_work;          // tc work items
     int vec;             // 1: dW destination is ci-contiguous -> 128-bit vector reductions
+    int swap;            // 1: M = input channels, N = output channels
     int* d_work_tab;     // [n_work, 8]
 };
 

@@ -199,41 +199,27 @@ struct TailParams {
     double* sums;            // [0] sum diff, [1] sum alpha, [2] sum |out*a - gt*a| over the crop
 };
 
-__device__ __forceinline__ float block_sum128(float v, float* s_tmp) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) s_tmp[w] = v;
-    __syncthreads();
-    float r = 0.f;
-    if (w == 0) {
-        r = lane < (blockDim.x >> 5) ? s_tmp[lane] : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    }
-    return r;
-}
-
-constexpr int kTailPx = 128;            // pixels (= threads) per block
-// row pitches in shared memory: smallest odd numbers > 3R resp. 2R (thread-per-row access without bank conflicts)
+constexpr int kTailPx = 32;             // pixels per group
+constexpr int kTailThreads = 256;       // work item = (pixel, ray): 32 x 26 items per group, ~3 per thread
+// row pitches in shared memory: smallest odd numbers > 3R resp. 2R
 __host__ __device__ __forceinline__ int raw_pitch(int R) { return (3 * R + 1) | 1; }
 __host__ __device__ __forceinline__ int uv_pitch(int R) { return (2 * R + 1) | 1; }
 
-// Coalesced staging of the block's rows of the last convolution's output ([P, ldraw], 3R used) and of rays_uv ([P, 2R]) into
-// shared memory: the per-pixel threads then walk their own row.  (Reading the rows straight from global memory, one thread
-// per 312-byte row, moved 6x the useful bytes through L1: profiles/r01_tail_v0.)
+// Coalesced staging of a group's rows of the last convolution's output ([P, ldraw], 3R used) and of rays_uv ([P, 2R]) into
+// shared memory.  (Reading the rows straight from global memory, one thread per 312-byte row, moved 6x the useful bytes
+// through L1; one thread per PIXEL left 12 warps per SM walking 26 dependent rays each: the kernels ran at 30 % issue
+// utilisation.  Items are now (pixel, ray) pairs, 2048 threads per SM.)
 __device__ __forceinline__ void stage_rows(const TailParams& q, int64_t p0, int np, float* s_raw, float* s_uv) {
     const int kRawPitch = raw_pitch(q.R), kUvPitch = uv_pitch(q.R);
     const int nch = 3 * q.R, nv = (nch + 3) >> 2;
-    for (int i = threadIdx.x; i < np * nv; i += kTailPx) {
+    for (int i = threadIdx.x; i < np * nv; i += kTailThreads) {
         const int px = i / nv, k = (i - px * nv) * 4;
         const float4 v = *(const float4*)(q.raw + (p0 + px) * q.ldraw + k);
         float* d = s_raw + px * kRawPitch + k;
         d[0] = v.x; if (k + 1 < kRawPitch) d[1] = v.y; if (k + 2 < kRawPitch) d[2] = v.z; if (k + 3 < kRawPitch) d[3] = v.w;
     }
     const int nuv = 2 * q.R;
-    for (int i = threadIdx.x; i < np * nuv; i += kTailPx) {
+    for (int i = threadIdx.x; i < np * nuv; i += kTailThreads) {
         const int px = i / nuv, k = i - px * nuv;
         s_uv[px * kUvPitch + k] = q.rays_uv[p0 * nuv + i];
     }
@@ -253,78 +239,115 @@ __device__ __forceinline__ void env_color(const TailParams& q, const Bilin& b, f
     col[2] = t00.z * b.w00 + t10.z * b.w10 + t01.z * b.w01 + t11.z * b.w11;
 }
 
-__global__ void __launch_bounds__(kTailPx) tail_fwd_kernel(const TailParams q) {
+__device__ __forceinline__ float block_sum256(float v, float* s_tmp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_tmp[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+        r = lane < (kTailThreads >> 5) ? s_tmp[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams q) {
     extern __shared__ float s_dyn[];
     const int kRawPitch = raw_pitch(q.R), kUvPitch = uv_pitch(q.R);
-    float* s_raw = s_dyn;                              // [128][kRawPitch]
-    float* s_uv = s_raw + kTailPx * kRawPitch;         // [128][kUvPitch]
+    float* s_raw = s_dyn;                              // [32][kRawPitch]: tanh outputs, then rays_lt * envmap colour
+    float* s_uv = s_raw + kTailPx * kRawPitch;         // [32][kUvPitch]
+    float* s_ch = s_uv + kTailPx * kUvPitch;           // [32][kRawPitch]: normalised rays_lt (chromaticity)
+    float* s_m = s_ch + kTailPx * kRawPitch;           // [32][4]: normalised mean chromaticity, alpha * image weight
     __shared__ float s_tmp[8];
     const int64_t HW = (int64_t)q.H * q.W;
-    const int64_t p0 = (int64_t)blockIdx.x * kTailPx;
-    const int64_t pix = p0 + threadIdx.x;
-    const int np = (int)((HW * q.N - p0) < kTailPx ? (HW * q.N - p0) : kTailPx);
-    stage_rows(q, p0, np, s_raw, s_uv);
-    __syncthreads();
+    const int64_t P = HW * q.N;
+    const int ngroups = (int)((P + kTailPx - 1) / kTailPx);
+    const int tid = threadIdx.x;
     float dsum = 0.f, asum = 0.f, lsum = 0.f;
-    if (pix < HW * q.N) {
-        const int n = (int)(pix / HW);
-        const int64_t p = pix % HW;
-        const float a = q.alpha[pix];
-        float wi = 1.f;
-        float gt[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) gt[c] = q.img[((int64_t)n * 3 + c) * HW + p];
-        wi = fminf(sqrtf(gt[0] * gt[0] + gt[1] * gt[1] + gt[2] * gt[2]) * 20.f, 1.0f);
-        const float* t = s_raw + threadIdx.x * kRawPitch;
-        const float* uvrow = s_uv + threadIdx.x * kUvPitch;
-        float ss[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
-        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-        for (int r = 0; r < q.R; r++) {
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int64_t p0 = (int64_t)grp * kTailPx;
+        const int np = (int)((P - p0) < kTailPx ? (P - p0) : kTailPx);
+        __syncthreads();                               // previous group's readers are done with the shared buffers
+        stage_rows(q, p0, np, s_raw, s_uv);
+        __syncthreads();
+        // ---- (pixel, ray): envmap colour, rays_lt, chromaticity ----
+        for (int i = tid; i < np * q.R; i += kTailThreads) {
+            const int px = i / q.R, r = i - px * q.R;
             Bilin b;
-            env_taps(q, uvrow, r, b);
+            env_taps(q, s_uv + px * kUvPitch, r, b);
             float col[3], lt[3];
             env_color(q, b, col);
+            float* t = s_raw + px * kRawPitch + r * 3;
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                lt[c] = (t[r * 3 + c] * 0.5f + 0.5f) * 2.0f;
-                const float tt = lt[c] * col[c];
-                if (r < q.Rs) ss[c] += tt; else sd[c] += tt;
-            }
+            for (int c = 0; c < 3; c++) { lt[c] = (t[c] * 0.5f + 0.5f) * 2.0f; t[c] = lt[c] * col[c]; }
             float x = lt[0], y = lt[1], z = lt[2];
             normalize3(x, y, z);
-            m0 += x; m1 += y; m2 += z;
+            float* ch = s_ch + px * kRawPitch + r * 3;
+            ch[0] = x; ch[1] = y; ch[2] = z;
         }
-        m0 /= (float)q.R; m1 /= (float)q.R; m2 /= (float)q.R;
-        normalize3(m0, m1, m2);
-        for (int r = 0; r < q.R; r++) {
-            float x = (t[r * 3 + 0] * 0.5f + 0.5f) * 2.0f, y = (t[r * 3 + 1] * 0.5f + 0.5f) * 2.0f, z = (t[r * 3 + 2] * 0.5f + 0.5f) * 2.0f;
-            normalize3(x, y, z);
-            dsum += (1.f - (x * m0 + y * m1 + z * m2)) * a * wi;
-        }
-        asum = a;
-        const int w = (int)(p % q.W), h = (int)(p / q.W);
-        const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
-        float* ax = q.aux + pix * 12;
-        float axv[12];
+        __syncthreads();
+        // ---- per pixel: ray sums (same summation order as the module kernels), image, L1, aux ----
+        if (tid < np) {
+            const int px = tid;
+            const int64_t pix = p0 + px;
+            const int n = (int)(pix / HW);
+            const int64_t p = pix % HW;
+            const float a = q.alpha[pix];
+            float gt[3];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float ls = ss[c] / (float)q.Rs;
-            const float os = q.albedo[pix * 8 + 3 + c] * ls;
-            float ld = 0.f, od = 0.f;
-            if (q.Rd > 0) { ld = sd[c] / (float)q.Rd; od = q.albedo[pix * 8 + c] * ld; }
-            const float out = os + od;
-            q.final_img[((int64_t)n * 3 + c) * HW + p] = out;
-            axv[c] = ls; axv[3 + c] = ld;
-            if (inside) lsum += fabsf(out * a - gt[c] * a);
+            for (int c = 0; c < 3; c++) gt[c] = q.img[((int64_t)n * 3 + c) * HW + p];
+            const float wi = fminf(sqrtf(gt[0] * gt[0] + gt[1] * gt[1] + gt[2] * gt[2]) * 20.f, 1.0f);
+            const float* tt = s_raw + px * kRawPitch;
+            const float* ch = s_ch + px * kRawPitch;
+            float ss[3] = {0, 0, 0}, sd[3] = {0, 0, 0};
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+            for (int r = 0; r < q.R; r++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) { if (r < q.Rs) ss[c] += tt[r * 3 + c]; else sd[c] += tt[r * 3 + c]; }
+                m0 += ch[r * 3 + 0]; m1 += ch[r * 3 + 1]; m2 += ch[r * 3 + 2];
+            }
+            m0 /= (float)q.R; m1 /= (float)q.R; m2 /= (float)q.R;
+            normalize3(m0, m1, m2);
+            s_m[px * 4 + 0] = m0; s_m[px * 4 + 1] = m1; s_m[px * 4 + 2] = m2; s_m[px * 4 + 3] = a * wi;
+            asum += a;
+            const int w = (int)(p % q.W), h = (int)(p / q.W);
+            const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
+            const float4 al0 = *(const float4*)(q.albedo + pix * 8), al1 = *(const float4*)(q.albedo + pix * 8 + 4);
+            const float adv[3] = {al0.x, al0.y, al0.z}, asv[3] = {al0.w, al1.x, al1.y};
+            float axv[12];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float ls = ss[c] / (float)q.Rs;
+                const float os = asv[c] * ls;
+                float ld = 0.f, od = 0.f;
+                if (q.Rd > 0) { ld = sd[c] / (float)q.Rd; od = adv[c] * ld; }
+                const float out = os + od;
+                q.final_img[((int64_t)n * 3 + c) * HW + p] = out;
+                axv[c] = ls; axv[3 + c] = ld;
+                if (inside) lsum += fabsf(out * a - gt[c] * a);
+            }
+            axv[6] = m0; axv[7] = m1; axv[8] = m2; axv[9] = wi; axv[10] = 0.f; axv[11] = 0.f;
+            float* ax = q.aux + pix * 12;
+            *(float4*)(ax + 0) = make_float4(axv[0], axv[1], axv[2], axv[3]);
+            *(float4*)(ax + 4) = make_float4(axv[4], axv[5], axv[6], axv[7]);
+            *(float4*)(ax + 8) = make_float4(axv[8], axv[9], axv[10], axv[11]);
         }
-        axv[6] = m0; axv[7] = m1; axv[8] = m2; axv[9] = wi; axv[10] = 0.f; axv[11] = 0.f;
-        *(float4*)(ax + 0) = make_float4(axv[0], axv[1], axv[2], axv[3]);
-        *(float4*)(ax + 4) = make_float4(axv[4], axv[5], axv[6], axv[7]);
-        *(float4*)(ax + 8) = make_float4(axv[8], axv[9], axv[10], axv[11]);
+        __syncthreads();
+        // ---- (pixel, ray): chromaticity deviation from the pixel's mean ----
+        for (int i = tid; i < np * q.R; i += kTailThreads) {
+            const int px = i / q.R, r = i - px * q.R;
+            const float* ch = s_ch + px * kRawPitch + r * 3;
+            const float* m = s_m + px * 4;
+            dsum += (1.f - (ch[0] * m[0] + ch[1] * m[1] + ch[2] * m[2])) * m[3];
+        }
     }
-    const float bd = block_sum128(dsum, s_tmp);
-    const float ba = block_sum128(asum, s_tmp);
-    const float bl = block_sum128(lsum, s_tmp);
+    const float bd = block_sum256(dsum, s_tmp);
+    const float ba = block_sum256(asum, s_tmp);
+    const float bl = block_sum256(lsum, s_tmp);
     if (threadIdx.x == 0) {
         if (bd != 0.f) atomicAdd(&q.sums[0], (double)bd);
         if (ba != 0.f) atomicAdd(&q.sums[1], (double)ba);
@@ -335,77 +358,91 @@ __global__ void __launch_bounds__(kTailPx) tail_fwd_kernel(const TailParams q) {
 struct TailBwdParams {
     TailParams f;
     float w_l1, w_chrom;     // loss weights (upstream gradient folded in)
-    __nv_bfloat16* gz;       // [N,H+2,W+2,ldg] zero halo; channels [0, 3R) of the interior are written
+    __nv_bfloat16* gz;       // [N,H+2,W+2,ldg] zero halo; channels [0, roundup8(3R)) of the interior are written
     int ldg;
     float* dbias;            // [3R] += sum over pixels of dz
     float* g_alb;            // [N,6,H,W]: d loss / d neural_img channels 0..5
     float4* g_lp4;           // [Hl*Wl] (r,g,b,unused) += envmap gradient, or null
 };
 
-__global__ void __launch_bounds__(kTailPx) tail_bwd_kernel(const TailBwdParams qq) {
+__global__ void __launch_bounds__(kTailThreads) tail_bwd_kernel(const TailBwdParams qq) {
     extern __shared__ float s_dyn[];
-    const int kRawPitch = raw_pitch(qq.f.R), kUvPitch = uv_pitch(qq.f.R);
-    float* s_raw = s_dyn;                              // [128][kRawPitch]: tanh outputs, overwritten in place by dz
-    float* s_uv = s_raw + kTailPx * kRawPitch;         // [128][kUvPitch]
     const TailParams& q = qq.f;
+    const int kRawPitch = raw_pitch(q.R), kUvPitch = uv_pitch(q.R);
+    float* s_raw = s_dyn;                              // [32][kRawPitch]: tanh outputs, overwritten in place by dz
+    float* s_uv = s_raw + kTailPx * kRawPitch;         // [32][kUvPitch]
+    float* s_px = s_uv + kTailPx * kUvPitch;           // [32][12]: Gls 0..2, Gld 3..5, mean chromaticity 6..8, chrom scale 9
     const int64_t HW = (int64_t)q.H * q.W;
-    const int64_t p0 = (int64_t)blockIdx.x * kTailPx;
-    const int64_t pix = p0 + threadIdx.x;
-    const int np = (int)((HW * q.N - p0) < kTailPx ? (HW * q.N - p0) : kTailPx);
+    const int64_t P = HW * q.N;
+    const int ngroups = (int)((P + kTailPx - 1) / kTailPx);
+    const int tid = threadIdx.x;
     const int nch = 3 * q.R;
-    stage_rows(q, p0, np, s_raw, s_uv);
-    __syncthreads();
-    float* mine = s_raw + threadIdx.x * kRawPitch;
-    if (pix < HW * q.N) {
-        const int n = (int)(pix / HW);
-        const int64_t p = pix % HW;
-        const float a = q.alpha[pix];
-        const float4 ax0 = *(const float4*)(q.aux + pix * 12), ax1 = *(const float4*)(q.aux + pix * 12 + 4), ax2 = *(const float4*)(q.aux + pix * 12 + 8);
-        const float lsv[3] = {ax0.x, ax0.y, ax0.z}, ldv[3] = {ax0.w, ax1.x, ax1.y};
-        const float m0 = ax1.z, m1 = ax1.w, m2 = ax2.x, wi = ax2.y;
-        const float4 al0 = *(const float4*)(q.albedo + pix * 8), al1 = *(const float4*)(q.albedo + pix * 8 + 4);
-        const float adv[3] = {al0.x, al0.y, al0.z}, asv[3] = {al0.w, al1.x, al1.y};
-        const int w = (int)(p % q.W), h = (int)(p / q.W);
-        const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
-        const double cnt = (double)q.N * 3 * (q.H - 2 * q.crop) * (q.W - 2 * q.crop);
-        float Gls[3], Gld[3];
+    const double cnt = (double)q.N * 3 * (q.H - 2 * q.crop) * (q.W - 2 * q.crop);
+    const float gl1 = (float)((double)qq.w_l1 / cnt);
+    float bias_acc = 0.f;                              // thread c < 3R owns the bias gradient of channel c across its groups
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int64_t p0 = (int64_t)grp * kTailPx;
+        const int np = (int)((P - p0) < kTailPx ? (P - p0) : kTailPx);
+        __syncthreads();
+        stage_rows(q, p0, np, s_raw, s_uv);
+        // ---- per pixel: image-loss gradient, albedo gradients, per-ray scale factors ----
+        if (tid < np) {
+            const int px = tid;
+            const int64_t pix = p0 + px;
+            const int n = (int)(pix / HW);
+            const int64_t p = pix % HW;
+            const float a = q.alpha[pix];
+            const float4 ax0 = *(const float4*)(q.aux + pix * 12), ax1 = *(const float4*)(q.aux + pix * 12 + 4), ax2 = *(const float4*)(q.aux + pix * 12 + 8);
+            const float lsv[3] = {ax0.x, ax0.y, ax0.z}, ldv[3] = {ax0.w, ax1.x, ax1.y};
+            const float4 al0 = *(const float4*)(q.albedo + pix * 8), al1 = *(const float4*)(q.albedo + pix * 8 + 4);
+            const float adv[3] = {al0.x, al0.y, al0.z}, asv[3] = {al0.w, al1.x, al1.y};
+            const int w = (int)(p % q.W), h = (int)(p / q.W);
+            const bool inside = h >= q.crop && h < q.H - q.crop && w >= q.crop && w < q.W - q.crop;
+            float* sp = s_px + px * 12;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float as = asv[c], ad = adv[c];
-            const float ls = lsv[c], ld = ldv[c];
-            const float os = as * ls;
-            const float od = (q.Rd > 0) ? ad * ld : 0.f;
-            const float out = os + od;
-            float go = 0.f;
-            if (inside) {
-                const float d = out * a - q.img[((int64_t)n * 3 + c) * HW + p] * a;
-                go = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * a * (float)((double)qq.w_l1 / cnt);
+            for (int c = 0; c < 3; c++) {
+                const float as = asv[c], ad = adv[c];
+                const float ls = lsv[c], ld = ldv[c];
+                const float os = as * ls;
+                const float od = (q.Rd > 0) ? ad * ld : 0.f;
+                const float out = os + od;
+                float go = 0.f;
+                if (inside) {
+                    const float d = out * a - q.img[((int64_t)n * 3 + c) * HW + p] * a;
+                    go = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * a * gl1;
+                }
+                sp[c] = go * as / (float)q.Rs;
+                sp[3 + c] = (q.Rd > 0) ? go * ad / (float)q.Rd : 0.f;
+                qq.g_alb[((int64_t)n * 6 + 3 + c) * HW + p] = go * ls;
+                qq.g_alb[((int64_t)n * 6 + c) * HW + p] = (q.Rd > 0) ? go * ld : 0.f;
             }
-            Gls[c] = go * as / (float)q.Rs;
-            Gld[c] = (q.Rd > 0) ? go * ad / (float)q.Rd : 0.f;
-            qq.g_alb[((int64_t)n * 6 + 3 + c) * HW + p] = go * ls;
-            qq.g_alb[((int64_t)n * 6 + c) * HW + p] = (q.Rd > 0) ? go * ld : 0.f;
+            sp[6] = ax1.z; sp[7] = ax1.w; sp[8] = ax2.x;
+            sp[9] = qq.w_chrom * a * ax2.y / ((float)q.sums[1] * (float)q.R);
         }
-        const float s = qq.w_chrom * a * wi / ((float)q.sums[1] * (float)q.R);
-        const float* uvrow = s_uv + threadIdx.x * kUvPitch;
-        for (int r = 0; r < q.R; r++) {
+        __syncthreads();
+        // ---- (pixel, ray): d loss / d rays_lt -> d loss / d (pre-tanh output), envmap gradient ----
+        for (int i = tid; i < np * q.R; i += kTailThreads) {
+            const int px = i / q.R, r = i - px * q.R;
+            const float* sp = s_px + px * 12;
             Bilin b;
-            env_taps(q, uvrow, r, b);
+            env_taps(q, s_uv + px * kUvPitch, r, b);
             float col[3];
             env_color(q, b, col);
+            float* t = s_raw + px * kRawPitch + r * 3;
             float th[3], lt[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) { th[c] = mine[r * 3 + c]; lt[c] = (th[c] * 0.5f + 0.5f) * 2.0f; }
+            for (int c = 0; c < 3; c++) { th[c] = t[c]; lt[c] = (th[c] * 0.5f + 0.5f) * 2.0f; }
             const float nr = fmaxf(sqrtf(lt[0] * lt[0] + lt[1] * lt[1] + lt[2] * lt[2]), 1e-12f);
             const float x = lt[0] / nr, y = lt[1] / nr, z = lt[2] / nr;
+            const float m0 = sp[6], m1 = sp[7], m2 = sp[8], sc = sp[9];
             const float cm = x * m0 + y * m1 + z * m2;
-            const float gch[3] = {-s * (m0 - x * cm) / nr, -s * (m1 - y * cm) / nr, -s * (m2 - z * cm) / nr};
+            const float gch[3] = {-sc * (m0 - x * cm) / nr, -sc * (m1 - y * cm) / nr, -sc * (m2 - z * cm) / nr};
             float gc[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                const float G = (r < q.Rs) ? Gls[c] : Gld[c];
+                const float G = (r < q.Rs) ? sp[c] : sp[3 + c];
                 const float glt = G * col[c] + gch[c];
-                mine[r * 3 + c] = glt * (1.f - th[c] * th[c]);
+                t[c] = glt * (1.f - th[c] * th[c]);
                 gc[c] = G * lt[c];
             }
             if (qq.g_lp4 && (gc[0] != 0.f || gc[1] != 0.f || gc[2] != 0.f)) {
@@ -415,30 +452,24 @@ __global__ void __launch_bounds__(kTailPx) tail_bwd_kernel(const TailBwdParams q
                 if (b.w11 != 0.f) atomicAdd(qq.g_lp4 + b.i11, make_float4(gc[0] * b.w11, gc[1] * b.w11, gc[2] * b.w11, 0.f));
             }
         }
-        for (int c = nch; c < kRawPitch; c++) mine[c] = 0.f;
-    } else {
-        for (int c = 0; c < kRawPitch; c++) mine[c] = 0.f;
-    }
-    __syncthreads();
-    // ---- gz rows: bf16, 8 channels per 16-byte store, channels [0, roundup8(3R)) ----
-    const int vpp = (nch + 7) >> 3;
-    const int Hp = q.H + 2, Wp = q.W + 2;
-    for (int i = threadIdx.x; i < kTailPx * vpp; i += kTailPx) {
-        const int px = i / vpp, c = (i - px * vpp) * 8;
-        const int64_t pp = p0 + px;
-        if (pp >= HW * q.N) break;
-        const int w = (int)(pp % q.W), h = (int)((pp / q.W) % q.H), n = (int)(pp / HW);
-        __align__(16) __nv_bfloat16 o[8];
+        __syncthreads();
+        // ---- gz rows: bf16, 8 channels per 16-byte store, channels [0, roundup8(3R)) ----
+        const int vpp = (nch + 7) >> 3;
+        const int Hp = q.H + 2, Wp = q.W + 2;
+        for (int i = tid; i < np * vpp; i += kTailThreads) {
+            const int px = i / vpp, c = (i - px * vpp) * 8;
+            const int64_t pp = p0 + px;
+            const int w = (int)(pp % q.W), h = (int)((pp / q.W) % q.H), n = (int)(pp / HW);
+            __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = __float2bfloat16_rn(c + e < nch ? s_raw[px * kRawPitch + c + e] : 0.f);
-        *(uint4*)(qq.gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * qq.ldg + c) = *(const uint4*)o;
+            for (int e = 0; e < 8; e++) o[e] = __float2bfloat16_rn(c + e < nch ? s_raw[px * kRawPitch + c + e] : 0.f);
+            *(uint4*)(qq.gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * qq.ldg + c) = *(const uint4*)o;
+        }
+        // ---- bias gradient of the last convolution: column sums, kept in a register across the block's groups ----
+        if (tid < nch)
+            for (int px = 0; px < np; px++) bias_acc += s_raw[px * kRawPitch + tid];
     }
-    // ---- bias gradient of the last convolution: column sums of the block, one red per channel ----
-    if (threadIdx.x < nch) {
-        float acc = 0.f;
-        for (int px = 0; px < kTailPx; px++) acc += s_raw[px * kRawPitch + threadIdx.x];
-        if (acc != 0.f) atomicAdd(qq.dbias + threadIdx.x, acc);
-    }
+    if (tid < nch && bias_acc != 0.f) atomicAdd(qq.dbias + tid, bias_acc);
 }
 
 }  // namespace
@@ -494,10 +525,12 @@ extern "C" int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, c
     int rc = fill_tail(q, raw, ldraw, rays_uv, albedo, lp4, Hl, Wl, alpha, img, Rs, Rd, N, H, W, crop, final_img, aux, sums);
     if (rc) return rc;
     RNR_REQUIRE(final_img, "tail: null output");
-    const size_t smem = (size_t)kTailPx * (raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd)) * sizeof(float);
+    const size_t smem = (size_t)kTailPx * (2 * raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd) + 4) * sizeof(float);
     static bool attr = false;
     if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-    tail_fwd_kernel<<<rnr_cdiv((int64_t)N * H * W, kTailPx), kTailPx, smem, (cudaStream_t)stream>>>(q);
+    int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    tail_fwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(q);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -515,10 +548,12 @@ extern "C" int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, c
     RNR_REQUIRE(!g_lp4 || ((uintptr_t)g_lp4 & 15) == 0, "tail bwd: envmap gradient must be 16-byte aligned");
     qq.w_l1 = w_l1; qq.w_chrom = w_chrom; qq.gz = (__nv_bfloat16*)gz; qq.ldg = ldg; qq.dbias = dbias; qq.g_alb = g_alb;
     qq.g_lp4 = (float4*)g_lp4;
-    const size_t smem = (size_t)kTailPx * (raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd)) * sizeof(float);
+    const size_t smem = (size_t)kTailPx * (raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd) + 12) * sizeof(float);
     static bool attr = false;
     if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-    tail_bwd_kernel<<<rnr_cdiv((int64_t)N * H * W, kTailPx), kTailPx, smem, (cudaStream_t)stream>>>(qq);
+    int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    tail_bwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(qq);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -29,12 +29,12 @@ struct WMaps {
 };
 
 struct WorkItem {          // 8 ints
-    int tap, co0, ci_off, n_ci_box, ci_valid, patch_begin, patch_end, pad;
+    int tap, co0, ci_off, n_ci_box, ci_valid, patch_begin, patch_end, n_mma;   // n_mma: N of the MMA (columns of the accumulator)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const WorkItem* __restrict__ work, int n_work,
-                int th, int tw, int tiles_y, int tiles_x, int vec) {
+                int th, int tw, int tiles_y, int tiles_x, int vec, int swap) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* aux = smem + (size_t)kStages * kStageBytes;
@@ -77,11 +77,20 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                 if (elect_one_sync()) {
                     uint8_t* st = smem + (size_t)stage * kStageBytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + wi.n_ci_box) * kBoxBytes));
-                    tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st, wi.co0, x0, y0, n_);
-                    tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st + kBoxBytes, wi.co0 + 64, x0, y0, n_);
-                    for (int b = 0; b < wi.n_ci_box; b++)
-                        tma_load_4d(&maps.a[tap.view], &full_bar[stage], st + (size_t)(2 + b) * kBoxBytes,
-                                    tap.c0 + wi.ci_off + 64 * b, x0 + tap.dx, y0 + tap.dy, n_);
+                    if (!swap) {
+                        tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st, wi.co0, x0, y0, n_);
+                        tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st + kBoxBytes, wi.co0 + 64, x0, y0, n_);
+                        for (int b = 0; b < wi.n_ci_box; b++)
+                            tma_load_4d(&maps.a[tap.view], &full_bar[stage], st + (size_t)(2 + b) * kBoxBytes,
+                                        tap.c0 + wi.ci_off + 64 * b, x0 + tap.dx, y0 + tap.dy, n_);
+                    } else {
+                        // swapped roles: the 128 input channels of the block are the M operand (boxes 0-1), the output channels the
+                        // N operand (boxes 2..): layers with few output channels (64 / 78) then fill all 128 accumulator lanes
+                        tma_load_4d(&maps.a[tap.view], &full_bar[stage], st, tap.c0 + wi.ci_off, x0 + tap.dx, y0 + tap.dy, n_);
+                        tma_load_4d(&maps.a[tap.view], &full_bar[stage], st + kBoxBytes, tap.c0 + wi.ci_off + 64, x0 + tap.dx, y0 + tap.dy, n_);
+                        for (int b = 0; b < wi.n_ci_box; b++)
+                            tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st + (size_t)(2 + b) * kBoxBytes, 64 * b, x0, y0, n_);
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -97,7 +106,8 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
             const WorkItem wi = work[w];
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const uint32_t idesc = make_idesc(128, wi.n_ci_box * 64, p.g_dtype, p.a_dtype, 1, 1);
+            const uint32_t idesc = swap ? make_idesc(128, wi.n_mma, p.a_dtype, p.g_dtype, 1, 1)
+                                        : make_idesc(128, wi.n_mma, p.g_dtype, p.a_dtype, 1, 1);
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
@@ -137,6 +147,26 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
+            if (swap) {
+                // lane = input channel (ci_off + row), column = output channel: lanes are adjacent in the ci-contiguous scratch,
+                // so every column is one coalesced 128-byte reduction per warp
+                const int ci = wi.ci_off + row;
+                float* d2 = p.dw + (int64_t)(tap.ci0 + ci) * p.s_ci + tap.off;
+                for (int c0 = 0; c0 < wi.n_mma; c0 += 16) {
+                    uint32_t rv[16];
+                    tmem_ld16(taddr + (uint32_t)c0, rv);
+                    tmem_ld_wait();
+                    if (ci < tap.nci) {
+#pragma unroll
+                        for (int e = 0; e < 16; e++)
+                            if (c0 + e < p.cout) atomicAdd(d2 + (int64_t)(c0 + e) * p.s_co, __uint_as_float(rv[e]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                continue;
+            }
             const int ncols = wi.n_ci_box * 64;
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t rv[32];
@@ -201,14 +231,32 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
         if (rc) return rc;
     }
     // output tiles
-    struct OT { int tap, co0, ci_off, nbox, valid; };
+    // operand roles: M = output channels (blocks of 128), N = input channels (chunks of <= 128) -- or swapped when that wastes
+    // fewer accumulator lanes (cout <= 128 only: 64- and 78-channel layers at full resolution)
+    long long cost_n = 0, cost_s = 0;
+    for (int t = 0; t < prob->n_taps; t++) {
+        const int nci = prob->taps[t].nci;
+        cost_n += (long long)rnr_cdiv(prob->cout, 128) * 128 * rnr_cdiv(nci, 64) * 64;
+        cost_s += (long long)rnr_cdiv(nci, 128) * 128 * rnr_cdiv(prob->cout, 16) * 16;
+    }
+    int swap = (prob->cout <= 128 && cost_s < cost_n) ? 1 : 0;
+    { const char* e = getenv("RNR_WGRAD_SWAP"); if (e) swap = (atoi(e) != 0 && prob->cout <= 128) ? 1 : 0; }
+    pl->swap = swap;
+    struct OT { int tap, co0, ci_off, nbox, valid, n_mma; };
     std::vector<OT> tiles;
     for (int t = 0; t < prob->n_taps; t++) {
         const rnr_wtap_t& tp = prob->taps[t];
+        if (swap) {
+            for (int ci = 0; ci < tp.nci; ci += 128) {
+                OT o = {t, 0, ci, rnr_cdiv(prob->cout, 64), prob->cout, rnr_cdiv(prob->cout, 16) * 16};
+                tiles.push_back(o);
+            }
+            continue;
+        }
         for (int co0 = 0; co0 < prob->cout; co0 += 128)
             for (int ci = 0; ci < tp.nci; ci += 128) {
                 const int rem = tp.nci - ci;
-                OT o = {t, co0, ci, rem > 64 ? 2 : 1, rem > 128 ? 128 : rem};
+                OT o = {t, co0, ci, rem > 64 ? 2 : 1, rem > 128 ? 128 : rem, (rem > 64 ? 2 : 1) * 64};
                 tiles.push_back(o);
             }
     }
@@ -221,7 +269,7 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
         const int pb = s * per, pe = (pb + per < n_patches) ? pb + per : n_patches;
         if (pb >= pe) continue;
         for (const OT& o : tiles) {
-            WorkItem w = {o.tap, o.co0, o.ci_off, o.nbox, o.valid, pb, pe, 0};
+            WorkItem w = {o.tap, o.co0, o.ci_off, o.nbox, o.valid, pb, pe, o.n_mma};
             work.push_back(w);
         }
     }
@@ -247,7 +295,7 @@ int rnr_wgrad_tc_run(const rnr_wgrad_plan* pl, cudaStream_t stream) {
     memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
     memcpy(maps.g, pl->tmap_g, sizeof(maps.g));
     wgrad_tc_kernel<<<pl->grid, kThreads, pl->smem_bytes, stream>>>(maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
-                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec);
+                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec, pl->swap);
     RNR_LAUNCH_CHECK();
     return 0;
 }
