@@ -191,7 +191,7 @@ int rnr_bn_finalize(const float* partials, int T, int ld, int C, double count,
 /* act = drop * act(raw*scale + shift), written fp16 with reflect halo [N,H+2,W+2,C];
  * act_bf16 (optional, same layout) receives a bf16 copy: the B operand of the weight-gradient MMA
  * (kind::f16 needs both operands in the same 16-bit format and gradients are bf16)               */
-int rnr_bn_act_fwd(const float* raw, const float* scale, const float* shift,
+int rnr_bn_act_fwd(const void* raw, int raw_dtype /* RNR_F32 or 16-bit */, const float* scale, const float* shift,
                    const float* drop /* [N,C] or NULL */, float slope,
                    void* act, void* act_bf16, int N, int H, int W, int C, void* stream);
 
@@ -219,13 +219,13 @@ int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count,
  * totals [2,C] (double, must be 0 before the first call; the kernel re-zeroes it) and the last block to finish (ticket: an
  * int32 in device memory, 0 before the first call, re-armed by the kernel) writes dbeta = sum(gz), dgamma = sum(gz*xhat)
  * (either may be NULL) and, when coef != NULL, the coefficients (A, B, D) of rnr_bn_bwd_apply.                          */
-int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const float* raw,
+int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const void* raw, int raw_dtype,
                           const float* scale, const float* shift, const float* mean, const float* invstd,
                           const float* drop, float slope, void* gz, double* totals, int* ticket, double count,
                           float* dgamma, float* dbeta, const float* gamma, float* coef,
                           int N, int H, int W, int C, void* stream);
 /* pass 2 (in place): gz <- A*gz + B*raw + D */
-int rnr_bn_bwd_apply(void* gz, const float* raw, const float* coef, int N, int H, int W, int C, void* stream);
+int rnr_bn_bwd_apply(void* gz, const void* raw, int raw_dtype, const float* coef, int N, int H, int W, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* layout glue of the module-level API (NCHW fp32 <-> channels-last 16-bit)                    */

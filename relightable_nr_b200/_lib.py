@@ -102,11 +102,11 @@ def lib():
         "rnr_wgrad_unpack_plan_create": [C.POINTER(WUnpackJob), i32, C.POINTER(vp)],
         "rnr_wgrad_unpack_run": [vp, vp],
         "rnr_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp],
-        "rnr_bn_act_fwd": [vp, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
+        "rnr_bn_act_fwd": [vp, i32, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
-        "rnr_bn_bwd_reduce_fin": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, f64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "rnr_bn_bwd_reduce_fin": [C.POINTER(GSrc), i32, vp, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, f64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_finalize": [vp, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
-        "rnr_bn_bwd_apply": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "rnr_bn_bwd_apply": [vp, vp, i32, vp, i32, i32, i32, i32, vp],
         "rnr_pack_nchw_to_act": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "rnr_unpack_nhwc_to_nchw": [vp, vp, i32, i32, i32, i32, i32, vp],
         "rnr_tanh_bwd_pack": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -49,7 +49,21 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
 // -------------------------------------------------------------------------------------------
 // forward apply: act = drop * lrelu(raw*scale + shift), fp16, reflect halo
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
+// 8 consecutive channels of the raw (pre-BatchNorm) convolution output: fp32 (2 x 16 bytes) or 16-bit (16 bytes)
+__device__ __forceinline__ void load_raw8(const void* raw, int64_t idx, int dtype, float* r) {
+    if (dtype == RNR_F32) {
+        const float4 a = __ldcs((const float4*)((const float*)raw + idx));
+        const float4 b = __ldcs((const float4*)((const float*)raw + idx + 4));
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+    } else {
+        const uint4 u = __ldcs((const uint4*)((const unsigned short*)raw + idx));
+        const unsigned short* us = (const unsigned short*)&u;
+#pragma unroll
+        for (int e = 0; e < 8; e++) r[e] = cvt16(us[e], dtype);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const void* __restrict__ raw, int raw_dtype, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ drop, float slope,
                                   __half* __restrict__ act, __nv_bfloat16* __restrict__ act_b, int N, int H, int W, int C) {
     // grid.y = image row (n*H + h); threads of a row = (w, 8-channel vector): 32-bit index math only
@@ -62,12 +76,12 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
     const int c = (int)(idx - (unsigned)w * vpp) * 8;
     const int Hp = H + 2, Wp = W + 2;
     const int64_t pix = (int64_t)row * W + w;
-    const float4 r0 = __ldcs((const float4*)(raw + pix * C + c));
-    const float4 r1 = __ldcs((const float4*)(raw + pix * C + c + 4));
+    float rr[8];
+    load_raw8(raw, pix * C + c, raw_dtype, rr);
     const float4 s0 = *(const float4*)(scale + c), s1 = *(const float4*)(scale + c + 4);
     const float4 t0 = *(const float4*)(shift + c), t1 = *(const float4*)(shift + c + 4);
-    float v[8] = {r0.x * s0.x + t0.x, r0.y * s0.y + t0.y, r0.z * s0.z + t0.z, r0.w * s0.w + t0.w,
-                  r1.x * s1.x + t1.x, r1.y * s1.y + t1.y, r1.z * s1.z + t1.z, r1.w * s1.w + t1.w};
+    float v[8] = {rr[0] * s0.x + t0.x, rr[1] * s0.y + t0.y, rr[2] * s0.z + t0.z, rr[3] * s0.w + t0.w,
+                  rr[4] * s1.x + t1.x, rr[5] * s1.y + t1.y, rr[6] * s1.z + t1.z, rr[7] * s1.w + t1.w};
     float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
     if (drop) {
         const float4 d0 = *(const float4*)(drop + n * C + c), d1 = *(const float4*)(drop + n * C + c + 4);
@@ -268,7 +282,7 @@ __device__ __forceinline__ void split_pix(int pix, int HW, int W, int lhw, int l
 }
 
 template <int NSRC>
-__global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs srcs, const float* __restrict__ raw,
+__global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs srcs, const void* __restrict__ raw, int raw_dtype,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ drop, float slope,
@@ -309,7 +323,7 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
     const bool pre1 = NSRC > 1 && S1.dtype != RNR_F32;
     if (pl < ppb)
     for (int u0 = blockIdx.x; u0 < units; u0 += kRU * gridDim.x) {
-        float4 r0[kRU], r1[kRU];
+        float4 r0[kRU], r1[kRU];                     // fp32 raw: 8 floats; 16-bit raw: r0 carries the packed vector
         uint4 q0[kRU], q1[NSRC > 1 ? kRU : 1];
         int pixv[kRU];
         // ---- load phase: everything a pixel needs from HBM, for kRU pixels ----
@@ -319,8 +333,12 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
             const int pix = u * ppb + pl;
             pixv[j] = (u < units && pix < P) ? pix : -1;
             if (pixv[j] >= 0) {
-                r0[j] = __ldcs((const float4*)(raw + (int64_t)pix * C + c));
-                r1[j] = __ldcs((const float4*)(raw + (int64_t)pix * C + c + 4));
+                if (raw_dtype == RNR_F32) {
+                    r0[j] = __ldcs((const float4*)((const float*)raw + (int64_t)pix * C + c));
+                    r1[j] = __ldcs((const float4*)((const float*)raw + (int64_t)pix * C + c + 4));
+                } else {
+                    r0[j] = __ldcs((const float4*)((const unsigned short*)raw + (int64_t)pix * C + c));
+                }
                 int n, h, w;
                 split_pix(pix, HW, W, lhw, lw, n, h, w);
                 const int64_t ctr = ((int64_t)n * Hp + h + 1) * Wp + w + 1;
@@ -348,7 +366,14 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
                 if (pre1) acc_packed(q1[j], S1.dtype, g); else load8(S1.ptr, o, S1.dtype, g);
                 if (S1.fold && border) fold_border(S1, o, h, w, H, W, Wp, g);
             }
-            const float r[8] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w, r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+            float r[8];
+            if (raw_dtype == RNR_F32) {
+                r[0] = r0[j].x; r[1] = r0[j].y; r[2] = r0[j].z; r[3] = r0[j].w; r[4] = r1[j].x; r[5] = r1[j].y; r[6] = r1[j].z; r[7] = r1[j].w;
+            } else {
+                const unsigned short* us = (const unsigned short*)&r0[j];
+#pragma unroll
+                for (int e = 0; e < 8; e++) r[e] = cvt16(us[e], raw_dtype);
+            }
             __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
             for (int e = 0; e < 8; e++) {
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __res
     }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ gz, const float* __restrict__ raw,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ gz, const void* __restrict__ raw, int raw_dtype,
                                     const float* __restrict__ coef, int N, int H, int W, int C) {
     // gz <- A*gz + B*raw + D with the per-channel coefficients of bn_bwd_finalize (3 vector loads instead of 5x8 scalars)
     const unsigned vpp = (unsigned)C >> 3;
@@ -460,12 +485,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __rest
     __nv_bfloat16* gp = gz + (((int64_t)n * Hp + h + 1) * Wp + w + 1) * C + c;
     uint4 u = *(const uint4*)gp;
     __nv_bfloat16* gb = (__nv_bfloat16*)&u;
-    const float4 r0 = __ldcs((const float4*)(raw + pix * C + c));
-    const float4 r1 = __ldcs((const float4*)(raw + pix * C + c + 4));
+    float r[8];
+    load_raw8(raw, pix * C + c, raw_dtype, r);
     const float4 a0 = *(const float4*)(coef + c), a1 = *(const float4*)(coef + c + 4);
     const float4 b0 = *(const float4*)(coef + C + c), b1 = *(const float4*)(coef + C + c + 4);
     const float4 d0 = *(const float4*)(coef + 2 * C + c), d1 = *(const float4*)(coef + 2 * C + c + 4);
-    const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
     const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     const float B[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -485,13 +509,13 @@ extern "C" int rnr_bn_finalize(const float* partials, int T, int ld, int C, doub
     return 0;
 }
 
-extern "C" int rnr_bn_act_fwd(const float* raw, const float* scale, const float* shift, const float* drop, float slope,
+extern "C" int rnr_bn_act_fwd(const void* raw, int raw_dtype, const float* scale, const float* shift, const float* drop, float slope,
                               void* act, void* act_bf16, int N, int H, int W, int C, void* stream) {
     RNR_REQUIRE(C % 8 == 0, "rnr_bn_act_fwd: C=%d must be a multiple of 8", C);
     RNR_REQUIRE(H >= 2 && W >= 2, "rnr_bn_act_fwd: reflect halo needs H,W >= 2");
     RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_act_fwd: N*H=%lld exceeds the grid limit", (long long)N * H);
     dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
-    bn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
+    bn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, raw_dtype, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -519,7 +543,7 @@ extern "C" int rnr_bn_bwd_reduce(const rnr_gsrc_t* srcs, int nsrc, const float* 
     return 0;
 }
 
-extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const float* raw, const float* scale, const float* shift,
+extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const void* raw, int raw_dtype, const float* scale, const float* shift,
                                      const float* mean, const float* invstd, const float* drop, float slope, void* gz,
                                      double* totals, int* ticket, double count, float* dgamma, float* dbeta, const float* gamma,
                                      float* coef, int N, int H, int W, int C, void* stream) {
@@ -564,11 +588,11 @@ extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const flo
     RNR_REQUIRE(smem <= 160 * 1024, "rnr_bn_bwd_reduce_fin: C=%d needs %zu bytes of shared memory", C, smem);
     if (nsrc == 1)
         bn_bwd_reduce_fin_kernel<1><<<T, threads, smem, (cudaStream_t)stream>>>(
-            gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
+            gs, raw, raw_dtype, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
             N, H, W, C, ppb, prow, lhw, lw);
     else
         bn_bwd_reduce_fin_kernel<2><<<T, threads, smem, (cudaStream_t)stream>>>(
-            gs, raw, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
+            gs, raw, raw_dtype, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
             N, H, W, C, ppb, prow, lhw, lw);
     RNR_LAUNCH_CHECK();
     return 0;
@@ -584,11 +608,11 @@ extern "C" int rnr_bn_bwd_finalize(const float* partials, int T, int C, double c
     return 0;
 }
 
-extern "C" int rnr_bn_bwd_apply(void* gz, const float* raw, const float* coef, int N, int H, int W, int C, void* stream) {
+extern "C" int rnr_bn_bwd_apply(void* gz, const void* raw, int raw_dtype, const float* coef, int N, int H, int W, int C, void* stream) {
     RNR_REQUIRE(C % 8 == 0, "rnr_bn_bwd_apply: C=%d must be a multiple of 8", C);
     RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_bwd_apply: N*H=%lld exceeds the grid limit", (long long)N * H);
     dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
-    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, coef, N, H, W, C);
+    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, raw_dtype, coef, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }

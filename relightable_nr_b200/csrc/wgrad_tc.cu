@@ -5,8 +5,9 @@
 // As a GEMM:  D[M = co (128), N = ci (<=128)]  +=  G^T [M x K]  *  A [K x N],   K = pixels.
 // Both operands are "MN-major": the contiguous memory dimension (channels) is the M resp. N dimension,
 // so the tiles are used exactly as TMA writes them ([pixel rows x 64 channels], 128-byte rows, SWIZZLE_128B)
-// with MN-major UMMA descriptors -- no transposition pass.  G is bf16 and A is fp16: kind::f16 takes the
-// two formats independently in the instruction descriptor.
+// with MN-major UMMA descriptors -- no transposition pass.  Both operands must have the SAME 16-bit format: the
+// instruction descriptor has separate A / B format fields, but kind::f16 with fp16 x bf16 raises an illegal-instruction
+// fault on sm_100a (measured), which is why the engine keeps a bf16 copy of the activations for this kernel.
 //
 // Work item = (tap entry, co block of 128, ci chunk of <=128, pixel range); one persistent CTA per SM
 // walks its items; partial sums leave TMEM through fp32 red.global.add (dW is pre-zeroed by the caller).

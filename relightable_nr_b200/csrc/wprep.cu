@@ -190,20 +190,28 @@ struct WUnJob {
     int32_t blk0, nblk;
 };
 
+constexpr int UCO = 4;      // co rows per block: 4 x ntaps x 64 floats in flight per block (the one-row version was launch/latency bound)
+
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const WUnJob* __restrict__ jobs, const int* __restrict__ blk2job) {
-    __shared__ float tile[MAXT][CB + 1];
+    __shared__ float tile[UCO][MAXT][CB + 1];
     const WUnJob& J = jobs[blk2job[blockIdx.x]];
     const int local = blockIdx.x - J.blk0;
-    const int co = local / J.tiles_c, c0 = (local - co * J.tiles_c) * CB;
+    const int cog = local / J.tiles_c, c0 = (local - cog * J.tiles_c) * CB;
+    const int co0 = cog * UCO;
+    const int nco = min(UCO, J.cout - co0);
     const int nc = min(CB, J.cin - c0);
-    for (int i = threadIdx.x; i < J.ntaps * CB; i += 256) {
-        const int t = i / CB, cc = i - t * CB;
-        if (cc < nc) tile[t][cc] = __ldcs(J.src + ((int64_t)t * J.cout + co) * J.cin + c0 + cc);
+    const int per = J.ntaps * CB;
+    for (int i = threadIdx.x; i < nco * per; i += 256) {
+        const int r = i / per, j = i - r * per;
+        const int t = j / CB, cc = j - t * CB;
+        if (cc < nc) tile[r][t][cc] = __ldcs(J.src + ((int64_t)t * J.cout + co0 + r) * J.cin + c0 + cc);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nc * J.ntaps; i += 256) {
-        const int cc = i / J.ntaps, t = i - cc * J.ntaps;
-        J.dst[(int64_t)co * J.s_co + (int64_t)(c0 + cc) * J.s_ci + t] = tile[t][cc];
+    const int pero = nc * J.ntaps;
+    for (int i = threadIdx.x; i < nco * pero; i += 256) {
+        const int r = i / pero, j = i - r * pero;
+        const int cc = j / J.ntaps, t = j - cc * J.ntaps;
+        J.dst[(int64_t)(co0 + r) * J.s_co + (int64_t)(c0 + cc) * J.s_ci + t] = tile[r][t][cc];
     }
 }
 
@@ -226,7 +234,7 @@ extern "C" int rnr_wgrad_unpack_plan_create(const rnr_wunpack_job_t* jobs, int n
         d.src = s.src; d.dst = s.dst; d.cout = s.cout; d.cin = s.cin; d.ntaps = s.ntaps; d.s_co = s.s_co; d.s_ci = s.s_ci;
         d.tiles_c = rnr_cdiv(s.cin, CB);
         d.blk0 = blk;
-        d.nblk = s.cout * d.tiles_c;
+        d.nblk = rnr_cdiv(s.cout, UCO) * d.tiles_c;
         blk += d.nblk;
     }
     rnr_wunpack_plan* p = new rnr_wunpack_plan();

@@ -12,6 +12,7 @@ The dead GCN branch of UnetSkipConnectionBlock.forward (pytorch_prototyping.py:4
 at :416-419) is not executed; it cannot influence outputs or gradients.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -182,6 +183,10 @@ class UNetEngine:
         self.impl = {'simt': 0, 'tc': 1}[impl]
         self.wgrad_impl = {'simt': 0, 'tc': 1}[wgrad_impl or impl]
         self.act_dt, self.grad_dt = act_dtype, grad_dtype
+        # pre-BatchNorm convolution outputs: stored in the activation format on the tensor-core path (the statistics come from
+        # the fp32 accumulators in the epilogue; every BN pass then streams 2 instead of 4 bytes per element), fp32 on the SIMT
+        # validation path.  RNR_RAW_FP32=1 keeps fp32.
+        self.raw_dt = act_dtype if (impl == 'tc' and os.environ.get('RNR_RAW_FP32', '0') != '1') else F32
         self.in_channels = in_channels
         self.in_cpad = _rup(in_channels, 64) if in_channels > 32 else _rup(in_channels, 16)
         self.input_grad_range = input_grad_range
@@ -213,7 +218,10 @@ class UNetEngine:
         self.acts['input'] = HaloTensor(N, s0.H, s0.W, self.in_cpad, adt, dev, zero=True)
         # bf16 copies of the activations: B operand of the weight-gradient MMA (same format as the gradients)
         self.acts_w: Dict[str, HaloTensor] = {}
-        self.dual = self.need_backward and self.act_dt != self.grad_dt
+        # The weight-gradient MMA multiplies bf16 gradients with the activations.  kind::f16 with A = fp16 and B = bf16 (or the
+        # reverse) raises "illegal instruction" on sm_100a (measured: rnr_wgrad_run with RNR_DUAL=0), so the forward pass keeps
+        # a bf16 copy of every activation next to the fp16 one.
+        self.dual = self.need_backward and self.act_dt != self.grad_dt and os.environ.get('RNR_DUAL', '1') != '0'
         if self.dual:
             self.acts_w['input'] = HaloTensor(N, s0.H, s0.W, self.in_cpad, gdt, dev, zero=True)
         self.ones = {}
@@ -232,7 +240,7 @@ class UNetEngine:
                 self.out_ld = _rup(sp.cout, 64) if sp.cout > 32 else _rup(sp.cout, 16)
                 st.raw = self._alloc((N, Ho, Wo, self.out_ld), torch.float32, zero=True)
             else:
-                st.raw = self._alloc((N, Ho, Wo, sp.cout), torch.float32)
+                st.raw = self._alloc((N, Ho, Wo, sp.cout), _TORCH_DT[self.raw_dt])
                 self.acts[sp.dst] = HaloTensor(N, Ho, Wo, sp.cout, adt, dev, zero=True)
                 if self.dual:
                     self.acts_w[sp.dst] = HaloTensor(N, Ho, Wo, sp.cout, gdt, dev, zero=True)
@@ -430,7 +438,7 @@ class UNetEngine:
             if epi & EPI_STATS:
                 st.stats = self._alloc((tiles, 2, cout), torch.float32, zero=True)
             st.fwd_plans.append(self._conv_problem(
-                views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32,
+                views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32 if final else self.raw_dt,
                 (Ho * Wo * ld_out, Wo * ld_out, ld_out), (1, 1, 0, 0), epi, bias_t, st.stats, cout, self.impl))
             st.n_stat_tiles = self.L.rnr_conv_plan_stat_rows(st.fwd_plans[-1].h)
         elif sp.kind == 'c4s2':
@@ -453,7 +461,7 @@ class UNetEngine:
             if epi & EPI_STATS:
                 st.stats = self._alloc((tiles, 2, cout), torch.float32, zero=True)
             st.fwd_plans.append(self._conv_problem(
-                views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32,
+                views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Ho, Wo, st.raw, F32 if final else self.raw_dt,
                 (Ho * Wo * ld_out, Wo * ld_out, ld_out), (1, 1, 0, 0), epi, bias_t, st.stats, cout, self.impl))
             st.n_stat_tiles = self.L.rnr_conv_plan_stat_rows(st.fwd_plans[-1].h)
         else:  # ConvTranspose 4x4 s2 p1: four parity sub-problems, each a 2x2 conv over the un-padded input
@@ -482,7 +490,7 @@ class UNetEngine:
                     st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 4,
                                                16, cout * 16, self._tapoff(tapoffs), chunked=chunked))
                     probs.append(self._conv_problem(
-                        views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Hi, Wi, st.raw, F32,
+                        views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Hi, Wi, st.raw, F32 if final else self.raw_dt,
                         (Ho * Wo * ld_out, Wo * ld_out, ld_out), (2, 2, ph, pw), epi, bias_t, st.stats, cout, self.impl, defer=True))
             self.keep.append(probs)
             fused = self._fused_plan(probs, self.impl)
@@ -752,7 +760,7 @@ class UNetEngine:
             else:
                 shift = self.params[sp.b_key]
             st.drop = drop_masks.get(sp.name) if (drop_masks and sp.drop) else None
-            _lib.check(L.rnr_bn_act_fwd(st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
+            _lib.check(L.rnr_bn_act_fwd(st.raw.data_ptr(), self.raw_dt, st.scale.data_ptr(), shift.data_ptr(),
                                         st.drop.data_ptr() if st.drop is not None else None, sp.slope,
                                         self.acts[sp.dst].ptr, self.acts_w[sp.dst].ptr if self.dual else None,
                                         N, Ho, Wo, Cc, s), 'rnr_bn_act_fwd')
@@ -774,7 +782,7 @@ class UNetEngine:
         for sp in self.specs[:-1]:
             st = self.layers[sp.name]
             shift = st.shift if sp.bn_key is not None else self.params[sp.b_key]
-            z = st.raw * st.scale + shift
+            z = st.raw.float() * st.scale + shift
             out[sp.name] = (z > 0).permute(0, 3, 1, 2).contiguous()
         return out
 
@@ -843,7 +851,7 @@ class UNetEngine:
                     dgam, dbet = None, self.grad_view(sp.b_key).data_ptr()
                 gam = self.params[sp.bn_key + '.weight'].data_ptr() if has_bn else None
                 # pass 1 (activation' / dropout gate, per-channel sums) with the finalize fused into its last block
-                _lib.check(L.rnr_bn_bwd_reduce_fin(arr, len(srcs), st.raw.data_ptr(), st.scale.data_ptr(), shift.data_ptr(),
+                _lib.check(L.rnr_bn_bwd_reduce_fin(arr, len(srcs), st.raw.data_ptr(), self.raw_dt, st.scale.data_ptr(), shift.data_ptr(),
                                                    st.mean.data_ptr(), st.invstd.data_ptr(),
                                                    st.drop.data_ptr() if st.drop is not None else None, sp.slope,
                                                    self.gz[sp.name].ptr, st.bwd_totals.data_ptr(), st.ticket.data_ptr(),
@@ -851,7 +859,7 @@ class UNetEngine:
                                                    N, Ho, Wo, Cc, s), 'rnr_bn_bwd_reduce_fin')
                 self.gpu_launches += 1
                 if has_bn:
-                    _lib.check(L.rnr_bn_bwd_apply(self.gz[sp.name].ptr, st.raw.data_ptr(), st.coef.data_ptr(), N, Ho, Wo, Cc, s),
+                    _lib.check(L.rnr_bn_bwd_apply(self.gz[sp.name].ptr, st.raw.data_ptr(), self.raw_dt, st.coef.data_ptr(), N, Ho, Wo, Cc, s),
                                'rnr_bn_bwd_apply')
                     self.gpu_launches += 1
             t0 = self._mark()
