@@ -10,7 +10,7 @@ views sharded over ranks (weak scaling), one NCCL all-reduce of the gradients pe
 
 Prints ONE JSON line (rank 0).  ``value`` = views/s with the per-view maps resident in HBM; ``e2e`` = the same step fed
 from pinned host buffers (H2D of the 8 per-view maps + D2H of the loss inside the timed region); ``roofline`` = live
-conv FLOPs of the tcgen05 implicit-GEMM kernel / its CUDA-event time / measured bf16 peak; ``cpu_baseline`` = the oracle
+conv FLOPs of the tcgen05 implicit-GEMM kernel (conv_halo_kernel) / its CUDA-event time / measured bf16 peak; ``cpu_baseline`` = the oracle
 port of the same step on the host cores.  ``--impl reference`` times that CPU path alone (the reference is PyTorch-CPU
 Python: it cannot travel to the GPU box, so the arm is the golden-pinned oracle port of it -- kind "port").
 """
@@ -360,7 +360,7 @@ def run_ours(args):
         conv_flops = fl['fwd'] + fl['dgrad']
         conv_ms = t['fwd'] + t['dgrad']
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
-        roof = {'kernel': 'conv_tc_kernel (tcgen05 implicit GEMM: 22 fwd + dgrad launches of the U-Net)', 'bound': 'tensor',
+        roof = {'kernel': 'conv_halo_kernel (tcgen05 implicit GEMM with shared-memory halo reuse: forward + data-gradient launches of the 22 U-Net layers)', 'bound': 'tensor',
                 'achieved': ach, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sust'], 'traffic': None,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (%s)' % pk['src'],
                 'flops_per_step': conv_flops, 'launches_per_step': nl['fwd'] + nl['dgrad'], 'avg_launch_us': conv_ms * 1e3 / (nl['fwd'] + nl['dgrad']),
