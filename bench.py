@@ -335,13 +335,14 @@ def run_ours(args):
 
     # ---- roofline leg: CUDA events around every conv launch (same stream), outside the timed regions -----------------------
     roof = None
+    # (every rank runs the eager steps: at N > 1 they contain the gradient all-reduce, a collective)
+    eng = [e for k, e in pipe.render_net.net._runner._engines.items() if e.need_backward][0]
+    eng.timing = []
+    for i in range(3):
+        eager_step(views[i % nviews])
+    torch.cuda.synchronize()
+    rec, eng.timing = eng.timing, None
     if rank == 0:
-        eng = [e for k, e in pipe.render_net.net._runner._engines.items() if e.need_backward][0]
-        eng.timing = []
-        for i in range(3):
-            eager_step(views[i % nviews])
-        torch.cuda.synchronize()
-        rec, eng.timing = eng.timing, None
         t = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
         nl = {'fwd': 0, 'dgrad': 0, 'wgrad': 0}
         for kind, name, a, b in rec:
@@ -369,10 +370,19 @@ def run_ours(args):
                                     'launches_per_step': nl['wgrad']},
                 'whole_step_tflops': (fl['fwd'] + fl['dgrad'] + fl['wgrad']) * args.steps / (ms * 1e-3) / 1e12}
 
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    def teardown():
+        # destroy_process_group() blocks forever while a captured CUDA graph still references the communicator's work
+        # (measured: both ranks parked in it after a complete run), so the ranks leave through os._exit once rank 0 has
+        # printed its line; the process exit tears NCCL down.
+        if world > 1:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
     if rank != 0:
+        teardown()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -387,9 +397,14 @@ def run_ours(args):
         'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'last_loss': last_loss[0],
     }
     print(json.dumps(line))
+    teardown()
 
 
 def main():
+    if os.environ.get('RNR_BENCH_WATCHDOG'):
+        # debugging aid: dump every thread's Python stack and exit if the run is still going after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['RNR_BENCH_WATCHDOG']), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
