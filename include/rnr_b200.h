@@ -354,6 +354,22 @@ int rnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
                   float eps, int step, float gscale, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* gcn_lib/dense EdgeConv (network.DenseDeepGCN, network.py:256-315)                           */
+/*   EdgeConv4D torch_vertex.py:23-35 over BasicConv = Conv2d(1x1) -> act -> BatchNorm2d        */
+/*   torch_nn.py:55-64.  pq [V, 2C] = (P | Q): P = X (W1-W2)^T + b, Q = X W2^T (one GEMM by the  */
+/*   caller; W = [W1 | W2] acts on cat[x_i, x_j - x_i]).  nbr [V,K] int32 = neighbour indices.   */
+/* ------------------------------------------------------------------------------------------ */
+/* a_k = act(P[v,c] + Q[nbr[v,k],c]); amax/amin [V,C] = max/min over k; sums[2C] (double, pre-zeroed, may be NULL)
+ * += sum a_k, sum a_k^2 over all V*K edges (BatchNorm batch statistics)                                              */
+int rnr_edgeconv_reduce(const float* pq, const int32_t* nbr, int V, int K, int C, float slope, float* amax, float* amin,
+                        double* sums, void* stream);
+/* out[v,c] = BN(max_k a_k) (+ residual): the affine BN map commutes with max (scale >= 0) or turns it into min (scale < 0);
+ * gamma == NULL: no normalisation.  training: batch statistics from sums / count (+ running-stat update), else running stats */
+int rnr_edgeconv_finish(const float* amax, const float* amin, const double* sums, double count, const float* gamma,
+                        const float* beta, float eps, float* running_mean, float* running_var, float momentum, int training,
+                        const float* residual, float* out, int V, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Fused producers / consumers around the U-Net (csrc/fused.cu): the same operators as above,  */
 /* composed so that no intermediate crosses HBM in a layout its consumer cannot use directly.  */
 /* ------------------------------------------------------------------------------------------ */

@@ -177,12 +177,33 @@ def gen_raster():
     return out
 
 
+def gen_gcn(ref):
+    """network.DenseDeepGCN (network.py:256-315) at a small size, training mode (batch-statistic BN, spectral-norm power
+    iteration), stochastic dilation off so that the run is deterministic.  The state dict is captured BEFORE the forward."""
+    import types
+    torch.manual_seed(0)
+    opt = types.SimpleNamespace(n_filters=16, kernel_size=4, act_type='relu', norm_type='batch', bias=True, epsilon=0.0,
+                                stochastic=False, conv_type='edge', n_blocks=4, num_v_gcn=96, out_channels_gcn=8, in_channels=6,
+                                block_type='res')
+    net = ref.network.DenseDeepGCN(opt)
+    net.train()
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(96, 3, generator=g)
+    sd = {k: t.detach().clone() for k, t in net.state_dict().items()}
+    inputs = types.SimpleNamespace(pos=v, x=v)
+    fea = net(inputs)
+    out = {'gcn_sd__' + k: t for k, t in sd.items()}
+    out.update(gcn_v=v, gcn_fea=fea.detach(), gcn_keys=np.array(sorted(sd.keys())))
+    return out
+
+
 def main():
     ref = import_reference()
+    np.savez_compressed(os.path.join(HERE, 'gcn_small.npz'), **_np(gen_gcn(ref)))
     np.savez_compressed(os.path.join(HERE, 'pixel_ops.npz'), **_np(gen_pixel_ops(ref)))
     np.savez_compressed(os.path.join(HERE, 'unet_small.npz'), **_np(gen_unet(ref)))
     np.savez_compressed(os.path.join(HERE, 'raster.npz'), **_np(gen_raster()))
-    for f in ('pixel_ops.npz', 'unet_small.npz', 'raster.npz'):
+    for f in ('pixel_ops.npz', 'unet_small.npz', 'raster.npz', 'gcn_small.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
 
 
