@@ -517,6 +517,11 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     // a wider N tile reads fewer shared-memory operand bytes per FLOP (the SS-mode MMA is shared-memory-bandwidth bound below N = 256),
     // so N is only narrowed when the launch would otherwise leave most SMs idle
     while (bn > 64 && bn % 32 == 0 && p.tiles_m * tiles_n * nsub < (bn > 128 ? 100 : 50)) { bn /= 2; tiles_n = rnr_cdiv(prob->n_rows_w, bn); }
+    // <= 32^2 layers: even N = 64 leaves most SMs without a tile and every CTA with a long, latency-bound K loop over a
+    // 512-channel input; N = 32 doubles the CTAs and halves the weight bytes each one has to pull through its B ring
+    if (bn == 64 && p.tiles_m * tiles_n * nsub <= 74 && prob->n_rows_w % 32 == 0 && !(getenv("RNR_CONV_BN32") && getenv("RNR_CONV_BN32")[0] == '0')) {
+        bn = 32; tiles_n = rnr_cdiv(prob->n_rows_w, bn);
+    }
     pl->bn = bn;
     pl->tiles_n = tiles_n;
     const int a_stage = ((rows * pitch * 128) + 1023) / 1024 * 1024;

@@ -190,28 +190,39 @@ struct WUnJob {
     int32_t blk0, nblk;
 };
 
-constexpr int UCO = 4;      // co rows per block: 4 x ntaps x 64 floats in flight per block (the one-row version was launch/latency bound)
+constexpr int UCO = 4;      // co rows per block (one per group of 64 threads)
 
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const WUnJob* __restrict__ jobs, const int* __restrict__ blk2job) {
     __shared__ float tile[UCO][MAXT][CB + 1];
     const WUnJob& J = jobs[blk2job[blockIdx.x]];
     const int local = blockIdx.x - J.blk0;
     const int cog = local / J.tiles_c, c0 = (local - cog * J.tiles_c) * CB;
-    const int co0 = cog * UCO;
-    const int nco = min(UCO, J.cout - co0);
+    const int r = threadIdx.x >> 6, cc = threadIdx.x & 63;     // thread = (co row of the block, input channel of the chunk)
+    const int co = cog * UCO + r;
     const int nc = min(CB, J.cin - c0);
-    const int per = J.ntaps * CB;
-    for (int i = threadIdx.x; i < nco * per; i += 256) {
-        const int r = i / per, j = i - r * per;
-        const int t = j / CB, cc = j - t * CB;
-        if (cc < nc) tile[r][t][cc] = __ldcs(J.src + ((int64_t)t * J.cout + co0 + r) * J.cin + c0 + cc);
+    const int ntaps = J.ntaps;
+    // loads: every thread fetches its channel of all taps (ntaps independent 4-byte loads in flight; a warp reads 128 B rows)
+    if (co < J.cout && cc < nc) {
+        const float* sp = J.src + (int64_t)co * J.cin + c0 + cc;
+        const int64_t tstride = (int64_t)J.cout * J.cin;
+        float v[MAXT];
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) v[t] = (t < ntaps) ? __ldcs(sp + t * tstride) : 0.f;
+#pragma unroll
+        for (int t = 0; t < MAXT; t++)
+            if (t < ntaps) tile[r][t][cc] = v[t];
     }
     __syncthreads();
-    const int pero = nc * J.ntaps;
-    for (int i = threadIdx.x; i < nco * pero; i += 256) {
-        const int r = i / pero, j = i - r * pero;
-        const int cc = j / J.ntaps, t = j - cc * J.ntaps;
-        J.dst[(int64_t)(co0 + r) * J.s_co + (int64_t)(c0 + cc) * J.s_ci + t] = tile[r][t][cc];
+    // stores: row r of the block is a contiguous run of nc * ntaps floats when s_ci == ntaps (nn.Conv2d); j / ntaps by a
+    // multiply-shift (j < 1024, ntaps <= 16: exact)
+    if (co < J.cout) {
+        const unsigned magic = (65536u + ntaps - 1) / ntaps;
+        float* dp = J.dst + (int64_t)co * J.s_co + (int64_t)c0 * J.s_ci;
+        const int run = nc * ntaps;
+        for (int j = cc; j < run; j += 64) {
+            const int ci = (int)(((unsigned)j * magic) >> 16), t = j - ci * ntaps;
+            dp[(int64_t)ci * J.s_ci + t] = tile[r][t][ci];
+        }
     }
 }
 
