@@ -1,0 +1,130 @@
+"""Launcher that runs the reference's UNCHANGED scripts (train_rnr.py, test_rnr.py, train_dnr.py, test_dnr.py, precompute.py)
+on top of the B200 drop-in modules (SURVEY.md 8b "How the unchanged scripts bind to the replacement"):
+
+    python -m relightable_nr_b200.run /path/to/relightable-nr/train_rnr.py --data_root ... --gpu_id 0
+
+The scripts do plain top-level imports (``import network``, ``import neural_renderer as nr``, train_rnr.py:14-24) and Python
+puts the script's own directory first on ``sys.path``, so the drop-ins are registered in ``sys.modules`` BEFORE the script
+starts: ``network, render, camera, sph_harm, misc, neural_renderer(.cuda.*), pytorch_prototyping(.pytorch_prototyping),
+gcn_lib(.dense/.sparse)`` resolve to relightable_nr_b200/dropin; ``dataio, data_util, util, metric`` (host I/O, out of scope)
+keep resolving to the reference's own files next to the script.
+
+Compatibility shims for this software stack (part of the boundary, not of the reference): ``np.int`` / ``np.float`` aliases
+(removed in numpy 1.24); ``tensorboardX.SummaryWriter`` -> ``torch.utils.tensorboard`` (or a no-op writer);
+``torch_geometric.data.Data`` (attribute bag with ``.to()``: the only thing train_rnr.py:258 uses); ``torch_cluster`` (imported
+by gcn_lib, never called on the dense path); ``pytorch_msssim`` (metric.py:3, validation only), ``skimage.transform``
+(data_util.py:3), ``pyshtools`` (replaced by the drop-in sph_harm), ``trimesh``: registered only when the real package is
+absent; ``torchvision.utils.make_grid(range=...)`` (renamed ``value_range``); ``OPENCV_IO_ENABLE_OPENEXR=1``.
+"""
+import importlib
+import os
+import runpy
+import sys
+import types
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    try:
+        return importlib.import_module(name)
+    except Exception:
+        pass
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__rnr_stub__ = True
+    sys.modules[name] = m
+    return m
+
+
+class _NullWriter:
+    """tensorboardX.SummaryWriter stand-in when no TensorBoard writer is importable: accepts and drops every call."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
+class Data:
+    """torch_geometric.data.Data as train_rnr.py:258 uses it: named tensors + ``.to(device)``."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def to(self, device, *a, **k):
+        import torch
+        return Data(**{k_: (v.to(device, *a, **k) if isinstance(v, torch.Tensor) else v) for k_, v in self.__dict__.items()})
+
+
+def install_shims():
+    os.environ.setdefault('OPENCV_IO_ENABLE_OPENEXR', '1')
+    import numpy as np
+    for nm, ty in (('int', int), ('float', float), ('bool', bool)):
+        if not hasattr(np, nm):
+            setattr(np, nm, ty)
+    # tensorboardX
+    try:
+        importlib.import_module('tensorboardX')
+    except Exception:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+        except Exception:
+            SummaryWriter = _NullWriter
+        _stub('tensorboardX', SummaryWriter=SummaryWriter)
+    # torch_geometric / torch_cluster
+    tg = _stub('torch_geometric')
+    if getattr(tg, '__rnr_stub__', False):
+        tg.data = _stub('torch_geometric.data', Data=Data)
+        tg.nn = _stub('torch_geometric.nn')
+        tg.utils = _stub('torch_geometric.utils')
+    _stub('torch_cluster', knn_graph=None)
+    _stub('pyshtools')
+    _stub('trimesh')
+    # pytorch_msssim.ssim is only called by the validation metrics (metric.py:47-84, out of scope)
+    def _no_ssim(*a, **k):
+        raise NotImplementedError('pytorch_msssim is not installed (validation-only metric, out of the hot path)')
+    _stub('pytorch_msssim', ssim=_no_ssim, ms_ssim=_no_ssim)
+    sk = _stub('skimage')
+    if getattr(sk, '__rnr_stub__', False):
+        sk.transform = _stub('skimage.transform')
+        sk.io = _stub('skimage.io')
+    # torchvision.utils.make_grid(range=...) -> value_range
+    try:
+        import inspect
+        import torchvision.utils as tvu
+        if 'range' not in inspect.signature(tvu.make_grid).parameters and not getattr(tvu.make_grid, '__rnr_wrapped__', False):
+            _orig = tvu.make_grid
+
+            def make_grid(tensor, *a, range=None, **k):
+                if range is not None and 'value_range' not in k:
+                    k['value_range'] = range
+                return _orig(tensor, *a, **k)
+
+            make_grid.__rnr_wrapped__ = True
+            tvu.make_grid = make_grid
+    except Exception:
+        pass
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv or argv[0] in ('-h', '--help'):
+        print(__doc__)
+        return 0
+    script = os.path.abspath(argv[0])
+    if not os.path.isfile(script):
+        raise SystemExit('relightable_nr_b200.run: no such script: %s' % script)
+    install_shims()
+    from . import dropin
+    installed = dropin.install()
+    print('relightable_nr_b200.run: drop-in modules registered: %s' % ', '.join(installed), file=sys.stderr)
+    sys.argv = [script] + argv[1:]
+    sys.path.insert(0, os.path.dirname(script))          # dataio / data_util / util / metric: the reference's own files
+    runpy.run_path(script, run_name='__main__')
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
