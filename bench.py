@@ -233,9 +233,20 @@ def run_ours(args):
             dist.all_reduce(g)
             g.mul_(1.0 / world)
 
+    def allreduce_mean(t):
+        dist.all_reduce(t)
+        t.mul_(1.0 / world)
+
+    if not args.no_fused and world > 1:
+        # fused step: the weight gradients are all-reduced in GEMM order while the backward pass is still running
+        # (relightable_nr_b200/fused.py); RNR_AR_OVERLAP=0 falls back to one bucket list after the backward pass
+        if os.environ.get('RNR_AR_OVERLAP', '1') != '0':
+            pipe.fused.allreduce = allreduce_mean
+        else:
+            pipe.fused.grad_hook = sync_grad_buffers
+
     def eager_step(view):
         if not args.no_fused:
-            pipe.fused.grad_hook = sync_grad_buffers if world > 1 else None
             return pipe.fused.train_step(view)[0]
         final, rays_lt, alpha_map = pipe.forward(view)
         loss, _ = pipe.losses(view, final, rays_lt, alpha_map)
@@ -252,7 +263,7 @@ def run_ours(args):
         if args.no_fused:
             step, _static = pipe.make_graphed_step(views[0], grad_hook=(lambda ps: sync_grads()) if world > 1 else None)
         else:
-            step, _static = pipe.make_graphed_step(views[0], grad_hook=sync_grad_buffers if world > 1 else None, fused=True)
+            step, _static = pipe.make_graphed_step(views[0], fused=True)
 
     def barrier():
         if world > 1:

@@ -15,6 +15,7 @@
 // The arithmetic of every stage is the one of the module-level kernels (texture.cu, rays.cu, loss.cu), statement by
 // statement, so the fused step and the drop-in modules agree to fp32 rounding.
 #include "pixel.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -504,6 +505,12 @@ extern "C" int rnr_head_fwd(const float* const* tex, const int* sizes, int n_lev
     return 0;
 }
 
+static int tail_carveout() {
+    const char* e = getenv("RNR_TAIL_CARVEOUT");            // percent of the SM's shared memory / L1 array given to shared memory
+    const int v = e ? atoi(e) : 50;
+    return v < 0 ? 0 : (v > 100 ? 100 : v);
+}
+
 static int fill_tail(TailParams& q, const float* raw, int ldraw, const float* rays_uv, const float* albedo, const float* lp4,
                      int Hl, int Wl, const float* alpha, const float* img, int Rs, int Rd, int N, int H, int W, int crop,
                      float* final_img, float* aux, double* sums) {
@@ -527,7 +534,13 @@ extern "C" int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, c
     RNR_REQUIRE(final_img, "tail: null output");
     const size_t smem = (size_t)kTailPx * (2 * raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd) + 4) * sizeof(float);
     static bool attr = false;
-    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+    if (!attr) {
+        RNR_CHECK(cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        // the kernel is bound by the envmap texel gathers (4 x 16 B per ray, L1 misses go to L2 one sector at a time): cap the
+        // shared-memory carve-out so that the rest of the 228 KB stays L1 for the 2 MB envmap's working set
+        RNR_CHECK(cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, tail_carveout()));
+        attr = true;
+    }
     int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
     if (blocks > 148 * 8) blocks = 148 * 8;
     tail_fwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(q);
@@ -550,7 +563,11 @@ extern "C" int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, c
     qq.g_lp4 = (float4*)g_lp4;
     const size_t smem = (size_t)kTailPx * (raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd) + 12) * sizeof(float);
     static bool attr = false;
-    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+    if (!attr) {
+        RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, tail_carveout()));
+        attr = true;
+    }
     int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
     if (blocks > 148 * 8) blocks = 148 * 8;
     tail_bwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(qq);

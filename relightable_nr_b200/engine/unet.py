@@ -255,9 +255,16 @@ class UNetEngine:
                 st.bwd_partials = self._alloc((148 * 8 * 2 * max(ld, 8),), torch.float32)
                 st.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
                 st.bwd_totals = torch.zeros(2 * max(ld, 8), dtype=torch.float64, device=dev)
-            # flat gradient storage
-            for key in (sp.w_key, sp.b_key, (sp.bn_key + '.weight') if sp.bn_key else None,
-                        (sp.bn_key + '.bias') if sp.bn_key else None):
+        # flat gradient storage: all convolution weights first, then the small tensors (biases, BatchNorm affine) as one
+        # contiguous tail -- a data-parallel step all-reduces the weight gradients early, in GEMM order (wscratch), and only this
+        # tail after the backward pass
+        for sp in self.specs:
+            n = self.params[sp.w_key].numel()
+            self.grad_slices[sp.w_key] = (grad_numel, n)
+            grad_numel += _rup(n, 4)
+        self.grad_small_offset = grad_numel
+        for sp in self.specs:
+            for key in (sp.b_key, (sp.bn_key + '.weight') if sp.bn_key else None, (sp.bn_key + '.bias') if sp.bn_key else None):
                 if key is not None:
                     n = self.params[key].numel()
                     self.grad_slices[key] = (grad_numel, n)
@@ -832,7 +839,10 @@ class UNetEngine:
         self.gpu_launches += 1
         return self._backward_layers()
 
-    def _backward_layers(self):
+    def _backward_layers(self, after_layer=None, before_unpack=None):
+        """Backward of every layer in reverse order.  ``after_layer(name)`` is called once a layer's weight- and data-gradient
+        launches are enqueued, ``before_unpack()`` before the weight gradients leave GEMM order (hooks of the data-parallel
+        step: early all-reduce of ``wscratch``)."""
         L, s = self.L, self._stream()
         N = self.N
         for sp in reversed(self.specs):
@@ -871,6 +881,10 @@ class UNetEngine:
                 self.gpu_launches += 1
             if st.dgrad_plans:
                 self._mark('dgrad', sp.name, t1)
+            if after_layer is not None:
+                after_layer(sp.name)
+        if before_unpack is not None:
+            before_unpack()
         if self.wunpack_plan is not None:
             _lib.check(L.rnr_wgrad_unpack_run(self.wunpack_plan.h, s), 'rnr_wgrad_unpack_run')
             self.gpu_launches += 1

@@ -47,6 +47,13 @@ class FusedRNRStep:
         self._shape = None
         self.side = torch.cuda.Stream(device=self.dev)
         self.grad_hook = None          # callable(list of gradient tensors) between backward and the optimiser (data parallel)
+        #: data-parallel averaging, overlapped with the backward pass: callable(tensor) that all-reduces ONE gradient buffer in
+        #: place and scales it by 1/world (enqueued on the current stream).  The weight gradients of the layers that finish
+        #: first in backward order -- 95 % of all parameters -- go out, still in GEMM order, while the full-resolution layers
+        #: are being differentiated; the rest follows before the un-transpose, the small tensors and textures at the end.
+        self.allreduce = None
+        self.comm = torch.cuda.Stream(device=self.dev)
+        self.early_layer = 'b3.down1'  # last layer (in backward order) whose weight gradient joins the early bucket
 
     # ------------------------------------------------------------------------------------------------------------------
     def _setup(self, N, H, W, need_backward):
@@ -209,7 +216,27 @@ class FusedRNRStep:
                                   eng.gz['out'].ptr, eng.out_ld, eng.grad_view(sp.b_key).data_ptr(), self.g_alb.data_ptr(),
                                   self.g_lp4.data_ptr(), _s()), 'rnr_tail_bwd')
         main.wait_stream(side)                      # data-gradient weight matrices + small-loss gradients are in place
-        gi = eng._backward_layers()                 # [N, C, H, W] gradient w.r.t. the texture channels of the input
+        after_layer = before_unpack = None
+        overlap = (self.allreduce is not None and eng.wscratch is not None and len(eng.wscratch_slices) == len(eng.specs)
+                   and self.early_layer in eng.wscratch_slices)
+        if overlap:
+            comm, ar = self.comm, self.allreduce
+            w0 = eng.wscratch_slices[self.early_layer][0]
+
+            def after_layer(name):
+                if name != self.early_layer:
+                    return
+                comm.wait_stream(main)              # every weight gradient from `early_layer` to the last layer is complete
+                with torch.cuda.stream(comm):
+                    ar(eng.wscratch[w0:])
+
+            def before_unpack():
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    if w0 > 0:
+                        ar(eng.wscratch[:w0])
+                main.wait_stream(comm)
+        gi = eng._backward_layers(after_layer, before_unpack)   # [N, C, H, W] gradient w.r.t. the texture channels of the input
         gi[:, :6] += self.g_alb
         tm = p.texture_mapper
         gp = (C.c_void_p * len(self.tex_grads))(*[g.data_ptr() for g in self.tex_grads])
@@ -225,6 +252,15 @@ class FusedRNRStep:
         # loss value (device scalars; no host sync)
         cnt = float(N * 3 * (H - 2 * self.CROP) * (W - 2 * self.CROP))
         loss = (self.sums[2] / cnt + self.sums[0] / self.sums[1] / self.R * p.w['rays_lt_chrom']).float() + small
+        if overlap:
+            # weights are averaged already (GEMM-order scratch); what is left: biases / BatchNorm affine, textures, SH coefficients
+            self.allreduce(eng.grad_flat[eng.grad_small_offset:])
+            for g in self.tex_grads:
+                self.allreduce(g)
+            self.allreduce(self.coeff_grad)
+        elif self.allreduce is not None:
+            for g in self.grad_tensors():
+                self.allreduce(g)
         if self.grad_hook is not None:
             self.grad_hook(self.grad_tensors())
         if step_optimizer:

@@ -197,7 +197,8 @@ class RNRPipeline:
 
         def body_fused():
             # grad_hook receives the step's gradient buffers (engine flat buffer, texture levels, SH coefficients)
-            self.fused.grad_hook = (lambda gs: grad_hook(gs)) if grad_hook is not None else None
+            if grad_hook is not None:
+                self.fused.grad_hook = lambda gs: grad_hook(gs)
             loss, _ = self.fused.train_step(static_view)
             return loss.detach()
 
