@@ -133,3 +133,35 @@ def test_fused_cuda_graph_step():
     print(ref, got)
     for x, y in zip(ref, got):
         assert abs(x - y) <= 2e-3 * max(1.0, abs(x)), (ref, got)
+
+
+def test_full_size_fused_step_matches_oracle():
+    """BASELINE.json's benchmark configuration itself (512x512 view, texture 512^2 x 24 ch x 4 mips, U-Net 108 -> 78 with nf0 = 64,
+    26 rays, SH lmax 10 / 256x512 envmap): one fused training step on the GPU against the CPU fp32 oracle of train_rnr.py:512-608.
+    Gates: render PSNR >= 50 dB, loss within 2e-3 relative, gradient cosine >= 0.98 for the textures / SH coefficients and
+    >= 0.97 for every U-Net tensor (fp16 activations, bf16 gradients; ~0.1 % of the ReLU gates flip at this depth)."""
+    from oracle.rnr_step import rnr_step, state_from_pipeline
+    from relightable_nr_b200.pipeline import RNRPipeline, synthetic_view
+    pipe = RNRPipeline(device='cuda:0', img_size=512, dropout=False)
+    view = synthetic_view(512, view_idx=7, device='cuda:0')
+    state = state_from_pipeline(pipe)
+    loss, final = pipe.fused.train_step(view, step_optimizer=False)
+    torch.cuda.synchronize()
+    ref_loss, ref_final, ref_grads = rnr_step(state, view)
+    p = psnr(final.cpu(), ref_final)
+    print('512^2 fused step: PSNR %.1f dB, loss %.6f vs oracle %.6f' % (p, loss.item(), ref_loss.item()))
+    assert p >= 50.0
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    for i, t in enumerate(pipe.texture_mapper.textures):
+        c = cosine(t.grad.cpu(), ref_grads['textures.%d' % i])
+        print('texture %d grad cosine %.5f' % (i, c))
+        assert c >= 0.98
+    assert cosine(pipe.lighting_model.coeff.grad[0].cpu(), ref_grads['coeff']) >= 0.98
+    worst, wk = 1.0, None
+    for k, p_ in pipe.render_net.named_parameters():
+        if p_.grad is not None and 'unet/' + k in ref_grads:
+            c = cosine(p_.grad.cpu(), ref_grads['unet/' + k])
+            if c < worst:
+                worst, wk = c, k
+    print('worst U-Net grad cosine %.5f (%s)' % (worst, wk))
+    assert worst >= 0.97
