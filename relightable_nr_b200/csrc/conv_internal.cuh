@@ -83,6 +83,8 @@ struct rnr_wgrad_plan {
     int n_work;          // tc work items
     int vec;             // 1: dW destination is ci-contiguous -> 128-bit vector reductions
     int swap;            // 1: M = input channels, N = output channels
+    // halo-reuse / multi-tap kernel (wgrad_halo.cu)
+    int halo, halo_pitch, halo_a_stride, halo_a_bytes, halo_stage_bytes, halo_nbuf;
     int* d_work_tab;     // [n_work, 8]
 };
 
@@ -93,3 +95,5 @@ int rnr_conv_halo_prepare(rnr_conv_plan* plan, const rnr_conv_problem_t* probs, 
 int rnr_conv_halo_run(const rnr_conv_plan* plan, cudaStream_t stream);
 int rnr_wgrad_tc_prepare(rnr_wgrad_plan* plan, const rnr_wgrad_problem_t* prob);
 int rnr_wgrad_tc_run(const rnr_wgrad_plan* plan, cudaStream_t stream);
+int rnr_wgrad_halo_prepare(rnr_wgrad_plan* plan, const rnr_wgrad_problem_t* prob);
+int rnr_wgrad_halo_run(const rnr_wgrad_plan* plan, cudaStream_t stream);

@@ -330,7 +330,8 @@ extern "C" int rnr_wgrad_plan_create(const rnr_wgrad_problem_t* prob, int impl, 
     if (e != cudaSuccess) { rnr_set_error("rnr_wgrad_plan_create: %s", cudaGetErrorString(e)); free(pl->h_taps); delete pl; return (int)e; }
     p.taps = pl->d_taps;
     if (impl == 1) {
-        int rc = rnr_wgrad_tc_prepare(pl, prob);
+        int rc = rnr_wgrad_halo_prepare(pl, prob);           // halo reuse + one accumulator per tap where the layer is large ...
+        if (rc == 0 && !pl->halo) rc = rnr_wgrad_tc_prepare(pl, prob);   // ... else one box pair per tap
         if (rc != 0) { cudaFree(pl->d_taps); free(pl->h_taps); delete pl; return rc; }
     } else {
         std::vector<int> tab;
@@ -364,7 +365,7 @@ extern "C" void rnr_wgrad_plan_destroy(rnr_wgrad_plan_t* plan) {
 
 extern "C" int rnr_wgrad_run(const rnr_wgrad_plan_t* plan, void* stream) {
     RNR_REQUIRE(plan, "rnr_wgrad_run: null plan");
-    if (plan->impl == 1) return rnr_wgrad_tc_run(plan, (cudaStream_t)stream);
+    if (plan->impl == 1) return plan->halo ? rnr_wgrad_halo_run(plan, (cudaStream_t)stream) : rnr_wgrad_tc_run(plan, (cudaStream_t)stream);
     dim3 grid(plan->n_tiles, plan->splitk);
     wgrad_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(plan->p, plan->d_tile_tab, plan->splitk);
     RNR_LAUNCH_CHECK();
