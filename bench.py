@@ -369,11 +369,16 @@ def run_ours(args):
                 r0, r1 = (eng.input_grad_range if sp.name == 'in' else (0, sum(sp.cin)))
                 fl['dgrad'] += f * (r1 - r0) / sum(sp.cin)
         pk = _peaks()
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'r01_conv_halo_traffic.json')     # dram bytes per launch from the committed ncu capture
+        if os.path.exists(tp) and args.size == 512:
+            traffic = json.load(open(tp)).get('traffic_bytes_per_launch')
         conv_flops = fl['fwd'] + fl['dgrad']
         conv_ms = t['fwd'] + t['dgrad']
         ach = conv_flops / (conv_ms * 1e-3) / 1e12
         roof = {'kernel': 'conv_halo_kernel (tcgen05 implicit GEMM with shared-memory halo reuse: forward + data-gradient launches of the 22 U-Net layers)', 'bound': 'tensor',
-                'achieved': ach, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sust'], 'traffic': None,
+                'achieved': ach, 'peak': pk['tf_sust'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf_sust'], 'traffic': traffic,
+                'traffic_source': 'profiles/r01_conv_halo_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu, 44 launches of one step)',
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (%s)' % pk['src'],
                 'flops_per_step': conv_flops, 'launches_per_step': nl['fwd'] + nl['dgrad'], 'avg_launch_us': conv_ms * 1e3 / (nl['fwd'] + nl['dgrad']),
                 'kernel_ms_per_step': conv_ms, 'share_of_step': conv_ms / (ms / args.steps),
