@@ -542,11 +542,14 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     if (b_stages > 8) b_stages = 8;
     if (b_stages < 2) return 0;
     pl->halo_T = T;
-    // cluster size: weights are the dominant L2->SM stream; share them across `cs` CTAs working on adjacent M tiles
+    // cluster size: `cs` CTAs working on adjacent M tiles can share the weight stream by TMA multicast.  Measured over the 22
+    // layers (tools/perf_unet.py, RNR_CONV_CLUSTER = 1 / 2 / 4): forward 0.794 / 0.821 / 1.076 ms, data gradient 0.850 / 0.884 /
+    // 1.203 ms -- at this size multicast does not reduce L2 traffic enough to pay for the cluster launch, the cluster barriers
+    // and the lock-step B ring, so the default is no cluster.
     int cs = 1;
     {
         const char* ce = getenv("RNR_CONV_CLUSTER");
-        const int want = ce ? atoi(ce) : 2;
+        const int want = ce ? atoi(ce) : 1;
         for (int c = want; c >= 2; c >>= 1)
             if ((bn / c) % 8 == 0 && bn % c == 0 && p.tiles_m >= 2 * c) { cs = c; break; }
     }
