@@ -177,6 +177,37 @@ def gen_raster():
     return out
 
 
+def gen_geometry(ref):
+    """render.get_TBN_map (render.py:124-168), camera.get_view_dir_map (camera.py:5-32) and network.LightingLP (network.py:631-699,
+    construction: cv2.resize INTER_AREA + bilinear sampling of the probes at the light directions) run by the real reference."""
+    g = torch.Generator().manual_seed(5)
+    out = {}
+    N, H, W, nf = 2, 9, 11, 40
+    faces_v = torch.randn(nf, 3, 3, generator=g)
+    faces_vt = torch.rand(nf, 3, 2, generator=g)
+    # orient every face's texture triangle so that the reference's clamp(min=1e-8) on the uv determinant is not the decisive term
+    det = (faces_vt[:, 1, 0] - faces_vt[:, 0, 0]) * (faces_vt[:, 2, 1] - faces_vt[:, 0, 1]) - \
+          (faces_vt[:, 2, 0] - faces_vt[:, 0, 0]) * (faces_vt[:, 1, 1] - faces_vt[:, 0, 1])
+    flip = det < 0
+    faces_vt[flip] = faces_vt[flip][:, [0, 2, 1]]
+    faces_v[flip] = faces_v[flip][:, [0, 2, 1]]
+    normal = torch.randn(N, H, W, 3, generator=g)
+    normal[0, 0, :3] = 0.0                                    # uncovered pixels: zero normal -> zero TBN
+    fidx = torch.randint(0, nf, (N, H, W), generator=g).int()
+    out.update(tbn_faces_v=faces_v, tbn_faces_vt=faces_vt, tbn_normal=normal, tbn_fidx=fidx,
+               tbn_out=ref.render.get_TBN_map(normal.clone(), fidx, faces_v, faces_vt))
+    K = torch.tensor([[[14.0, 0, 5.5], [0, 13.0, 4.5], [0, 0, 1]], [[20.0, 0.3, 6.0], [0, 21.0, 4.0], [0, 0, 1]]])
+    R = torch.linalg.qr(torch.randn(2, 3, 3, generator=g))[0]
+    vd, vdc = ref.camera.get_view_dir_map((H, W), torch.inverse(K), R.transpose(1, 2).contiguous())
+    out.update(vd_Kinv=torch.inverse(K), vd_Rinv=R.transpose(1, 2).contiguous(), vd_out=vd, vd_cam=vdc)
+    l_dir = torch.nn.functional.normalize(torch.randn(3, 64, generator=g), dim=0)
+    probes = [{'lp_img': torch.rand(1, 3, 30, 60, generator=g) * 4}, {'lp_img': torch.rand(1, 3, 25, 50, generator=g)}]
+    lp = ref.network.LightingLP(l_dir, lp_dataloader=probes, lp_img_h=20, lp_img_w=40)
+    out.update(lp_l_dir=l_dir, lp_probe0=probes[0]['lp_img'], lp_probe1=probes[1]['lp_img'], lp_l_samples=lp.l_samples.data,
+               lp_lps=lp.lps, lp_uv=lp.l_samples_uv)
+    return out
+
+
 def gen_gcn(ref):
     """network.DenseDeepGCN (network.py:256-315) at a small size, training mode (batch-statistic BN, spectral-norm power
     iteration), stochastic dilation off so that the run is deterministic.  The state dict is captured BEFORE the forward."""
@@ -200,10 +231,11 @@ def gen_gcn(ref):
 def main():
     ref = import_reference()
     np.savez_compressed(os.path.join(HERE, 'gcn_small.npz'), **_np(gen_gcn(ref)))
+    np.savez_compressed(os.path.join(HERE, 'geometry.npz'), **_np(gen_geometry(ref)))
     np.savez_compressed(os.path.join(HERE, 'pixel_ops.npz'), **_np(gen_pixel_ops(ref)))
     np.savez_compressed(os.path.join(HERE, 'unet_small.npz'), **_np(gen_unet(ref)))
     np.savez_compressed(os.path.join(HERE, 'raster.npz'), **_np(gen_raster()))
-    for f in ('pixel_ops.npz', 'unet_small.npz', 'raster.npz', 'gcn_small.npz'):
+    for f in ('pixel_ops.npz', 'unet_small.npz', 'raster.npz', 'gcn_small.npz', 'geometry.npz'):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, 'KiB')
 
 
