@@ -1,0 +1,41 @@
+"""Host-side accounting of the U-Net (no GPU): the live-layer table the engine executes and the FLOP counts bench.py's roofline
+uses must match SURVEY.md Appendix A / section 8d (22 live layers; RNR 428.7 GFLOP forward per 512^2 view, DNR-16 553.6)."""
+import pytest
+
+torch = pytest.importorskip('torch')
+
+
+def _specs(in_ch, out_ch, nf0, H=512):
+    from relightable_nr_b200.engine.unet import unet_layer_specs
+    return unet_layer_specs(in_ch, out_ch, nf0, 5, 8 * nf0, H, H)
+
+
+def _gflop(specs):
+    from relightable_nr_b200.engine.unet import UNetEngine
+    return sum(UNetEngine.layer_flops(sp, 1) for sp in specs) / 1e9
+
+
+def test_rnr_layer_table_and_flops():
+    specs = _specs(108, 78, 64)
+    assert len(specs) == 22
+    kinds = [sp.kind for sp in specs]
+    assert kinds.count('ct') == 5 and kinds.count('c4s2') == 5 and kinds.count('c3') == 12
+    assert specs[0].name == 'in' and specs[-1].name == 'out' and specs[-1].src == ['x0', 'y0']
+    assert [sp.cout for sp in specs[:11]] == [64, 64, 128, 128, 256, 256, 512, 512, 512, 512, 512]
+    # innermost block has no BatchNorm but biases; the last layer has a bias and no activation
+    inner = [sp for sp in specs if sp.name.startswith('b4.')]
+    assert all(sp.bn_key is None and sp.b_key is not None for sp in inner)
+    assert specs[-1].bn_key is None and specs[-1].slope is None
+    assert abs(_gflop(specs) - 428.7) < 0.1
+    # fwd + dgrad (first layer: 24 of 108 input channels) + wgrad
+    f = _gflop(specs)
+    first = 2.0 * 512 * 512 * 108 * 64 * 9 / 1e9
+    assert abs((3 * f - first * 84 / 108) - 1260.7) < 0.5
+
+
+def test_dnr_flops():
+    assert abs(_gflop(_specs(16, 3, 80)) - 553.6) < 0.1
+
+
+def test_quarter_resolution_scales_flops_by_four():
+    assert abs(_gflop(_specs(108, 78, 64, 256)) * 4 - _gflop(_specs(108, 78, 64))) < 1e-6
