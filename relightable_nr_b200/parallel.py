@@ -48,3 +48,134 @@ def allreduce_flat_mean_(flat, group=None, async_op=False):
     if not async_op:
         flat.mul_(1.0 / dist.get_world_size(group))
     return work
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Data parallelism for the reference's UNCHANGED single-process training scripts: the launcher
+# (relightable_nr_b200/run.py --dp) starts one process per GPU and calls install_script_hooks() before runpy.  train_rnr.py has
+# no sampler, no collective and no rank logic, so everything is injected from outside:
+#   * training DataLoaders (shuffle=True) get a rank-strided sampler with a shared seed -> every rank draws a different view of
+#     the same permutation (1 view per GPU per step, the script's own constraint);
+#   * every Parameter that receives a gradient is averaged over the ranks: post-accumulate-grad hooks enqueue an asynchronous
+#     all-reduce per parameter bucket while loss.backward() (train_rnr.py:618) is still running, and a global optimizer-step
+#     pre-hook waits for them and scales by 1/world before optimizerG.step() (:622);
+#   * ranks > 0 get a no-op SummaryWriter and do not write checkpoints.
+# ----------------------------------------------------------------------------------------------------------------------
+class RankStridedSampler(torch.utils.data.Sampler):
+    """Indices rank, rank + world, ... of one permutation shared by all ranks (seed + epoch); every rank gets the same count."""
+
+    def __init__(self, data_source, rank, world, shuffle=True, seed=0):
+        self.n, self.rank, self.world, self.shuffle, self.seed, self.epoch = len(data_source), rank, world, shuffle, seed, 0
+
+    def __iter__(self):
+        if self.shuffle:
+            g = torch.Generator()
+            g.manual_seed(self.seed + self.epoch)
+            order = torch.randperm(self.n, generator=g).tolist()
+        else:
+            order = list(range(self.n))
+        self.epoch += 1
+        per = -(-self.n // self.world)
+        order = (order + order[:per * self.world - self.n])[:per * self.world]       # pad by wrapping, like DistributedSampler
+        return iter(order[self.rank::self.world])
+
+    def __len__(self):
+        return -(-self.n // self.world)
+
+
+class _GradAverager:
+    """Bucketed asynchronous gradient all-reduce driven by autograd hooks."""
+
+    def __init__(self, bucket_bytes=64 << 20, group=None):
+        self.bucket_bytes, self.group = bucket_bytes, group
+        self.pending = []          # [(work, flat, [grads])]
+        self.cur, self.cur_bytes = [], 0
+        self.hooked = set()
+
+    def attach(self, params):
+        for p in params:
+            if p.requires_grad and id(p) not in self.hooked:
+                self.hooked.add(id(p))
+                p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def _on_grad(self, p):
+        if p.grad is None:
+            return
+        self.cur.append(p.grad)
+        self.cur_bytes += p.grad.numel() * p.grad.element_size()
+        if self.cur_bytes >= self.bucket_bytes:
+            self._flush()
+
+    def _flush(self):
+        if not self.cur:
+            return
+        grads, self.cur, self.cur_bytes = self.cur, [], 0
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append((work, flat, grads))
+
+    def finish(self):
+        """Wait for every bucket, scale by 1/world and scatter back into the .grad tensors (called before optimizer.step())."""
+        self._flush()
+        world = dist.get_world_size(self.group)
+        for work, flat, grads in self.pending:
+            work.wait()
+            flat.mul_(1.0 / world)
+            o = 0
+            for g in grads:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+        self.pending = []
+
+
+def install_script_hooks(rank=None, world=None, seed=0, bucket_bytes=64 << 20):
+    """Make an unchanged single-process training script data-parallel (see above).  Requires an initialised process group.
+    Returns the gradient averager (its ``attach`` is applied automatically to the parameters of every optimizer created later)."""
+    import torch.optim
+    import torch.utils.data as tud
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    avg = _GradAverager(bucket_bytes)
+    if getattr(tud.DataLoader, '__rnr_dp__', False):
+        return avg
+    orig_loader = tud.DataLoader
+
+    class DataLoader(orig_loader):
+        __rnr_dp__ = True
+
+        def __init__(self, dataset, *a, **k):
+            shuffle = k.get('shuffle', a[1] if len(a) > 1 else False)
+            if shuffle and k.get('sampler') is None and k.get('batch_sampler') is None and world > 1:
+                k['sampler'] = RankStridedSampler(dataset, rank, world, shuffle=True, seed=seed)
+                k['shuffle'] = False
+                a = a[:1] + (False,) + a[2:] if len(a) > 1 else a
+            super().__init__(dataset, *a, **k)
+
+    tud.DataLoader = DataLoader
+    torch.utils.data.DataLoader = DataLoader
+    # parameters are discovered when the script builds its optimizer (train_rnr.py:376): hook them there
+    orig_init = torch.optim.Optimizer.__init__
+
+    def opt_init(self, params, defaults):
+        orig_init(self, params, defaults)
+        for grp in self.param_groups:
+            avg.attach(grp['params'])
+
+    torch.optim.Optimizer.__init__ = opt_init
+    from torch.optim.optimizer import register_optimizer_step_pre_hook
+    register_optimizer_step_pre_hook(lambda opt, args, kwargs: avg.finish())
+    if rank != 0:
+        import sys
+        import types
+        null = types.ModuleType('tensorboardX')
+
+        class SummaryWriter:
+            def __init__(self, *a, **k):
+                pass
+
+            def __getattr__(self, name):
+                return lambda *a, **k: None
+
+        null.SummaryWriter = SummaryWriter
+        sys.modules['tensorboardX'] = null
+    return avg

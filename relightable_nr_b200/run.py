@@ -2,6 +2,7 @@
 on top of the B200 drop-in modules (SURVEY.md 8b "How the unchanged scripts bind to the replacement"):
 
     python -m relightable_nr_b200.run /path/to/relightable-nr/train_rnr.py --data_root ... --gpu_id 0
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 -m relightable_nr_b200.run /path/to/train_rnr.py ... --gpu_id 0   # data parallel
 
 The scripts do plain top-level imports (``import network``, ``import neural_renderer as nr``, train_rnr.py:14-24) and Python
 puts the script's own directory first on ``sys.path``, so the drop-ins are registered in ``sys.modules`` BEFORE the script
@@ -116,14 +117,50 @@ def main(argv=None):
     script = os.path.abspath(argv[0])
     if not os.path.isfile(script):
         raise SystemExit('relightable_nr_b200.run: no such script: %s' % script)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:
+        _enter_data_parallel()
     install_shims()
     from . import dropin
     installed = dropin.install()
     print('relightable_nr_b200.run: drop-in modules registered: %s' % ', '.join(installed), file=sys.stderr)
     sys.argv = [script] + argv[1:]
     sys.path.insert(0, os.path.dirname(script))          # dataio / data_util / util / metric: the reference's own files
+    if world > 1 and int(os.environ.get('RANK', '0')) != 0:
+        _mute_checkpoints()
     runpy.run_path(script, run_name='__main__')
     return 0
+
+
+def _enter_data_parallel():
+    """Launched by torchrun (one process per GPU): pin this process to its GPU *before* the script's own
+    ``os.environ["CUDA_VISIBLE_DEVICES"] = opt.gpu_id`` (train_rnr.py:148-150) can matter -- CUDA is initialised here, so that
+    later write is inert and the script's ``cuda:0`` (pass ``--gpu_id 0``) is this rank's device -- then join the process group and
+    install the sampler / gradient-averaging hooks (relightable_nr_b200/parallel.py::install_script_hooks, SURVEY.md 8e)."""
+    local = os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0'))
+    os.environ['CUDA_VISIBLE_DEVICES'] = local
+    import torch
+    import torch.distributed as dist
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.init()
+        torch.cuda.set_device(0)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl' if cuda else 'gloo')
+    from . import parallel
+    parallel.install_script_hooks(seed=int(os.environ.get('RNR_DP_SEED', '0')))
+    print('relightable_nr_b200.run: data parallel, rank %d of %d (%s)' % (dist.get_rank(), dist.get_world_size(),
+                                                                          'nccl' if cuda else 'gloo'), file=sys.stderr)
+
+
+def _mute_checkpoints():
+    """Only rank 0 writes checkpoints (util.custom_save, util.py:33-47); the replicas are identical anyway."""
+    try:
+        util = importlib.import_module('util')
+        if hasattr(util, 'custom_save'):
+            util.custom_save = lambda *a, **k: None
+    except Exception:
+        pass
 
 
 if __name__ == '__main__':

@@ -31,3 +31,34 @@ def test_unchanged_script_starts_under_the_launcher(script):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert 'usage: %s' % script in r.stdout and '--gpu_id' in r.stdout and 'drop-in modules registered' in r.stderr
+
+
+TOY_SCRIPT = """
+import os, torch
+from torch.utils.data import DataLoader, TensorDataset
+torch.manual_seed(0)
+loader = DataLoader(TensorDataset(torch.arange(8, dtype=torch.float32).view(8, 1)), batch_size=1, shuffle=True)
+model = torch.nn.Linear(1, 3)
+opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+seen = []
+for (x,) in loader:
+    seen.append(int(x.item())); opt.zero_grad(); (model(x) ** 2).sum().backward(); opt.step()
+torch.save({'seen': seen, 'w': model.weight.detach().clone()}, os.path.join(r'%s', 'out_' + os.environ.get('RANK', '0') + '.pt'))
+"""
+
+
+def test_launcher_data_parallel_mode(tmp_path):
+    """torchrun + the launcher turn a plain single-process training script into a 2-rank data-parallel run (gloo on CPU):
+    disjoint samples, replicas in sync.  The script below has no rank logic at all."""
+    script = tmp_path / 'toy_train.py'
+    script.write_text(TOY_SCRIPT % str(tmp_path))
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29533', '-m', 'relightable_nr_b200.run', str(script)], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import torch
+    a = torch.load(str(tmp_path / 'out_0.pt'))
+    b = torch.load(str(tmp_path / 'out_1.pt'))
+    assert sorted(a['seen'] + b['seen']) == list(range(8)) and len(a['seen']) == 4
+    assert torch.allclose(a['w'], b['w'], atol=1e-6)
