@@ -128,6 +128,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     if (cs > 1) cluster_sync_all();          // peers' barriers must exist before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (dbg & 256) {
+        // programmatic dependent launch (RNR_PDL=1, experimental): this grid may have been scheduled while its predecessor in the
+        // stream was still running -- everything above (barrier init, TMEM allocation, table loads of constant plan data) overlaps
+        // the predecessor's tail; no activation / weight byte is touched before the predecessor has completed and flushed
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     if (warp == kProducerWarp) {
         // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
@@ -609,6 +616,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
         attr_set = true;
     }
     { const char* d = getenv("RNR_CONV_DBG"); pl->dbg = d ? atoi(d) : 0; }
+    { const char* d = getenv("RNR_PDL"); if (d && atoi(d) != 0) pl->dbg |= 256; }
     pl->halo = 1;
     return 0;
 }
@@ -635,13 +643,18 @@ int rnr_conv_halo_run(const rnr_conv_plan* pl, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = pl->smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pl->halo_cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (pl->dbg & 256) {
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+    }
     RNR_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel, maps, pl->p, (const HaloGroup*)pl->d_groups, pl->n_groups,
                                  (const HaloTap*)pl->d_taps, pl->n_taps, pl->bn, pl->tiles_n, pl->stages, pl->halo_a_stage,
                                  pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc));
