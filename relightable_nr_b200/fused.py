@@ -35,6 +35,11 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _cf(t):
+    """fp32 contiguous view of a per-view map (a no-op for the maps ViewDataset / synthetic_view produce)."""
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
 class FusedRNRStep:
     """Fused execution of one RNRPipeline iteration.  Built lazily per (N, H, W); owns only scratch buffers."""
 
@@ -123,7 +128,7 @@ class FusedRNRStep:
         eng = self.eng
         raw = eng.layers['out'].raw
         _lib.check(self.L.rnr_tail_fwd(raw.data_ptr(), eng.out_ld, self.rays_uv.data_ptr(), self.albedo.data_ptr(), lp.data_ptr(),
-                                       self.Hl, self.Wl, view['alpha_map'].data_ptr(), view['img_gt'].data_ptr(), self.Rs, self.Rd,
+                                       self.Hl, self.Wl, _cf(view['alpha_map']).data_ptr(), _cf(view['img_gt']).data_ptr(), self.Rs, self.Rd,
                                        eng.N, eng.H, eng.W, self.CROP, self.final.data_ptr(), self.aux.data_ptr(),
                                        self.sums.data_ptr(), _s()), 'rnr_tail_fwd')
 
@@ -211,7 +216,7 @@ class FusedRNRStep:
         sp = eng.specs[-1]
         raw = eng.layers['out'].raw
         _lib.check(L.rnr_tail_bwd(raw.data_ptr(), eng.out_ld, self.rays_uv.data_ptr(), self.albedo.data_ptr(), lp.data_ptr(),
-                                  self.Hl, self.Wl, view['alpha_map'].data_ptr(), view['img_gt'].data_ptr(), self.Rs, self.Rd,
+                                  self.Hl, self.Wl, _cf(view['alpha_map']).data_ptr(), _cf(view['img_gt']).data_ptr(), self.Rs, self.Rd,
                                   N, H, W, self.CROP, self.aux.data_ptr(), self.sums.data_ptr(), 1.0, float(p.w['rays_lt_chrom']),
                                   eng.gz['out'].ptr, eng.out_ld, eng.grad_view(sp.b_key).data_ptr(), self.g_alb.data_ptr(),
                                   self.g_lp4.data_ptr(), _s()), 'rnr_tail_bwd')
@@ -241,7 +246,7 @@ class FusedRNRStep:
         tm = p.texture_mapper
         gp = (C.c_void_p * len(self.tex_grads))(*[g.data_ptr() for g in self.tex_grads])
         _lib.check(L.rnr_texmap_bwd(C.cast(gp, _pp), C.cast(self._tex_sizes, _ip), len(self.tex_grads), self.C,
-                                    view['uv_map'].data_ptr(), view['sh_basis_map'].data_ptr(), 6, gi.data_ptr(), N, H, W, _s()),
+                                    _cf(view['uv_map']).data_ptr(), _cf(view['sh_basis_map']).data_ptr(), 6, gi.data_ptr(), N, H, W, _s()),
                    'rnr_texmap_bwd')
         # envmap gradient -> SH coefficients: grad_coeff += basis_recon^T g_lp   (a17-bwd)
         lm = p.lighting_model
