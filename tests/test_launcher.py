@@ -52,9 +52,14 @@ def test_launcher_data_parallel_mode(tmp_path):
     disjoint samples, replicas in sync.  The script below has no rank logic at all."""
     script = tmp_path / 'toy_train.py'
     script.write_text(TOY_SCRIPT % str(tmp_path))
+    import socket
+    sock = socket.socket()
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+    sock.close()
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
-                        '--master-port', '29533', '-m', 'relightable_nr_b200.run', str(script)], cwd=ROOT, env=env,
+                        '--master-port', str(port), '-m', 'relightable_nr_b200.run', str(script)], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     import torch
