@@ -57,17 +57,31 @@ def dnr_forward(textures, unet_sd, view, drop=None):
     return (rendering_net_forward(unet_sd, neural_img, drop=drop) * 0.5 + 0.5) * 2.0
 
 
+def sh_tables(l_dir, lmax, lp_hw):
+    """LightingSH's two basis tables (network.py:557, 577-581) from the ORACLE's evaluate_sh_basis (scipy-pinned,
+    tests/test_oracle_golden.py): ``l_dir`` [3,S] float32 -> (basis_val [S,B], basis_val_recon [H*W,B]) float32."""
+    import numpy as np
+    basis_val = torch.from_numpy(P.evaluate_sh_basis(lmax, l_dir.t().contiguous().numpy())).float()
+    h, w = lp_hw
+    vv, uu = torch.meshgrid(torch.arange(h, dtype=torch.float32) / (h - 1), torch.arange(w, dtype=torch.float32) / (w - 1), indexing='ij')
+    grid_dir = P.spherical_mapping_inv(torch.stack((uu, vv)).flatten(1)).t().contiguous()
+    return basis_val, torch.from_numpy(P.evaluate_sh_basis(lmax, grid_dir.numpy())).float()
+
+
 def state_from_pipeline(pipe):
     """CPU copies of everything the oracle needs from a relightable_nr_b200.pipeline.RNRPipeline (duck-typed: the
-    oracle never imports the product)."""
+    oracle never imports the product).  Learnable state and inputs are copied; the SH basis tables are NOT taken from the
+    pipeline under test -- they are rebuilt by the oracle from the light directions (``pipe.l_dir``)."""
     cpu = lambda t: t.detach().cpu().clone()
     lm = pipe.lighting_model
+    lp_hw = (int(lm.lp_recon_h), int(lm.lp_recon_w))
+    basis_val, basis_val_recon = sh_tables(cpu(pipe.l_dir).float(), int(lm.lmax), lp_hw)
     return dict(
         textures=[cpu(t) for t in pipe.texture_mapper.textures],
         tex_init=cpu(pipe.texture_mapper.tex_flatten_mipmap_init),
         unet_sd={k: cpu(v) for k, v in pipe.render_net.state_dict().items()},
         coeff=cpu(lm.coeff[pipe.lighting_idx]),
-        basis_val=cpu(lm.basis_val), basis_val_recon=cpu(lm.basis_val_recon), lp_hw=(int(lm.lp_recon_h), int(lm.lp_recon_w)),
+        basis_val=basis_val, basis_val_recon=basis_val_recon, lp_hw=lp_hw,
         pivots_s=cpu(pipe.ray_sampler.pivots_dir), pivots_d=cpu(pipe.ray_sampler_diffuse.pivots_dir),
         l_init=cpu(pipe.l_samples_init), l_mask=cpu(pipe.l_samples_init_mask), w=dict(pipe.w),
     )
@@ -95,3 +109,28 @@ def rnr_step(state, view, requires_grad=True, drop=None):
             if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None:
                 grads['unet/' + k] = v.grad
     return loss.detach(), final.detach(), grads
+
+
+def rnr_trajectory(state, views, lr=1e-3):
+    """``len(views)`` consecutive iterations of train_rnr.py:490-623 on CPU in fp32: forward, the four losses, backward and
+    ``torch.optim.Adam(lr)`` (train_rnr.py:376) over textures + SH coefficients + U-Net parameters, BatchNorm in batch-statistic
+    mode, dropout off.  Returns (losses, final state tensors) -- the reference trajectory a GPU run must follow."""
+    tex = [t.clone().requires_grad_(True) for t in state['textures']]
+    coeff = state['coeff'].clone().requires_grad_(True)
+    sd = {k: (v.clone().requires_grad_(True) if (v.dtype.is_floating_point and 'running' not in k and v.dim() > 0) else v)
+          for k, v in state['unet_sd'].items()}
+    leaves = tex + [coeff] + [v for v in sd.values() if isinstance(v, torch.Tensor) and v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=lr)
+    losses = []
+    for view in views:
+        view = {k: v.detach().cpu() for k, v in view.items()}
+        opt.zero_grad(set_to_none=True)
+        final, rays_lt, alpha_map = rnr_forward(tex, sd, coeff, state['basis_val_recon'], state['lp_hw'], state['pivots_s'],
+                                                state['pivots_d'], view)
+        loss = rnr_losses(tex, state['tex_init'], coeff, state['basis_val'], state['l_init'], state['l_mask'], view, final, rays_lt,
+                          alpha_map, state['w'])
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    return losses, dict(textures=[t.detach() for t in tex], coeff=coeff.detach(),
+                        unet_sd={k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in sd.items()})

@@ -19,6 +19,9 @@ import torch.nn.functional as F
 
 
 def _bn(x, sd, key, eps=1e-5):
+    if _Q.bn_eval:      # nn.BatchNorm2d.eval(): running statistics (only reached by module.eval() without set_bn_train)
+        return F.batch_norm(x, sd[key + '.running_mean'], sd[key + '.running_var'], sd[key + '.weight'], sd[key + '.bias'],
+                            training=False, eps=eps)
     return F.batch_norm(x, None, None, sd[key + '.weight'], sd[key + '.bias'], training=True, momentum=0.0, eps=eps)
 
 
@@ -38,7 +41,7 @@ class _Q:
     agree with the engine's, so backward parity can be checked much tighter than against pure fp32
     (where ~0.1% of gates flip and alone cause a few % relative-L2 gradient difference)."""
     on = False
-
+    bn_eval = False
 
     gates = None     # optional {layer name: bool mask [N,C,H,W]} of (pre-activation > 0) taken from the engine
 
@@ -98,16 +101,18 @@ def _block(x, sd, pfx, i, num_down, drop, acts):
     return torch.cat([x, y], 1)
 
 
-def unet_forward(sd, x, num_down=5, drop=None, prefix='', return_acts=False, q16=False, gates=None):
+def unet_forward(sd, x, num_down=5, drop=None, prefix='', return_acts=False, q16=False, gates=None, bn_eval=False):
     """sd: state_dict of the reference ``Unet`` (keys relative to ``prefix``).  Returns pre-tanh output.
     q16=True emulates the engine's fp16 storage of weights/activations (see _Q)."""
     _Q.on = bool(q16)
     _Q.gates = gates
+    _Q.bn_eval = bool(bn_eval)
     try:
         return _unet_forward(sd, x, num_down, drop, prefix, return_acts)
     finally:
         _Q.on = False
         _Q.gates = None
+        _Q.bn_eval = False
 
 
 def _unet_forward(sd, x, num_down, drop, prefix, return_acts):

@@ -579,12 +579,10 @@ extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const voi
             lw = 0; while ((1 << lw) < W) lw++;
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
+    });
     RNR_REQUIRE(smem <= 160 * 1024, "rnr_bn_bwd_reduce_fin: C=%d needs %zu bytes of shared memory", C, smem);
     if (nsrc == 1)
         bn_bwd_reduce_fin_kernel<1><<<T, threads, smem, (cudaStream_t)stream>>>(

@@ -39,6 +39,20 @@ void rnr_count_launch(void);          // every kernel launch of the library is c
         }                                                                                 \
     } while (0)
 
+// Runs the statements once per CUDA device (function attributes such as MaxDynamicSharedMemorySize are per device; a
+// process-wide flag would leave a second GPU of the same process without the opt-in).  Racing threads may both run it: the
+// attribute calls are idempotent.
+#define RNR_ONCE_PER_DEVICE(...)                                                          \
+    do {                                                                                  \
+        static unsigned char _rnr_done[64] = {0};                                         \
+        int _rnr_dev = 0;                                                                 \
+        RNR_CHECK(cudaGetDevice(&_rnr_dev));                                              \
+        if (_rnr_dev < 0 || _rnr_dev >= 64 || !_rnr_done[_rnr_dev]) {                     \
+            __VA_ARGS__;                                                                  \
+            if (_rnr_dev >= 0 && _rnr_dev < 64) _rnr_done[_rnr_dev] = 1;                  \
+        }                                                                                 \
+    } while (0)
+
 static inline int rnr_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int rnr_dtype_size(int dt) { return dt == RNR_F32 ? 4 : 2; }
 

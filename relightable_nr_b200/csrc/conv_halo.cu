@@ -610,11 +610,9 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     RNR_CHECK(cudaMemcpy(pl->d_taps, taps.data(), sizeof(HaloTap) * taps.size(), cudaMemcpyHostToDevice));
     pl->n_groups = n_groups;
     pl->n_taps = (int)taps.size();
-    static bool attr_set = false;
-    if (!attr_set) {
+    RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    });
     { const char* d = getenv("RNR_CONV_DBG"); pl->dbg = d ? atoi(d) : 0; }
     { const char* d = getenv("RNR_PDL"); if (d && atoi(d) != 0) pl->dbg |= 256; }
     pl->halo = 1;

@@ -291,11 +291,9 @@ int rnr_conv_tc_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* prob) {
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         RNR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(Wmat) failed with CUresult %d", (int)r);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    });
     return 0;
 }
 

@@ -496,8 +496,7 @@ extern "C" int rnr_head_fwd(const float* const* tex, const int* sizes, int n_lev
     q.act = (__half*)act; q.act_b = (__nv_bfloat16*)act_bf16; q.Cpad = Cpad;
     q.rays_uv = rays_uv; q.albedo = albedo; q.N = N; q.H = H; q.W = W;
     const size_t smem = ((size_t)kHeadPx * Cpad + kHeadPx * 2 * kMaxRays + kHeadPx * 13 + 6 * kMaxRays) * sizeof(float);
-    static bool attr = false;
-    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+    RNR_ONCE_PER_DEVICE({ RNR_CHECK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); });
     RNR_REQUIRE(smem <= 64 * 1024, "head: shared memory %zu too large", smem);
     const int64_t P = (int64_t)N * H * W;
     head_fwd_kernel<<<rnr_cdiv(P, kHeadPx), kHeadThreads, smem, (cudaStream_t)stream>>>(q);
@@ -533,14 +532,12 @@ extern "C" int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, c
     if (rc) return rc;
     RNR_REQUIRE(final_img, "tail: null output");
     const size_t smem = (size_t)kTailPx * (2 * raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd) + 4) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         // the kernel is bound by the envmap texel gathers (4 x 16 B per ray, L1 misses go to L2 one sector at a time): cap the
         // shared-memory carve-out so that the rest of the 228 KB stays L1 for the 2 MB envmap's working set
         RNR_CHECK(cudaFuncSetAttribute(tail_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, tail_carveout()));
-        attr = true;
-    }
+    });
     int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
     if (blocks > 148 * 8) blocks = 148 * 8;
     tail_fwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(q);
@@ -562,12 +559,10 @@ extern "C" int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, c
     qq.w_l1 = w_l1; qq.w_chrom = w_chrom; qq.gz = (__nv_bfloat16*)gz; qq.ldg = ldg; qq.dbias = dbias; qq.g_alb = g_alb;
     qq.g_lp4 = (float4*)g_lp4;
     const size_t smem = (size_t)kTailPx * (raw_pitch(Rs + Rd) + uv_pitch(Rs + Rd) + 12) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         RNR_CHECK(cudaFuncSetAttribute(tail_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, tail_carveout()));
-        attr = true;
-    }
+    });
     int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
     if (blocks > 148 * 8) blocks = 148 * 8;
     tail_bwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(qq);

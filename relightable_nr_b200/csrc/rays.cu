@@ -196,8 +196,7 @@ extern "C" int rnr_ray_sampler_fwd(const float* tbn, const float* vdt, const flo
                                    void* stream) {
     RNR_REQUIRE(R >= 1 && R <= RNR_MAX_RAYS, "ray sampler: 1..%d rays supported, got %d", RNR_MAX_RAYS, R);
     const size_t smem = (size_t)128 * 8 * R * sizeof(float);
-    static bool attr = false;
-    if (!attr) { RNR_CHECK(cudaFuncSetAttribute(ray_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 8 * RNR_MAX_RAYS * 4)); attr = true; }
+    RNR_ONCE_PER_DEVICE({ RNR_CHECK(cudaFuncSetAttribute(ray_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 8 * RNR_MAX_RAYS * 4)); });
     ray_sampler_kernel<<<rnr_cdiv(P, 128), 128, smem, (cudaStream_t)stream>>>(tbn, vdt, alpha, pivots, R, reflect, rays_dir, rays_uv,
                                                                             rays_dir_tangent, P);
     RNR_LAUNCH_CHECK();

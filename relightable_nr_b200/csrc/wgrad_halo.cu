@@ -361,11 +361,9 @@ int rnr_wgrad_halo_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) 
     pl->halo_nbuf = nbuf;
     pl->smem_bytes = stages * stage_bytes + 256 + 1024;
     pl->grid = pl->n_work < 148 ? pl->n_work : 148;
-    static bool attr_set = false;
-    if (!attr_set) {
+    RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    });
     pl->halo = 1;
     return 0;
 }

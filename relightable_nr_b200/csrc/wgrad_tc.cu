@@ -283,11 +283,9 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
     RNR_CHECK(cudaMemcpy(pl->d_work_tab, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
     pl->smem_bytes = kStages * kStageBytes + 256 + 1024;
     pl->grid = pl->n_work < 148 ? pl->n_work : 148;
-    static bool attr_set = false;
-    if (!attr_set) {
+    RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    });
     return 0;
 }
 

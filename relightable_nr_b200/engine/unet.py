@@ -742,6 +742,7 @@ class UNetEngine:
         L, s = self.L, self._stream()
         if not weights_ready:
             self.prepare_weights(backward=self.need_backward)
+        self.bn_training = bool(training)
         for sp in self.specs:
             st = self.layers[sp.name]
             t0 = self._mark()
@@ -752,10 +753,18 @@ class UNetEngine:
             if sp.dst == 'out':
                 continue
             N, Ho, Wo, Cc = self.N, sp.Ho, sp.Wo, sp.cout
-            if sp.bn_key is not None:
-                rm = rv = None
-                if training:
-                    rm, rv = self.buffers[sp.bn_key + '.running_mean'], self.buffers[sp.bn_key + '.running_var']
+            if sp.bn_key is not None and not training:
+                # nn.BatchNorm2d in eval(): normalise with the RUNNING statistics (scale = gamma / sqrt(running_var + eps),
+                # shift = beta - running_mean * scale); the batch sums of the conv epilogue are ignored and nothing is updated
+                rm, rv = self.buffers[sp.bn_key + '.running_mean'], self.buffers[sp.bn_key + '.running_var']
+                with torch.no_grad():
+                    torch.add(rv, eps, out=st.invstd).rsqrt_()
+                    st.mean.copy_(rm)
+                    torch.mul(self.params[sp.bn_key + '.weight'], st.invstd, out=st.scale)
+                    torch.addcmul(self.params[sp.bn_key + '.bias'], st.mean, st.scale, value=-1.0, out=st.shift)
+                shift = st.shift
+            elif sp.bn_key is not None:
+                rm, rv = self.buffers[sp.bn_key + '.running_mean'], self.buffers[sp.bn_key + '.running_var']
                 _lib.check(L.rnr_bn_finalize(st.stats.data_ptr(), st.n_stat_tiles, Cc, Cc, float(N * Ho * Wo),
                                              self.params[sp.bn_key + '.weight'].data_ptr(),
                                              self.params[sp.bn_key + '.bias'].data_ptr(), eps,
@@ -845,6 +854,9 @@ class UNetEngine:
         step: early all-reduce of ``wscratch``)."""
         L, s = self.L, self._stream()
         N = self.N
+        if not getattr(self, 'bn_training', True) and any(sp.bn_key for sp in self.specs):
+            raise NotImplementedError('backward through BatchNorm in eval() mode (running statistics) is not implemented: the '
+                                      'reference scripts always differentiate with BatchNorm in train() mode')
         for sp in reversed(self.specs):
             st = self.layers[sp.name]
             Ho, Wo, Cc = sp.Ho, sp.Wo, sp.cout

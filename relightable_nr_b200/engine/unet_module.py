@@ -144,6 +144,15 @@ class UnetRunner:
         bn_mod = unet.in_layer[1]
         drop_mod = unet.in_layer[3]
         training_bn = bool(bn_mod.training)
+        # the engine applies ONE BatchNorm mode and ONE Dropout2d (mode, p) to every live layer: refuse mixed settings rather
+        # than silently ignoring a per-module .eval() / a different p (the dead `fuse` branch is never executed)
+        for name, m in unet.named_modules():
+            if '.fuse' in name:
+                continue
+            if isinstance(m, torch.nn.BatchNorm2d) and bool(m.training) != training_bn:
+                raise NotImplementedError('Unet: BatchNorm2d modules are in mixed train()/eval() modes (%s)' % name)
+            if isinstance(m, torch.nn.Dropout2d) and (bool(m.training) != bool(drop_mod.training) or float(m.p) != float(drop_mod.p)):
+                raise NotImplementedError('Unet: Dropout2d modules differ in mode or p (%s)' % name)
         drop_masks = None
         if drop_mod.training and drop_mod.p > 0:
             p = float(drop_mod.p)

@@ -38,6 +38,10 @@ def _s():
 def _cuda_f32(t, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
         raise TypeError('%s must be a CUDA tensor (librnr_b200 has no CPU path)' % name)
+    if t.device.index != torch.cuda.current_device():
+        # kernels are launched on the CURRENT device's stream: a tensor living elsewhere would be dereferenced on the wrong GPU
+        raise RuntimeError('%s lives on %s but the current CUDA device is cuda:%d; wrap the call in torch.cuda.device(%s.device)'
+                           % (name, t.device, torch.cuda.current_device(), name))
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()

@@ -91,6 +91,7 @@ class _GradAverager:
         self.pending = []          # [(work, flat, [grads])]
         self.cur, self.cur_bytes = [], 0
         self.hooked = set()
+        self.checked = False       # bucket layout verified across ranks (first step only)
 
     def attach(self, params):
         for p in params:
@@ -118,6 +119,18 @@ class _GradAverager:
         """Wait for every bucket, scale by 1/world and scatter back into the .grad tensors (called before optimizer.step())."""
         self._flush()
         world = dist.get_world_size(self.group)
+        if not self.checked:
+            # every rank must have produced the same buckets in the same order, or the collectives above pair up wrongly /
+            # hang: compare (bucket count, total elements) across ranks once, on the first step
+            sig = torch.tensor([len(self.pending), sum(f.numel() for _, f, _ in self.pending)], dtype=torch.int64,
+                               device=self.pending[0][1].device if self.pending else 'cpu')
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+            if not torch.equal(lo, hi):
+                raise RuntimeError('data-parallel ranks produced different gradient buckets (min %s, max %s): every rank must '
+                                   'differentiate the same parameters in the same order' % (lo.tolist(), hi.tolist()))
+            self.checked = True
         for work, flat, grads in self.pending:
             work.wait()
             flat.mul_(1.0 / world)
@@ -126,6 +139,32 @@ class _GradAverager:
                 g.copy_(flat[o:o + g.numel()].view_as(g))
                 o += g.numel()
         self.pending = []
+
+
+def broadcast_params_(tensors, src=0, group=None):
+    """In-place broadcast of ``tensors`` (parameters or buffers) from rank ``src``, one flat bucket per dtype."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    by_dtype = {}
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.numel() > 0:
+            by_dtype.setdefault((t.dtype, t.device), []).append(t)
+    with torch.no_grad():
+        for ts in by_dtype.values():
+            flat = torch.cat([t.detach().reshape(-1) for t in ts])
+            dist.broadcast(flat, src=src, group=group)
+            o = 0
+            for t in ts:
+                t.detach().copy_(flat[o:o + t.numel()].view_as(t))
+                o += t.numel()
+
+
+def broadcast_module_state_(modules, src=0, group=None):
+    """Parameters AND buffers (BatchNorm running statistics, spectral-norm u / v, ...) of ``modules`` from rank ``src``."""
+    ts = []
+    for m in modules:
+        ts += [p for p in m.parameters()] + [b for b in m.buffers()]
+    broadcast_params_(ts, src, group)
 
 
 def install_script_hooks(rank=None, world=None, seed=0, bucket_bytes=64 << 20):
@@ -155,11 +194,21 @@ def install_script_hooks(rank=None, world=None, seed=0, bucket_bytes=64 << 20):
     torch.utils.data.DataLoader = DataLoader
     # parameters are discovered when the script builds its optimizer (train_rnr.py:376): hook them there
     orig_init = torch.optim.Optimizer.__init__
+    state = {'reseeded': False}
 
     def opt_init(self, params, defaults):
         orig_init(self, params, defaults)
         for grp in self.param_groups:
+            # the scripts never seed (train_rnr.py / train_dnr.py have no torch.manual_seed): every rank built its own random
+            # U-Net / GCN.  Replicas must start identical -- gradients are averaged and only rank 0 checkpoints -- so rank 0's
+            # parameters are broadcast to everyone the moment the script hands them to its optimizer (train_rnr.py:376).
+            broadcast_params_(grp['params'])
             avg.attach(grp['params'])
+        if not state['reseeded']:
+            # construction-time randomness was shared (the launcher seeds every rank alike); from here on each rank draws its
+            # own dropout masks / stochastic kNN dilation
+            state['reseeded'] = True
+            torch.manual_seed(1000003 * (seed + 1) + rank)
 
     torch.optim.Optimizer.__init__ = opt_init
     from torch.optim.optimizer import register_optimizer_step_pre_hook

@@ -73,11 +73,14 @@ class RNRPipeline:
 
     def __init__(self, device='cuda', img_size=512, texture_size=512, texture_num_ch=24, mipmap_level=4, nf0=64, sh_lmax=10,
                  num_l_samples=4096, lp_recon_h=256, lp_recon_w=512, lr=1e-3, seed=0, loss_weights=None, dropout=True,
-                 capturable=False):
+                 capturable=False, l_dir=None):
         self.device = torch.device(device)
         self.img_size = img_size
         torch.manual_seed(seed)
-        l_dir = fibonacci_sphere(num_l_samples)
+        # light directions [3, S]: the caller's (the reference loads sphere_samples_4096.mat, train_rnr.py:167-169) or a Fibonacci sphere
+        l_dir = fibonacci_sphere(num_l_samples) if l_dir is None else torch.as_tensor(l_dir, dtype=torch.float32)
+        num_l_samples = l_dir.shape[1]
+        self.l_dir = l_dir.clone()
         self.interpolater = _network.Interpolater()
         self.texture_mapper = _network.TextureMapper(texture_size, texture_num_ch, mipmap_level, apply_sh=True)
         g = torch.Generator().manual_seed(seed + 11)

@@ -124,9 +124,12 @@ def main(argv=None):
     from . import dropin
     installed = dropin.install()
     print('relightable_nr_b200.run: drop-in modules registered: %s' % ', '.join(installed), file=sys.stderr)
+    rank = int(os.environ.get('RANK', '0'))
+    if world > 1 and rank != 0:
+        argv = _per_rank_log_dir(argv, rank)
     sys.argv = [script] + argv[1:]
     sys.path.insert(0, os.path.dirname(script))          # dataio / data_util / util / metric: the reference's own files
-    if world > 1 and int(os.environ.get('RANK', '0')) != 0:
+    if world > 1 and rank != 0:
         _mute_checkpoints()
     runpy.run_path(script, run_name='__main__')
     return 0
@@ -148,9 +151,30 @@ def _enter_data_parallel():
     if not dist.is_initialized():
         dist.init_process_group('nccl' if cuda else 'gloo')
     from . import parallel
-    parallel.install_script_hooks(seed=int(os.environ.get('RNR_DP_SEED', '0')))
+    # identical construction-time randomness on every rank (buffers such as spectral-norm u / v and BatchNorm statistics start
+    # equal; the parameters are additionally broadcast from rank 0 when the optimizer is built)
+    seed = int(os.environ.get('RNR_DP_SEED', '0'))
+    import random
+    import numpy as np
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    parallel.install_script_hooks(seed=seed)
     print('relightable_nr_b200.run: data parallel, rank %d of %d (%s)' % (dist.get_rank(), dist.get_world_size(),
                                                                           'nccl' if cuda else 'gloo'), file=sys.stderr)
+
+
+def _per_rank_log_dir(argv, rank):
+    """Ranks > 0 still run the script's validation / image dumps (train_rnr.py:626-887): give each its own log directory so
+    they do not race on rank 0's files -- the scripts append ``_<exp_name>`` to the directory name (train_rnr.py:446-450)."""
+    argv = list(argv)
+    tag = 'rank%d' % rank
+    if '--exp_name' in argv[:-1]:
+        i = argv.index('--exp_name')
+        argv[i + 1] = (argv[i + 1] + '_' + tag) if argv[i + 1] else tag
+    else:
+        argv += ['--exp_name', tag]
+    return argv
 
 
 def _mute_checkpoints():

@@ -228,8 +228,17 @@ def gen_gcn(ref):
     return out
 
 
+def gen_sphere_samples():
+    """The reference's only in-tree data fixture: the 4096 quadrature directions every script loads
+    (train_rnr.py:167, test_rnr.py, precompute.py) -- stored as float32 [4096,3]."""
+    import scipy.io
+    from tests.golden.ref_import import REF
+    return {'sphere_samples': scipy.io.loadmat(os.path.join(REF, 'sphere_samples_4096.mat'))['sphere_samples'].astype(np.float32)}
+
+
 def main():
     ref = import_reference()
+    np.savez_compressed(os.path.join(HERE, 'sphere_samples_4096.npz'), **gen_sphere_samples())
     np.savez_compressed(os.path.join(HERE, 'gcn_small.npz'), **_np(gen_gcn(ref)))
     np.savez_compressed(os.path.join(HERE, 'geometry.npz'), **_np(gen_geometry(ref)))
     np.savez_compressed(os.path.join(HERE, 'pixel_ops.npz'), **_np(gen_pixel_ops(ref)))

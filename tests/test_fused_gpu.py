@@ -135,6 +135,38 @@ def test_fused_cuda_graph_step():
         assert abs(x - y) <= 2e-3 * max(1.0, abs(x)), (ref, got)
 
 
+@pytest.mark.parametrize('size,nf0', [(64, 16), (128, 16)])
+def test_fused_training_trajectory_follows_the_oracle(size, nf0):
+    """20 consecutive Adam iterations (3 views cycled, dropout off): the fused GPU step (fp16 activations, bf16 gradients) against
+    the CPU fp32 oracle running the SAME iterations with torch.optim.Adam (oracle.rnr_step.rnr_trajectory).  Gate: the loss
+    agrees within 1 % at EVERY step, and the accumulated parameter updates of the textures / SH coefficients point the same
+    way (cosine >= 0.9) -- the evidence that reduced-precision gradients train the same model."""
+    from oracle.rnr_step import rnr_trajectory, state_from_pipeline
+    from relightable_nr_b200.pipeline import synthetic_view
+    pipe = _pipe(img_size=size, nf0=nf0)
+    views = [synthetic_view(size, view_idx=i, device='cuda:0') for i in (2, 9, 4)]
+    seq = [views[i % 3] for i in range(20)]
+    state = state_from_pipeline(pipe)
+    got = [pipe.train_step(v, fused=True)[0].item() for v in seq]
+    torch.cuda.synchronize()
+    ref, end = rnr_trajectory(state, seq, lr=1e-3)
+    dev = [abs(a - b) / max(abs(b), 1e-12) for a, b in zip(got, ref)]
+    print('loss GPU   :', ' '.join('%.5f' % x for x in got))
+    print('loss oracle:', ' '.join('%.5f' % x for x in ref))
+    print('max relative deviation over 20 steps: %.3e' % max(dev))
+    assert ref[-1] < ref[0], 'the oracle trajectory must make progress for the comparison to mean anything'
+    assert max(dev) <= 1e-2, dev
+    for i, t in enumerate(pipe.texture_mapper.textures):
+        d_gpu = t.detach().cpu() - state['textures'][i]
+        d_ref = end['textures'][i] - state['textures'][i]
+        c = cosine(d_gpu, d_ref)
+        print('texture %d accumulated-update cosine %.4f' % (i, c))
+        assert c >= 0.9
+    c = cosine(pipe.lighting_model.coeff.detach()[0].cpu() - state['coeff'], end['coeff'] - state['coeff'])
+    print('SH coefficient accumulated-update cosine %.4f' % c)
+    assert c >= 0.9
+
+
 def test_full_size_fused_step_matches_oracle():
     """BASELINE.json's benchmark configuration itself (512x512 view, texture 512^2 x 24 ch x 4 mips, U-Net 108 -> 78 with nf0 = 64,
     26 rays, SH lmax 10 / 256x512 envmap): one fused training step on the GPU against the CPU fp32 oracle of train_rnr.py:512-608.

@@ -36,7 +36,7 @@ def test_unchanged_script_starts_under_the_launcher(script):
 TOY_SCRIPT = """
 import os, torch
 from torch.utils.data import DataLoader, TensorDataset
-torch.manual_seed(0)
+%s
 loader = DataLoader(TensorDataset(torch.arange(8, dtype=torch.float32).view(8, 1)), batch_size=1, shuffle=True)
 model = torch.nn.Linear(1, 3)
 opt = torch.optim.Adam(model.parameters(), lr=1e-2)
@@ -47,11 +47,15 @@ torch.save({'seen': seen, 'w': model.weight.detach().clone()}, os.path.join(r'%s
 """
 
 
-def test_launcher_data_parallel_mode(tmp_path):
+@pytest.mark.parametrize('seeding', ['torch.manual_seed(0)', '', "torch.manual_seed(7 + int(os.environ.get('RANK', '0')))"],
+                         ids=['seeded', 'unseeded', 'seeded-differently-per-rank'])
+def test_launcher_data_parallel_mode(tmp_path, seeding):
     """torchrun + the launcher turn a plain single-process training script into a 2-rank data-parallel run (gloo on CPU):
-    disjoint samples, replicas in sync.  The script below has no rank logic at all."""
+    disjoint samples, replicas in sync.  The script below has no rank logic at all.  The reference scripts never seed
+    (train_rnr.py has no torch.manual_seed), so the replicas must also end up identical when the script does not seed, or even
+    seeds every rank differently: the launcher broadcasts rank 0's parameters when the optimizer is built."""
     script = tmp_path / 'toy_train.py'
-    script.write_text(TOY_SCRIPT % str(tmp_path))
+    script.write_text(TOY_SCRIPT % (seeding, str(tmp_path)))
     import socket
     sock = socket.socket()
     sock.bind(('127.0.0.1', 0))

@@ -108,6 +108,55 @@ def test_dnr_step_matches_oracle():
     assert l1 < l0
 
 
+@pytest.mark.parametrize('size', [256, 512])
+def test_dnr_real_widths_match_oracle(size):
+    """DNR at its real size (train_dnr.py:31,38: nf0 = 80 -> 80/160/320/640 channels, 16-channel 512^2 x 4-level texture;
+    BASELINE.json configs[0] at 256^2 and configs[3] at 512^2): forward PSNR >= 50 dB and the gradients of one
+    train_dnr.py:240-262 iteration (masked, cropped L1) against the CPU oracle -- cosine >= 0.97 on every U-Net tensor and
+    texture level (fp16 activations / bf16 gradients vs the pure-fp32 oracle; the measured values are printed)."""
+    import torch.nn.functional as F
+    from oracle.rnr_step import dnr_forward
+    from relightable_nr_b200.pipeline import DNRPipeline, synthetic_view
+    pipe = DNRPipeline(device='cuda:0', img_size=size, texture_size=512, texture_num_ch=16, mipmap_level=4, nf0=80)
+    for m in pipe.render_net.modules():
+        if isinstance(m, torch.nn.Dropout2d):
+            m.eval()
+    with torch.no_grad():
+        for lvl, t in enumerate(pipe.texture_mapper.textures):
+            t.add_(0.1 * torch.randn(t.shape, generator=torch.Generator().manual_seed(40 + lvl)).to(t.device))
+    view = synthetic_view(size, view_idx=4, device='cuda:0')
+    tex = [t.detach().cpu().clone().requires_grad_(True) for t in pipe.texture_mapper.textures]
+    sd = {k: v.detach().cpu().clone() for k, v in pipe.render_net.state_dict().items()}
+    sd = {k: (v.requires_grad_(True) if (v.dtype.is_floating_point and 'running' not in k and v.dim() > 0) else v) for k, v in sd.items()}
+    out = pipe.forward(view)
+    a = view['alpha_map'][:, None, 5:-5, 5:-5]
+    loss = F.l1_loss((out[:, :, 5:-5, 5:-5] * a).reshape(-1), (view['img_gt'][:, :, 5:-5, 5:-5] * a).reshape(-1))
+    pipe.optimizer.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    cv = {k: v.cpu() for k, v in view.items()}
+    ref = dnr_forward(tex, sd, cv)
+    ac = cv['alpha_map'][:, None, 5:-5, 5:-5]
+    ref_loss = F.l1_loss((ref[:, :, 5:-5, 5:-5] * ac).reshape(-1), (cv['img_gt'][:, :, 5:-5, 5:-5] * ac).reshape(-1))
+    ref_loss.backward()
+    p = psnr(out.detach().cpu() * 0.5, ref.detach() * 0.5)
+    print('DNR nf0=80 %d^2: psnr %.1f dB, loss %.6f vs %.6f' % (size, p, loss.item(), ref_loss.item()))
+    assert p >= 50.0
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    worst = 1.0
+    for i, t in enumerate(pipe.texture_mapper.textures):
+        c = cosine(t.grad.cpu(), tex[i].grad)
+        print('texture %d grad cosine %.5f' % (i, c))
+        worst = min(worst, c)
+    n = 0
+    for k, prm in pipe.render_net.named_parameters(remove_duplicate=False):
+        if prm.grad is not None and k in sd and sd[k].grad is not None:
+            worst = min(worst, cosine(prm.grad.cpu(), sd[k].grad))
+            n += 1
+    print('worst gradient cosine %.5f over %d U-Net tensors + %d texture levels' % (worst, n, len(tex)))
+    assert n >= 60 and worst >= 0.97
+
+
 def test_state_dict_roundtrip_strict():
     import numpy as np, os
     from relightable_nr_b200.dropin import network

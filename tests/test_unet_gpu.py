@@ -43,19 +43,22 @@ def _oracle_fwd_bwd(sd, x, num_down, R, grad_range, q16=False, gates=None):
     return out.detach(), grads, xg.grad[:, grad_range[0]:grad_range[1]]
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("impl,wgrad_impl", [("simt", "simt"), ("tc", "simt"), ("tc", "tc")])
 @pytest.mark.parametrize("cfg", [
     dict(in_ch=20, out_ch=6, nf0=16, H=64, N=1, num_down=5, grad_range=(4, 20)),
     dict(in_ch=108, out_ch=78, nf0=64, H=64, N=2, num_down=5, grad_range=(84, 108)),
 ])
-def test_unet_forward_backward(cfg, impl):
+def test_unet_forward_backward(cfg, impl, wgrad_impl):
+    """("tc", "tc") is the product configuration: tcgen05 forward / data gradient AND tcgen05 weight gradient (wgrad_tc /
+    wgrad_halo kernels, GEMM-order scratch + un-transpose) against the gate-matched oracle; the SIMT rows isolate the
+    validation kernels."""
     sd, x = _setup(cfg['in_ch'], cfg['out_ch'], cfg['nf0'], cfg['H'], cfg['N'], cfg['num_down'])
     g = torch.Generator().manual_seed(7)
     R = torch.randn(cfg['N'], cfg['out_ch'], cfg['H'], cfg['H'], generator=g) / (cfg['H'] * cfg['H'])
     ref_out, ref_grads32, _ = _oracle_fwd_bwd(sd, x, cfg['num_down'], R, cfg['grad_range'])
 
     eng, params = _engine(sd, x, cfg['out_ch'], cfg['nf0'], cfg['num_down'], impl, cfg['grad_range'],
-                          wgrad_impl='simt')
+                          wgrad_impl=wgrad_impl)
     eng.set_input_nchw(x.cuda())
     eng.forward(training=True, drop_masks=None)
     out = eng.output_nchw().cpu()
@@ -77,8 +80,35 @@ def test_unet_forward_backward(cfg, impl):
         c32 = cosine(gm, ref_grads32[k])
         assert c32 >= 0.98, f"{k}: cosine vs fp32 oracle {c32:.5f}"
     r = rel_l2(gx.cpu(), ref_gx)
-    print(f"[{impl}] worst param-grad rel_l2 {worst:.2e}; input-grad rel_l2 {r:.2e}")
+    print(f"[{impl}/{wgrad_impl}] worst param-grad rel_l2 {worst:.2e}; input-grad rel_l2 {r:.2e}")
     assert r <= 3e-2
+
+
+def test_eval_mode_batchnorm_uses_running_statistics():
+    """module.eval() WITHOUT the scripts' set_bn_train (test_rnr.py:220-233 re-enables train mode): nn.BatchNorm2d then
+    normalises with running_mean / running_var.  Engine vs oracle (F.batch_norm(training=False)) on non-trivial running
+    statistics: PSNR >= 50 dB; and the statistics must be left untouched."""
+    from oracle.unet import unet_forward
+    sd, x = _setup(20, 6, 16, 64, 1, 5)
+    g = torch.Generator().manual_seed(11)
+    for k in list(sd):
+        if k.endswith('running_mean'):
+            sd[k] = 0.3 * torch.randn(sd[k].shape, generator=g)
+        if k.endswith('running_var'):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+    eng, _ = _engine(sd, x, 6, 16, 5, 'tc', None)
+    before = {k: v.clone() for k, v in eng.buffers.items()}
+    eng.set_input_nchw(x.cuda())
+    eng.forward(training=False, drop_masks=None)
+    out = eng.output_nchw().cpu()
+    ref = torch.tanh(unet_forward(sd, x, num_down=5, bn_eval=True))
+    ref_train = torch.tanh(unet_forward(sd, x, num_down=5))
+    p = psnr(out * 0.5 + 0.5, ref * 0.5 + 0.5)
+    print('eval-mode BN: psnr %.1f dB (vs the batch-statistic output: %.1f dB)' % (p, psnr(out * 0.5 + 0.5, ref_train * 0.5 + 0.5)))
+    assert p >= 50.0
+    assert psnr(ref * 0.5 + 0.5, ref_train * 0.5 + 0.5) < 40.0, 'the two BatchNorm modes must differ for this test to mean anything'
+    for k, v in eng.buffers.items():
+        assert torch.equal(v, before[k]), k
 
 
 def test_batched_weight_prep_is_bit_identical_to_per_layer():
