@@ -13,7 +13,7 @@ keep resolving to the reference's own files next to the script.
 Compatibility shims for this software stack (part of the boundary, not of the reference): ``np.int`` / ``np.float`` aliases
 (removed in numpy 1.24); ``tensorboardX.SummaryWriter`` -> ``torch.utils.tensorboard`` (or a no-op writer);
 ``torch_geometric.data.Data`` (attribute bag with ``.to()``: the only thing train_rnr.py:258 uses); ``torch_cluster`` (imported
-by gcn_lib, never called on the dense path); ``pytorch_msssim`` (metric.py:3, validation only), ``skimage.transform``
+by gcn_lib, never called on the dense path); ``pytorch_msssim`` (metric.py:3: a Gaussian-window SSIM in relightable_nr_b200/compat), ``skimage.transform``
 (data_util.py:3), ``pyshtools`` (replaced by the drop-in sph_harm), ``trimesh``: registered only when the real package is
 absent; ``torchvision.utils.make_grid(range=...)`` (renamed ``value_range``); ``OPENCV_IO_ENABLE_OPENEXR=1``.
 """
@@ -83,10 +83,13 @@ def install_shims():
     _stub('torch_cluster', knn_graph=None)
     _stub('pyshtools')
     _stub('trimesh')
-    # pytorch_msssim.ssim is only called by the validation metrics (metric.py:47-84, out of scope)
-    def _no_ssim(*a, **k):
-        raise NotImplementedError('pytorch_msssim is not installed (validation-only metric, out of the hot path)')
-    _stub('pytorch_msssim', ssim=_no_ssim, ms_ssim=_no_ssim)
+    # pytorch_msssim.ssim: called by the validation pass of the training scripts (metric.py:78-84), which the unchanged
+    # train_rnr.py / train_dnr.py execute at iteration 0 -- a real Gaussian-window SSIM, not a stub
+    try:
+        importlib.import_module('pytorch_msssim')
+    except Exception:
+        from .compat import pytorch_msssim as _ssim_mod
+        sys.modules['pytorch_msssim'] = _ssim_mod
     sk = _stub('skimage')
     if getattr(sk, '__rnr_stub__', False):
         sk.transform = _stub('skimage.transform')

@@ -9,7 +9,9 @@ import os
 import sys
 import types
 
-REF = '/root/reference'
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'baseline', '_ref', 'relightable-nr')
+# the build container has the reference itself; the GPU box only the copy staged by tools/stage_reference.py (git-ignored)
+REF = '/root/reference' if os.path.isdir('/root/reference') else _STAGED
 
 
 def available():
@@ -55,4 +57,16 @@ def import_reference():
     for name in ('misc', 'camera', 'render', 'sph_harm', 'data_util', 'network'):
         mods[name] = importlib.import_module(name)
     mods['pytorch_prototyping'] = importlib.import_module('pytorch_prototyping.pytorch_prototyping')
+    # pyshtools (sph_harm.py:66-68) is not installable here: the reference's evaluate_sh_basis is the ONE function replaced,
+    # by the scipy-pinned oracle restatement (tests/test_oracle_golden.py); everything else is the reference's own code
+    from oracle import pixel_ops as _P
+
+    def evaluate_sh_basis(lmax=0, azi=None, pol=None, directions=None):
+        import numpy as _np
+        if directions is None:
+            a, p = _np.deg2rad(_np.asarray(azi, dtype=_np.float64)), _np.deg2rad(_np.asarray(pol, dtype=_np.float64))
+            directions = _np.stack((_np.sin(p) * _np.cos(a), _np.sin(p) * _np.sin(a), _np.cos(p)), -1)
+        return _P.evaluate_sh_basis(lmax, _np.asarray(directions))
+
+    mods['sph_harm'].evaluate_sh_basis = evaluate_sh_basis
     return types.SimpleNamespace(**mods)
