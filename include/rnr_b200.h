@@ -105,6 +105,14 @@ int  rnr_conv_plan_tiles_m(const rnr_conv_plan_t* plan);
 int  rnr_debug_set_trace(long long* buf);
 /* rows of `stats` the plan writes ([rows, 2, ldstats]; the caller sizes / zero-fills the buffer accordingly) */
 int  rnr_conv_plan_stat_rows(const rnr_conv_plan_t* plan);
+/* Fuse nn.BatchNorm2d's batch-statistics finalize (pytorch_prototyping.py:177-197: mean / biased variance of the conv output,
+ * running_mean / running_var / num_batches_tracked update) into the plan's kernel: its last CTA reduces the per-CTA partial
+ * sums and writes mean / invstd / scale = gamma*invstd / shift = beta - mean*scale.  cudaErrorNotSupported (no error text)
+ * when the plan does not run on the halo kernel with RNR_EPI_STATS -- the caller then launches rnr_bn_finalize itself.
+ * `ticket`: one zero-initialised int per plan.  running_* / num_batches_tracked may be NULL (no update). */
+int  rnr_conv_plan_set_bn(rnr_conv_plan_t* plan, const float* gamma, const float* beta, double count, float eps, float momentum,
+                          float* mean, float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, int* ticket, int enabled);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Weight-gradient problem (autograd of Conv2d/ConvTranspose2d w.r.t. weight)                  */
@@ -178,6 +186,42 @@ void rnr_wgrad_unpack_plan_destroy(rnr_wunpack_plan_t* plan);
 int  rnr_wgrad_unpack_run(const rnr_wunpack_plan_t* plan, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Optimiser: torch.optim.Adam(lr) of train_rnr.py:376,618-623 / train_dnr.py:176,259-262       */
+/*   (fused-Adam arithmetic: m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2;                        */
+/*    p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)), step counter resident on the device   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {               /* a conv weight whose gradient sits in GEMM order (see rnr_wunpack_job_t) */
+    float*       scratch;      /* [ntaps, cout, cin] gradient; re-zeroed by the pass when zero_grad */
+    float*       p;            /* fp32 master weight, parameter layout: (co, ci, t) at co*s_co + ci*s_ci + t */
+    float*       m;            /* exp_avg,    parameter layout */
+    float*       v;            /* exp_avg_sq, parameter layout */
+    float*       gdst;         /* optional: also write the un-transposed gradient here (NULL: never materialised) */
+    int32_t      cout, cin, ntaps;
+    int64_t      s_co, s_ci;
+} rnr_adam_wjob_t;
+typedef struct {               /* a plain tensor (bias, BatchNorm affine, texture level, SH coefficients) */
+    float*       p;
+    float*       g;            /* gradient; re-zeroed by the pass when zero_grad */
+    float*       m;
+    float*       v;
+    int64_t      n;
+} rnr_adam_job_t;
+typedef struct rnr_adam_plan rnr_adam_plan_t;
+int  rnr_adam_plan_create(const rnr_adam_wjob_t* wjobs, int n_wjobs, const rnr_adam_job_t* jobs, int n_jobs, rnr_adam_plan_t** plan);
+void rnr_adam_plan_destroy(rnr_adam_plan_t* plan);
+/* One Adam step over the plan's tensors (<= 2 launches).  `step`: device float, number of steps taken so far; with
+ * advance_step the last block of the tensor-job launch increments it.  gscale multiplies every gradient (1/world). */
+int  rnr_adam_run(const rnr_adam_plan_t* plan, float* step, float lr, float beta1, float beta2, float eps, float gscale,
+                  int zero_grad, int advance_step, void* stream);
+/* out[0] = sums[2]/cnt + sums[0]/sums[1]/R*w_chrom + sum(extra[0..n_extra)): the scalar of train_rnr.py:608 from the device
+ * accumulators of rnr_tail_fwd and the small-loss kernels (no host round trip, no ATen glue) */
+int  rnr_loss_combine(double* sums, double cnt, double R, double w_chrom, const double* extra, int n_extra, float* out,
+                      int n_clear, void* stream);   /* then zeroes sums[0..n_clear): the accumulators clean up behind themselves */
+/* nn.Dropout2d channel masks (pytorch_prototyping.py:181,190,255,268: p = 0.1): out[i] = 0 w.p. p else 1/(1-p); counter-based
+ * generator keyed by (seed, *counter); *counter is advanced by the launch (fresh masks on every CUDA-graph replay) */
+int  rnr_dropout_masks(float* out, int n, float p, unsigned long long seed, unsigned long long* counter, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* BatchNorm2d (batch statistics) + activation + Dropout2d                                     */
 /*   replaces nn.BatchNorm2d / LeakyReLU / ReLU / Dropout2d of pytorch_prototyping.py:177-197,  */
 /*   250-272, 471-476 (forward and backward)                                                   */
@@ -237,6 +281,8 @@ int rnr_unpack_nhwc_to_nchw(const float* src, float* dst, int N, int C, int ld, 
 int rnr_tanh_bwd_pack(const float* grad_nchw, const float* tanh_nhwc, void* gz, float* dbias /* [C] atomics, pre-zeroed */,
                       int N, int C, int ld, int H, int W, void* stream);
 /* folded grad w.r.t. reflect-padded input [N,H+2,W+2,ld] -> NCHW fp32 [N,C,H,W] (channels c0..c0+C) */
+int rnr_fold_to_nchw_add(const void* gpad, int dtype, float* dst, int N, int C, int c0, int ld, int H, int W,
+                         const float* add, int nadd, void* stream);
 int rnr_fold_to_nchw(const void* gpad, int dtype, float* dst, int N, int C, int c0, int ld, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
@@ -337,6 +383,10 @@ int rnr_sh_basis(const float* dirs /* [P,3] */, double* out, int64_t P, int lmax
 int rnr_sh_reconstruct(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int Lc, void* stream);
 /* res[l,b,c] += scale * sum_p basis[p,b] v[l,p,c]   (res pre-zeroed / accumulated) */
 int rnr_sh_project(const float* basis, const float* v, float* res, int64_t P, int B, int Cc, int Lc, float scale, void* stream);
+/* pitched variants for one lighting: out rows ldo >= Cc apart (extra columns untouched) / v rows ldv >= Cc apart, optionally cleared
+ * as they are consumed (the [P,4] envmap texels and their gradient accumulator of the fused step) */
+int rnr_sh_reconstruct_ld(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int ldo, void* stream);
+int rnr_sh_project_ld(const float* basis, float* v, float* res, int64_t P, int B, int Cc, int ldv, float scale, int zero_v, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Losses and optimiser: network.RaysLTChromLoss (network.py:395-411), masked cropped L1         */
@@ -352,6 +402,16 @@ int rnr_l1_masked(const float* out, const float* gt, const float* alpha, int N, 
                   float weight, float* g_out, double* loss_sum, void* stream);
 int rnr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, int step, float gscale, void* stream);
+/* Lighting L1 (train_rnr.py:571-579) for ONE lighting: est = basis[S,B] coeff[B,3]; *loss += sum_s |l_init - est| w_s with
+ * w_s = w_cov (mask[s] != 0) or w_unc -- the caller passes weight / sample count; sgn[S,3] = d loss / d est (scatter it into
+ * the coefficient gradient with rnr_sh_project). */
+int rnr_lighting_l1(const float* basis, const float* coeff, const float* l_init, const unsigned char* mask, int S, int B,
+                    float w_cov, float w_unc, float* sgn, double* loss, void* stream);
+/* Albedo-mean loss (train_rnr.py:596-607) on tex6 = flatten_mipmap(channels 0:6) [P,6] against the initial flattened texture:
+ * sums[8] (zeroed by the caller) receive the touched-texel counts / channel sums, gout[P,6] = d (w_alb*loss) / d tex6,
+ * *loss += w_alb * loss (scatter gout into the levels with rnr_flatten_mipmap(backward = 1)). */
+int rnr_albedo_mean_loss(const float* tex6, const float* init6, int64_t P, float w_alb, double* sums, float* gout, double* loss,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* gcn_lib/dense EdgeConv (network.DenseDeepGCN, network.py:256-315)                           */

@@ -64,6 +64,15 @@ class WUnpackJob(C.Structure):
                 ("s_co", C.c_int64), ("s_ci", C.c_int64)]
 
 
+class AdamWJob(C.Structure):
+    _fields_ = [("scratch", C.c_void_p), ("p", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("gdst", C.c_void_p),
+                ("cout", C.c_int32), ("cin", C.c_int32), ("ntaps", C.c_int32), ("s_co", C.c_int64), ("s_ci", C.c_int64)]
+
+
+class AdamJob(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64)]
+
+
 class RnrError(RuntimeError):
     pass
 
@@ -93,6 +102,7 @@ def lib():
         "rnr_conv_run": [vp, vp],
         "rnr_conv_plan_tiles_m": [vp],
         "rnr_conv_plan_stat_rows": [vp],
+        "rnr_conv_plan_set_bn": [vp, vp, vp, f64, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp, i32],
         "rnr_debug_set_trace": [vp],
         "rnr_wgrad_plan_create": [C.POINTER(WgradProblem), i32, C.POINTER(vp)],
         "rnr_wgrad_run": [vp, vp],
@@ -111,6 +121,7 @@ def lib():
         "rnr_unpack_nhwc_to_nchw": [vp, vp, i32, i32, i32, i32, i32, vp],
         "rnr_tanh_bwd_pack": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "rnr_fold_to_nchw": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp],
+        "rnr_fold_to_nchw_add": [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(L, name)
@@ -124,6 +135,8 @@ def lib():
     L.rnr_wprep_plan_destroy.restype = None
     L.rnr_wgrad_unpack_plan_destroy.argtypes = [vp]
     L.rnr_wgrad_unpack_plan_destroy.restype = None
+    L.rnr_adam_plan_destroy.argtypes = [vp]
+    L.rnr_adam_plan_destroy.restype = None
     _register_optional(L)
     _lib = L
     return L

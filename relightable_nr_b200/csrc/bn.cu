@@ -5,6 +5,7 @@
 //
 // HBM-bound elementwise/reduction kernels: 128-bit loads, 8 channels per thread, channels-last.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const GSrcs srcs,
 //     fp32 partials is order-independent to ~1e-16, far below the fp32 result's rounding);
 //   * the LAST block to finish (threadfence + ticket) turns the totals into dgamma / dbeta / the fused apply coefficients,
 //     re-zeroes the accumulator and re-arms the ticket -- the separate finalize launch disappears.
-constexpr int kRU = 2;
+constexpr int kRUmax = 4;    // pixel vectors in flight per thread (template parameter RU of bn_bwd_reduce_fin_kernel)
 
 __device__ __forceinline__ void acc_packed(const uint4& u, int dtype, float* out) {
     const unsigned short* us = (const unsigned short*)&u;
@@ -281,7 +282,7 @@ __device__ __forceinline__ void split_pix(int pix, int HW, int W, int lhw, int l
     }
 }
 
-template <int NSRC>
+template <int NSRC, int kRU>
 __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs srcs, const void* __restrict__ raw, int raw_dtype,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -579,19 +580,21 @@ extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const voi
             lw = 0; while ((1 << lw) < W) lw++;
         }
     }
-    RNR_ONCE_PER_DEVICE({
-        RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    });
     RNR_REQUIRE(smem <= 160 * 1024, "rnr_bn_bwd_reduce_fin: C=%d needs %zu bytes of shared memory", C, smem);
-    if (nsrc == 1)
-        bn_bwd_reduce_fin_kernel<1><<<T, threads, smem, (cudaStream_t)stream>>>(
-            gs, raw, raw_dtype, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
-            N, H, W, C, ppb, prow, lhw, lw);
-    else
-        bn_bwd_reduce_fin_kernel<2><<<T, threads, smem, (cudaStream_t)stream>>>(
-            gs, raw, raw_dtype, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta, gamma, coef,
-            N, H, W, C, ppb, prow, lhw, lw);
+    // pixel vectors in flight per thread.  Measured on B200 (bench.py, 512^2 step): RU = 2 / 3 / 4 -> 201.7 / 200.2 / 198.5 views/s --
+    // the extra loads in flight of RU > 2 do not pay for the register spills of a 128-register, 512-thread block.  RNR_BN_RU overrides.
+    int ru = 2;
+    { const char* e = getenv("RNR_BN_RU"); if (e && atoi(e) >= 2 && atoi(e) <= kRUmax) ru = atoi(e); }
+#define RNR_BN_LAUNCH(NS, RU)                                                                                                        \
+    do {                                                                                                                             \
+        RNR_ONCE_PER_DEVICE({ RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<NS, RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); }); \
+        bn_bwd_reduce_fin_kernel<NS, RU><<<T, threads, smem, (cudaStream_t)stream>>>(                                                \
+            gs, raw, raw_dtype, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta,   \
+            gamma, coef, N, H, W, C, ppb, prow, lhw, lw);                                                                            \
+    } while (0)
+    if (nsrc == 1) { if (ru == 2) RNR_BN_LAUNCH(1, 2); else if (ru == 3) RNR_BN_LAUNCH(1, 3); else RNR_BN_LAUNCH(1, 4); }
+    else { if (ru == 2) RNR_BN_LAUNCH(2, 2); else if (ru == 3) RNR_BN_LAUNCH(2, 3); else RNR_BN_LAUNCH(2, 4); }
+#undef RNR_BN_LAUNCH
     RNR_LAUNCH_CHECK();
     return 0;
 }

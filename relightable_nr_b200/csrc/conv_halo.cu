@@ -74,7 +74,7 @@ __device__ __forceinline__ void trace(long long* base, int role, int& idx) {
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, const HaloGroup* __restrict__ groups, int n_groups,
                  const HaloTap* __restrict__ taps, int n_taps, int bn, int tiles_n, int b_stages, int a_stage_bytes,
-                 int b_stage_bytes, int pitch, int a_bytes, int dbg, int T, int cs, int gtaps, const HaloCfg hc) {
+                 int b_stage_bytes, int pitch, int a_bytes, int dbg, int T, int cs, int gtaps, const HaloCfg hc, const BnFin bnf) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -393,6 +393,61 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 p.stats[((int64_t)blockIdx.x * 2 + 0) * p.ldstats + co] = s_acc[co];
                 p.stats[((int64_t)blockIdx.x * 2 + 1) * p.ldstats + co] = s_acc[512 + co];
             }
+            if (bnf.enabled) {
+                // ---- fused BatchNorm finalize: last CTA to arrive reduces every CTA's row (same order as bn_finalize_kernel) ----
+                int* s_last = (int*)s_rowoff;
+                __threadfence();
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                if (e == 0) *s_last = (atomicAdd(bnf.ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                if (*s_last) {
+                    __threadfence();
+                    // All 512 threads: G = 512 / Cp row groups x Cp channels (Cp = channels rounded up to a power of two); group g sums
+                    // rows g, g + G, ... of every CTA's partial sums in double (independent L2 loads, coalesced over channels), the
+                    // G partials of a channel are then added in a fixed order: deterministic whichever CTA comes last.
+                    double* ss = (double*)s_stage;            // [G][Cp] sums, then [G][Cp] sums of squares: 2 * 512 * 8 B = 8 KB
+                    const int T = (int)gridDim.x;
+                    for (int c0 = 0; c0 < p.cout; c0 += 512) {
+                        const int nch = min(512, p.cout - c0);
+                        int Cp = 32;
+                        while (Cp < nch) Cp <<= 1;
+                        const int G = 512 / Cp;
+                        const int g = e / Cp, c = c0 + (e % Cp);
+                        double s1 = 0.0, s2 = 0.0;
+                        if (c < p.cout) {
+#pragma unroll 4
+                            for (int t = g; t < T; t += G) {
+                                s1 += (double)__ldcg(p.stats + ((int64_t)t * 2 + 0) * p.ldstats + c);
+                                s2 += (double)__ldcg(p.stats + ((int64_t)t * 2 + 1) * p.ldstats + c);
+                            }
+                        }
+                        ss[e] = s1; ss[512 + e] = s2;
+                        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                        if (e < Cp && c < p.cout) {
+                            for (int i = 1; i < G; i++) { s1 += ss[i * Cp + e]; s2 += ss[512 + i * Cp + e]; }
+                            const double m = s1 / bnf.count;
+                            double var = s2 / bnf.count - m * m;
+                            if (var < 0.0) var = 0.0;
+                            const float istd = (float)(1.0 / sqrt(var + (double)bnf.eps));
+                            const float gm = bnf.gamma ? bnf.gamma[c] : 1.f, b = bnf.beta ? bnf.beta[c] : 0.f;
+                            bnf.mean[c] = (float)m;
+                            bnf.invstd[c] = istd;
+                            bnf.scale[c] = gm * istd;
+                            bnf.shift[c] = b - (float)m * gm * istd;
+                            if (bnf.running_mean) {
+                                const double unbiased = bnf.count > 1.0 ? var * bnf.count / (bnf.count - 1.0) : var;
+                                bnf.running_mean[c] = (1.f - bnf.momentum) * bnf.running_mean[c] + bnf.momentum * (float)m;
+                                bnf.running_var[c] = (1.f - bnf.momentum) * bnf.running_var[c] + bnf.momentum * (float)unbiased;
+                            }
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                    }
+                    if (e == 0) {
+                        *bnf.ticket = 0;                       // ready for the next launch of this plan
+                        if (bnf.num_batches_tracked && bnf.running_mean) *bnf.num_batches_tracked += 1;
+                    }
+                }
+            }
         }
     }
 
@@ -619,6 +674,22 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     return 0;
 }
 
+// Fuse the BatchNorm statistics finalize into this plan's launches (halo kernel with RNR_EPI_STATS only; returns
+// cudaErrorNotSupported otherwise and the caller keeps the separate rnr_bn_finalize launch).  May be called again at any time
+// (e.g. running statistics on / off); `enabled = 0` restores the plain behaviour.
+extern "C" int rnr_conv_plan_set_bn(rnr_conv_plan_t* pl, const float* gamma, const float* beta, double count, float eps, float momentum,
+                                    float* mean, float* invstd, float* scale, float* shift, float* running_mean, float* running_var,
+                                    long long* num_batches_tracked, int* ticket, int enabled) {
+    RNR_REQUIRE(pl, "rnr_conv_plan_set_bn: null plan");
+    if (!(pl->impl == 1 && pl->halo && (pl->p.epi & RNR_EPI_STATS))) return (int)cudaErrorNotSupported;
+    RNR_REQUIRE(!enabled || (mean && invstd && scale && shift && ticket), "rnr_conv_plan_set_bn: null output pointer");
+    BnFin& b = pl->bnf;
+    b.gamma = gamma; b.beta = beta; b.mean = mean; b.invstd = invstd; b.scale = scale; b.shift = shift;
+    b.running_mean = running_mean; b.running_var = running_var; b.num_batches_tracked = num_batches_tracked; b.ticket = ticket;
+    b.count = count; b.eps = eps; b.momentum = momentum; b.enabled = enabled ? 1 : 0;
+    return 0;
+}
+
 extern "C" int rnr_debug_set_trace(long long* buf) {
     RNR_CHECK(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
     return 0;
@@ -655,7 +726,7 @@ int rnr_conv_halo_run(const rnr_conv_plan* pl, cudaStream_t stream) {
     }
     RNR_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel, maps, pl->p, (const HaloGroup*)pl->d_groups, pl->n_groups,
                                  (const HaloTap*)pl->d_taps, pl->n_taps, pl->bn, pl->tiles_n, pl->stages, pl->halo_a_stage,
-                                 pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc));
+                                 pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc, pl->bnf));
     rnr_count_launch();
     return 0;
 }

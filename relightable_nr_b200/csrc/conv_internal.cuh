@@ -21,6 +21,25 @@ struct ConvParams {
     int ldstats;
 };
 
+// BatchNorm statistics finalize fused into the halo kernel: the LAST CTA to publish its partial sums (ticket counter) reduces
+// all gridDim.x rows in the fixed order of bn_finalize_kernel (bit-identical results, whichever CTA comes last) and writes
+// mean / invstd / scale / shift (+ running statistics, num_batches_tracked) -- one launch less on the dependent chain per layer.
+struct BnFin {
+    const float* gamma;
+    const float* beta;
+    float* mean;
+    float* invstd;
+    float* scale;
+    float* shift;
+    float* running_mean;       // nullptr: no running-statistics update
+    float* running_var;
+    long long* num_batches_tracked;   // nullptr: not counted here
+    int* ticket;               // zero-initialised; reset by the last CTA
+    double count;
+    float eps, momentum;
+    int enabled;
+};
+
 struct HaloGroup {       // one (view, 64-channel chunk): a single halo box load serves all of its taps
     int16_t view, c0, ox, oy, first_tap, n_taps;
 };
@@ -53,6 +72,7 @@ struct rnr_conv_plan {
     HaloTap* d_taps;
     int n_groups, n_taps;
     int dbg;             // RNR_CONV_DBG ablation bits (profiling only)
+    BnFin bnf;           // fused BatchNorm finalize (rnr_conv_plan_set_bn; halo kernel only)
 };
 
 struct WgradParams {

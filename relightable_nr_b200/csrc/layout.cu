@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256) tanh_bwd_pack_kernel(const float* __restr
 
 // grad w.r.t. reflect-padded input [N,H+2,W+2,ld] -> fold halo -> NCHW fp32 for channels [c0,c0+C)
 __global__ void __launch_bounds__(256) fold_to_nchw_kernel(const void* __restrict__ gpad, int dtype, float* __restrict__ dst,
-                                                         int N, int C, int c0, int ld, int H, int W) {
+                                                         int N, int C, int c0, int ld, int H, int W,
+                                                         const float* __restrict__ add, int nadd) {
     extern __shared__ float tile[];   // [C][TP+1]
     const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
     const int Hp = H + 2, Wp = W + 2;
@@ -151,7 +152,11 @@ __global__ void __launch_bounds__(256) fold_to_nchw_kernel(const void* __restric
     __syncthreads();
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     for (int c = wp; c < C; c += 8)
-        if (w0 + lane < W) dst[(((int64_t)n * C + c) * H + h) * W + w0 + lane] = tile[c * (TP + 1) + lane];
+        if (w0 + lane < W) {
+            float v = tile[c * (TP + 1) + lane];
+            if (c < nadd) v += add[(((int64_t)n * nadd + c) * H + h) * W + w0 + lane];     // e.g. the albedo gradient of the tail kernel
+            dst[(((int64_t)n * C + c) * H + h) * W + w0 + lane] = v;
+        }
 }
 
 }  // namespace
@@ -191,7 +196,19 @@ extern "C" int rnr_fold_to_nchw(const void* gpad, int dtype, float* dst, int N, 
     const size_t smem = (size_t)C * (TP + 1) * sizeof(float);
     RNR_REQUIRE(smem <= 48 * 1024, "rnr_fold_to_nchw: too many channels (%d)", C);
     dim3 grid(rnr_cdiv(W, TP), H, N);
-    fold_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gpad, dtype, dst, N, C, c0, ld, H, W);
+    fold_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gpad, dtype, dst, N, C, c0, ld, H, W, nullptr, 0);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+// same, plus dst[:, :nadd] += add ([N, nadd, H, W] fp32): folds `gi[:, :6] += g_alb` of the fused step into this pass
+extern "C" int rnr_fold_to_nchw_add(const void* gpad, int dtype, float* dst, int N, int C, int c0, int ld, int H, int W,
+                                    const float* add, int nadd, void* stream) {
+    const size_t smem = (size_t)C * (TP + 1) * sizeof(float);
+    RNR_REQUIRE(smem <= 48 * 1024, "rnr_fold_to_nchw_add: too many channels (%d)", C);
+    RNR_REQUIRE(nadd >= 0 && nadd <= C && (nadd == 0 || add), "rnr_fold_to_nchw_add: bad add tensor");
+    dim3 grid(rnr_cdiv(W, TP), H, N);
+    fold_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gpad, dtype, dst, N, C, c0, ld, H, W, add, nadd);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) sh_basis_general_kernel(const float* __re
 
 // out[l, p, c] = sum_b basis[p, b] * coeff[l, b, c]        one warp per (l, p)
 __global__ void __launch_bounds__(256) sh_reconstruct_kernel(const float* __restrict__ basis, const float* __restrict__ coeff,
-                                                           float* __restrict__ out, int64_t P, int B, int Cc, int Lc) {
+                                                           float* __restrict__ out, int64_t P, int B, int Cc, int Lc, int ldo) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= P * Lc) return;
@@ -90,26 +90,61 @@ __global__ void __launch_bounds__(256) sh_reconstruct_kernel(const float* __rest
         if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < 4; c++)
-                if (c0 + c < Cc) out[((int64_t)l * P + pp) * Cc + c0 + c] = a[c];
+                if (c0 + c < Cc) out[((int64_t)l * P + pp) * ldo + c0 + c] = a[c];
         }
     }
 }
 
 // res[l, b, c] += scale * sum_p basis[p, b] * v[l, p, c]     (backward of reconstruct, and fit_sh_coeff)
 // block = 128 threads (one basis function each, looping if B > 128) x a chunk of points
-__global__ void __launch_bounds__(128) sh_project_kernel(const float* __restrict__ basis, const float* __restrict__ v,
+__global__ void __launch_bounds__(128) sh_project_kernel(const float* __restrict__ basis, float* __restrict__ v,
                                                        float* __restrict__ res, int64_t P, int B, int Cc, int Lc, float scale,
-                                                       int chunk) {
+                                                       int chunk, int ldv, int zero_v) {
     extern __shared__ float s_v[];    // [chunk][Cc]
     const int l = blockIdx.y;
     const int64_t p0 = (int64_t)blockIdx.x * chunk;
     const int64_t np = (P - p0) < chunk ? (P - p0) : chunk;
-    for (int64_t i = threadIdx.x; i < np * Cc; i += 128) s_v[i] = v[((int64_t)l * P + p0) * Cc + i];
+    if (ldv == Cc && !zero_v) {
+        for (int64_t i = threadIdx.x; i < np * Cc; i += 128) s_v[i] = v[((int64_t)l * P + p0) * Cc + i];
+    } else {
+        // pitched rows (ldv >= Cc); zero_v: the accumulator is cleared on the way (every element is read by exactly one block)
+        if (ldv == 4 && ((((uintptr_t)v) & 15) == 0)) {
+            float4* v4 = (float4*)v + ((int64_t)l * P + p0);
+            for (int64_t pp = threadIdx.x; pp < np; pp += 128) {
+                const float4 t = v4[pp];
+                const float tt[4] = {t.x, t.y, t.z, t.w};
+                for (int c = 0; c < Cc; c++) s_v[pp * Cc + c] = tt[c];
+                if (zero_v) v4[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int64_t i = threadIdx.x; i < np * ldv; i += 128) {
+                const int64_t pp = i / ldv;
+                const int c = (int)(i - pp * ldv);
+                float* src = v + ((int64_t)l * P + p0) * ldv + i;
+                if (c < Cc) s_v[pp * Cc + c] = *src;
+                if (zero_v) *src = 0.f;
+            }
+        }
+    }
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += 128) {
         for (int c0 = 0; c0 < Cc; c0 += 4) {
             float a[4] = {0, 0, 0, 0};
-            for (int64_t i = 0; i < np; i++) {
+            // a pure stream over the basis table (484 B per point at lmax 10): 8 independent loads in flight per thread -- with
+            // one it ran at 1/10 of the copy bandwidth (the loop is load-latency bound, not FMA bound)
+            int64_t i = 0;
+            for (; i + 8 <= np; i += 8) {
+                float bv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) bv[u] = __ldcs(basis + (p0 + i + u) * B + b);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if (c0 + c < Cc) a[c] += bv[u] * s_v[(i + u) * Cc + c0 + c];
+                }
+            }
+            for (; i < np; i++) {
                 const float bv = basis[(p0 + i) * B + b];
 #pragma unroll
                 for (int c = 0; c < 4; c++)
@@ -142,7 +177,17 @@ extern "C" int rnr_sh_basis(const float* dirs, double* out, int64_t P, int lmax,
 extern "C" int rnr_sh_reconstruct(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int Lc,
                                   void* stream) {
     if (P * Lc == 0) return 0;
-    sh_reconstruct_kernel<<<rnr_cdiv(P * Lc * 32, 256), 256, 0, (cudaStream_t)stream>>>(basis, coeff, out, P, B, Cc, Lc);
+    sh_reconstruct_kernel<<<rnr_cdiv(P * Lc * 32, 256), 256, 0, (cudaStream_t)stream>>>(basis, coeff, out, P, B, Cc, Lc, Cc);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+// same with an output row pitch ldo >= Cc (columns >= Cc are left untouched): the fused step keeps the envmap as [P, 4] texels
+extern "C" int rnr_sh_reconstruct_ld(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int ldo,
+                                     void* stream) {
+    RNR_REQUIRE(ldo >= Cc, "rnr_sh_reconstruct_ld: ldo %d < Cc %d", ldo, Cc);
+    if (P == 0) return 0;
+    sh_reconstruct_kernel<<<rnr_cdiv(P * 32, 256), 256, 0, (cudaStream_t)stream>>>(basis, coeff, out, P, B, Cc, 1, ldo);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -153,7 +198,21 @@ extern "C" int rnr_sh_project(const float* basis, const float* v, float* res, in
     int chunk = 256;
     RNR_REQUIRE((size_t)chunk * Cc * 4 <= 48 * 1024, "sh_project: too many channels (%d)", Cc);
     dim3 grid(rnr_cdiv(P, chunk), Lc);
-    sh_project_kernel<<<grid, 128, (size_t)chunk * Cc * 4, (cudaStream_t)stream>>>(basis, v, res, P, B, Cc, Lc, scale, chunk);
+    sh_project_kernel<<<grid, 128, (size_t)chunk * Cc * 4, (cudaStream_t)stream>>>(basis, const_cast<float*>(v), res, P, B, Cc, Lc, scale, chunk, Cc, 0);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+// res[b, c] += scale * sum_p basis[p, b] * v[p*ldv + c] for c < Cc; with zero_v the (accumulator) rows of v are cleared as they
+// are consumed -- the envmap-gradient texels [P, 4] of the fused step need no separate copy / memset
+extern "C" int rnr_sh_project_ld(const float* basis, float* v, float* res, int64_t P, int B, int Cc, int ldv, float scale, int zero_v,
+                                 void* stream) {
+    RNR_REQUIRE(ldv >= Cc, "rnr_sh_project_ld: ldv %d < Cc %d", ldv, Cc);
+    if (P == 0) return 0;
+    int chunk = 256;
+    RNR_REQUIRE((size_t)chunk * Cc * 4 <= 48 * 1024, "sh_project: too many channels (%d)", Cc);
+    dim3 grid(rnr_cdiv(P, chunk), 1);
+    sh_project_kernel<<<grid, 128, (size_t)chunk * Cc * 4, (cudaStream_t)stream>>>(basis, v, res, P, B, Cc, 1, scale, chunk, ldv, zero_v);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -167,6 +167,8 @@ class _LayerState:
     drop: Optional[torch.Tensor] = None
     ticket: Optional[torch.Tensor] = None
     bwd_totals: Optional[torch.Tensor] = None
+    bn_ticket: Optional[torch.Tensor] = None   # last-CTA ticket of the fused forward BatchNorm finalize
+    bn_fused: bool = False                     # statistics finalize runs inside the conv kernel (rnr_conv_plan_set_bn)
 
 
 class UNetEngine:
@@ -197,6 +199,8 @@ class UNetEngine:
         self.keep = []            # keeps ctypes arrays / tensors referenced by plans alive
         self.gpu_launches = 0
         self.timing = None        # list of (kind, layer, start_event, end_event) when enabled (bench.py roofline leg)
+        self._bn_mode = None      # (training, momentum, eps) the fused finalize is currently configured for
+        self._gi = None           # persistent input-gradient buffer of the fused step
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -275,6 +279,7 @@ class UNetEngine:
         self.wscratch = None
         self.wscratch_slices = {}
         self._wunpack_jobs = []
+        self._wunpack_names = []
         if self.need_backward and self.wgrad_impl == 1:
             n = 0
             for sp in self.specs:
@@ -516,6 +521,12 @@ class UNetEngine:
                         rows_pp = self.L.rnr_conv_plan_stat_rows(st.fwd_plans[-1].h)
                         if st.stats is not None:
                             st.n_stat_tiles = 4 * rows_pp
+        # BatchNorm finalize inside the conv kernel's last CTA: possible when the layer is ONE halo-kernel launch.  OFF by default:
+        # measured on B200 (bench.py, 512^2 step) 198.5 views/s with it vs 205.1 without -- one CTA reducing 148 rows while 147 SMs
+        # idle at the tail of every conv launch costs more than the 17 tiny finalize launches it removes (RNR_BN_FUSED_FINALIZE=1 enables)
+        if (epi & EPI_STATS) and len(st.fwd_plans) == 1 and self.impl == 1 and os.environ.get('RNR_BN_FUSED_FINALIZE', '0') == '1':
+            st.bn_ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+            st.bn_fused = self._set_bn(st, True, 0.1, 1e-5, probe=True)
         if not self.need_backward:
             return
 
@@ -590,6 +601,7 @@ class UNetEngine:
             # scratch destination [tap][co][ci]: tap offset = kernel tap index * cout * cin
             w0, _wn = self.wscratch_slices[sp.name]
             self._wunpack_jobs.append((self.wscratch.data_ptr() + 4 * w0, wp.dw, cout, cin_tot, kk, int(wp.s_co), int(wp.s_ci)))
+            self._wunpack_names.append(sp.name)
             for i in range(len(wtaps)):
                 tarr[i].off = int(tarr[i].off) * cout * cin_tot
             wp.dw = self.wscratch.data_ptr() + 4 * w0
@@ -695,6 +707,34 @@ class UNetEngine:
         k = 3 if sp.kind == 'c3' else 4
         return 2.0 * N * sp.Ho * sp.Wo * cin * sp.cout * k * k
 
+    def _set_bn(self, st, training, momentum, eps, probe=False):
+        """(Re)configure the fused BatchNorm finalize of one layer's forward plan; returns False when the plan cannot host it."""
+        sp = st.spec
+        N = self.N
+        rm = rv = nbt = None
+        if training:
+            rm, rv = self.buffers[sp.bn_key + '.running_mean'], self.buffers[sp.bn_key + '.running_var']
+            nbt = self.buffers.get(sp.bn_key + '.num_batches_tracked')
+            if nbt is not None and not (nbt.is_cuda and nbt.dtype == torch.int64):
+                nbt = None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        rc = self.L.rnr_conv_plan_set_bn(st.fwd_plans[0].h, self.params[sp.bn_key + '.weight'].data_ptr(),
+                                         self.params[sp.bn_key + '.bias'].data_ptr(), float(N * sp.Ho * sp.Wo), eps, momentum,
+                                         st.mean.data_ptr(), st.invstd.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(),
+                                         ptr(rm), ptr(rv), ptr(nbt), st.bn_ticket.data_ptr(), 1 if training else 0)
+        if rc != 0 and not probe:
+            _lib.check(rc, 'rnr_conv_plan_set_bn(%s)' % sp.name)
+        return rc == 0
+
+    def counts_batches_in_kernel(self, bn_key):
+        """True when num_batches_tracked of this BatchNorm layer is incremented by the conv kernel's fused finalize (the
+        host-side nn.Module bookkeeping must then skip it)."""
+        for sp in self.specs:
+            if sp.bn_key == bn_key:
+                nbt = self.buffers.get(bn_key + '.num_batches_tracked')
+                return bool(self.layers[sp.name].bn_fused and nbt is not None and nbt.is_cuda and nbt.dtype == torch.int64)
+        return False
+
     def _wprep(self, items: List[_WPrep], s):
         for w in items:
             src = self.params[w.src_key]
@@ -716,6 +756,30 @@ class UNetEngine:
             return
         _lib.check(self.L.rnr_wprep_run(plan.h, self._stream()), 'rnr_wprep_run')
         self.gpu_launches += 1
+
+    def wprep_plan_for(self, layer_names, backward=True):
+        """Batched weight-preparation plan (one launch) for the forward (+ data-gradient) matrices of a subset of layers: the
+        fused optimiser refreshes each group of layers right after its Adam update."""
+        items = []
+        for sp in self.specs:
+            if sp.name in layer_names:
+                st = self.layers[sp.name]
+                items += st.wprep_fwd + (st.wprep_dgrad if backward else [])
+        return self._wprep_plan(items) if items else None
+
+    def run_wprep_plan(self, plan):
+        if plan is not None:
+            _lib.check(self.L.rnr_wprep_run(plan.h, self._stream()), 'rnr_wprep_run')
+            self.gpu_launches += 1
+
+    def wgrad_scratch_jobs(self, layer_names=None):
+        """[(layer name, weight key, scratch ptr, cout, cin, ntaps, s_co, s_ci)] of the layers whose weight gradient is
+        accumulated in GEMM order (all of them on the tensor-core path) -- the job table of the fused un-transpose + Adam pass."""
+        out = []
+        for name, (src, _dst, cout, cin, kk, s_co, s_ci) in zip(self._wunpack_names, self._wunpack_jobs):
+            if layer_names is None or name in layer_names:
+                out.append((name, self.layers[name].spec.w_key, src, cout, cin, kk, s_co, s_ci))
+        return out
 
     def prepare_weights_per_layer(self, backward=False):
         """Same result through the single-matrix entry point (kept as the cross-check of the batched kernel)."""
@@ -743,6 +807,12 @@ class UNetEngine:
         if not weights_ready:
             self.prepare_weights(backward=self.need_backward)
         self.bn_training = bool(training)
+        mode = (bool(training), float(momentum), float(eps))
+        if mode != self._bn_mode:
+            for sp in self.specs:
+                if self.layers[sp.name].bn_fused:
+                    self._set_bn(self.layers[sp.name], *mode)
+            self._bn_mode = mode
         for sp in self.specs:
             st = self.layers[sp.name]
             t0 = self._mark()
@@ -763,6 +833,8 @@ class UNetEngine:
                     torch.mul(self.params[sp.bn_key + '.weight'], st.invstd, out=st.scale)
                     torch.addcmul(self.params[sp.bn_key + '.bias'], st.mean, st.scale, value=-1.0, out=st.shift)
                 shift = st.shift
+            elif sp.bn_key is not None and st.bn_fused:
+                shift = st.shift                 # mean / invstd / scale / shift were written by the conv kernel's last CTA
             elif sp.bn_key is not None:
                 rm, rv = self.buffers[sp.bn_key + '.running_mean'], self.buffers[sp.bn_key + '.running_var']
                 _lib.check(L.rnr_bn_finalize(st.stats.data_ptr(), st.n_stat_tiles, Cc, Cc, float(N * Ho * Wo),
@@ -848,7 +920,7 @@ class UNetEngine:
         self.gpu_launches += 1
         return self._backward_layers()
 
-    def _backward_layers(self, after_layer=None, before_unpack=None):
+    def _backward_layers(self, after_layer=None, before_unpack=None, unpack=True, input_grad_add=None):
         """Backward of every layer in reverse order.  ``after_layer(name)`` is called once a layer's weight- and data-gradient
         launches are enqueued, ``before_unpack()`` before the weight gradients leave GEMM order (hooks of the data-parallel
         step: early all-reduce of ``wscratch``)."""
@@ -897,15 +969,23 @@ class UNetEngine:
                 after_layer(sp.name)
         if before_unpack is not None:
             before_unpack()
-        if self.wunpack_plan is not None:
+        # ``unpack=False``: the caller consumes the GEMM-order scratch itself (fused un-transpose + Adam, rnr_adam_run)
+        if unpack and self.wunpack_plan is not None:
             _lib.check(L.rnr_wgrad_unpack_run(self.wunpack_plan.h, s), 'rnr_wgrad_unpack_run')
             self.gpu_launches += 1
         st = self.layers['in']
         if st.gx is None:
             return None
         r0, r1 = self.input_grad_range
-        gi = torch.empty((N, r1 - r0, self.H, self.W), dtype=torch.float32, device=self.device)
-        _lib.check(L.rnr_fold_to_nchw(st.gx.data_ptr(), self.grad_dt, gi.data_ptr(), N, r1 - r0, 0, st.gx_ld, self.H, self.W, s),
-                   'rnr_fold_to_nchw')
+        if self._gi is None or self._gi.shape[1] != r1 - r0:
+            self._gi = torch.empty((N, r1 - r0, self.H, self.W), dtype=torch.float32, device=self.device)
+        gi = self._gi if input_grad_add is not None else torch.empty_like(self._gi)
+        if input_grad_add is not None:
+            # ``input_grad_add`` [N, k, H, W] is added to the first k channels in the same pass (the fused step's albedo gradient)
+            _lib.check(L.rnr_fold_to_nchw_add(st.gx.data_ptr(), self.grad_dt, gi.data_ptr(), N, r1 - r0, 0, st.gx_ld, self.H, self.W,
+                                              input_grad_add.data_ptr(), int(input_grad_add.shape[1]), s), 'rnr_fold_to_nchw_add')
+        else:
+            _lib.check(L.rnr_fold_to_nchw(st.gx.data_ptr(), self.grad_dt, gi.data_ptr(), N, r1 - r0, 0, st.gx_ld, self.H, self.W, s),
+                       'rnr_fold_to_nchw')
         self.gpu_launches += 1
         return gi

@@ -106,7 +106,7 @@ class UnetRunner:
         for k, p in live.items():
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                 raise TypeError('U-Net parameter %s must be a contiguous fp32 CUDA tensor (librnr_b200 has no CPU path)' % k)
-        live_bufs = {k: v for k, v in bufs.items() if 'running' in k}
+        live_bufs = {k: v for k, v in bufs.items() if 'running' in k or k.endswith('num_batches_tracked')}
         eng = UNetEngine(specs, live, live_bufs, N, Cin, device, impl='tc', input_grad_range=rng,
                          need_backward=need_backward, final_tanh=apply_tanh)
         eng.version = 0
@@ -164,7 +164,9 @@ class UnetRunner:
                 drop_masks[n] = r[:, o:o + c].contiguous()
                 o += c
         if training_bn:
-            nbt = [b for k, b in unet.named_buffers() if k.endswith('num_batches_tracked') and '.fuse.' not in k]
+            # (layers whose statistics are finalized inside the conv kernel count their batches there)
+            nbt = [b for k, b in unet.named_buffers() if k.endswith('num_batches_tracked') and '.fuse.' not in k
+                   and not eng.counts_batches_in_kernel(k[:-len('.num_batches_tracked')])]
             if nbt:
                 torch._foreach_add_(nbt, 1)
         return training_bn, drop_masks

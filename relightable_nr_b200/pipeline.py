@@ -25,10 +25,29 @@ def fibonacci_sphere(n, device='cpu'):
     return torch.stack((r * torch.cos(phi), r * torch.sin(phi), z)).float().to(device)
 
 
+def _view_dir_map(H, W, K, R, device):
+    """camera.get_view_dir_map (camera.py:5-32) in plain torch ops (any device): the ray through each pixel centre,
+    -K^-1 [u+.5, v+.5, 1] normalised, rotated to world space (R: world->camera rotation) and normalised -- points to the camera."""
+    v, u = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=device) + 0.5, torch.arange(W, dtype=torch.float32, device=device) + 0.5,
+                          indexing='ij')
+    pix = torch.stack((u, v, torch.ones_like(u)), -1)                        # [H,W,3]
+    cam = torch.nn.functional.normalize(-(pix @ torch.inverse(K).t()), dim=-1)
+    return torch.nn.functional.normalize(cam @ R, dim=-1)                    # R^T applied to row vectors
+
+
+def _sh_basis_l2(d):
+    """sph_harm.evaluate_sh_basis(lmax=2) in closed form (real, orthonormal, no Condon-Shortley phase) -> [...,9]."""
+    x, y, z = d[..., 0], d[..., 1], d[..., 2]
+    return torch.stack((torch.full_like(x, 0.28209479177387814), 0.4886025119029199 * y, 0.4886025119029199 * z, 0.4886025119029199 * x,
+                        1.0925484305920792 * x * y, 1.0925484305920792 * y * z, 0.31539156525252005 * (3 * z * z - 1),
+                        1.0925484305920792 * x * z, 0.5462742152960396 * (x * x - y * y)), -1)
+
+
 def synthetic_view(img_size=512, view_idx=0, device='cuda', radius=3.0, focal=None, seed=0):
     """Per-view maps of a unit sphere at the origin seen from spiral camera ``view_idx``: the dict a
     ``ViewDataset`` item holds after precompute.py (dataio.py:219-245) -- uv_map, sh_basis_map, normal_map, view_dir_map,
-    view_dir_map_tangent, TBN_map, alpha_map, img_gt -- as fp32 tensors with batch dimension 1 on ``device``."""
+    view_dir_map_tangent, TBN_map, alpha_map, img_gt -- as fp32 tensors with batch dimension 1 on ``device``.  Plain torch
+    arithmetic on any device: bench.py feeds the SAME tensors to the GPU arm and to the CPU reference arm."""
     H = W = int(img_size)
     focal = focal if focal is not None else 1.2 * img_size
     azi = math.radians(-2.0 * view_idx)
@@ -37,7 +56,7 @@ def synthetic_view(img_size=512, view_idx=0, device='cuda', radius=3.0, focal=No
     RT = _camera.RT_from_pos_lookat(pos)
     R = torch.tensor(RT[:3, :3], dtype=torch.float32, device=device)
     K = torch.tensor([[focal, 0, W / 2], [0, focal, H / 2], [0, 0, 1]], dtype=torch.float32, device=device)
-    view_dir, _ = _camera.get_view_dir_map((H, W), torch.inverse(K)[None], R.t()[None].contiguous())     # [1,H,W,3], points to the camera
+    view_dir = _view_dir_map(H, W, K, R, device)[None]                       # [1,H,W,3], points to the camera
     o = torch.tensor(pos, dtype=torch.float32, device=device)
     d = -view_dir[0]
     b = (d * o).sum(-1)
@@ -57,7 +76,7 @@ def synthetic_view(img_size=512, view_idx=0, device='cuda', radius=3.0, focal=No
     tan = torch.nn.functional.normalize(torch.cross(bit, p, dim=-1), dim=-1)
     TBN = torch.stack((tan, bit, p), dim=-1) * alpha[..., None, None]
     vdt = torch.einsum('hwji,hwj->hwi', TBN, view_dir[0])
-    sh = _sph_harm.evaluate_sh_basis_l2(view_dir[0].contiguous())
+    sh = _sh_basis_l2(view_dir[0])
     g = torch.Generator(device='cpu').manual_seed(seed + view_idx)
     img = torch.rand((1, 3, H, W), generator=g).to(device) * alpha[None, None]
     return {
