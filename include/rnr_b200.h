@@ -164,6 +164,7 @@ typedef struct {
     int64_t      s_r, s_c;     /* element strides of row / column index in src; min(s_r, s_c) = taps per (row, col) pair <= 16 */
     int32_t      tapoff[16];   /* source tap index of each destination tap */
     int32_t      chunked;      /* 0: columns [tap][cpad]; 1: columns [cpad/64][tap][64] (all taps of a 64-channel chunk adjacent) */
+    int64_t      ld;           /* destination row pitch in elements; 0 = ntaps*cpad (a job may fill a column block of a wider matrix) */
 } rnr_wprep_job_t;
 typedef struct rnr_wprep_plan rnr_wprep_plan_t;
 int  rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr_wprep_plan_t** plan);
@@ -457,6 +458,35 @@ int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, const float*
                  const float* alpha, const float* img_gt, int Rs, int Rd, int N, int H, int W, int crop, const float* aux,
                  const double* sums, float w_l1, float w_chrom, void* gz, int ldg, float* dbias, float* g_alb,
                  float* g_lp4, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* neural_renderer.cuda: the cold entry points (never on the relighting path; provided so that  */
+/* the extension's seven functions all exist).  Same arithmetic as the reference kernels.        */
+/* ------------------------------------------------------------------------------------------ */
+/* rasterize_cuda.cpp:97-122 / rasterize_cuda_kernel.cu:172-242: rgb_map [B,is,is,3] (+ 8 sampling indices / weights per pixel) from
+ * the per-face texture cubes textures [B,nf,ts,ts,ts,3]; background pixels are left untouched */
+int rnr_nr_forward_texture_sampling(const float* faces, const float* textures, const int32_t* face_index_map, const float* weight_map,
+                                    const float* depth_map, float* rgb_map, int32_t* sampling_index_map, float* sampling_weight_map,
+                                    int batch, int num_faces, int image_size, int texture_size, float eps, void* stream);
+/* rasterize_cuda.cpp:124-148 / kernel :245-505: silhouette gradient into grad_faces [B,nf,3,3] (front faces overwritten, back faces untouched) */
+int rnr_nr_backward_pixel_map(const float* faces, const int32_t* face_index_map, const float* rgb_map, const float* alpha_map,
+                              const float* grad_rgb_map, const float* grad_alpha_map, float* grad_faces, int batch, int num_faces,
+                              int image_size, float eps, int return_rgb, int return_alpha, void* stream);
+/* rasterize_cuda.cpp:150-167 / kernel :507-541: grad_textures += scatter of grad_rgb_map through the sampling indices / weights */
+int rnr_nr_backward_textures(const int32_t* face_index_map, const float* sampling_weight_map, const int32_t* sampling_index_map,
+                             const float* grad_rgb_map, float* grad_textures, int batch, int num_faces, int image_size, int texture_size,
+                             void* stream);
+/* rasterize_cuda.cpp:169-191 / kernel :543-591: grad_faces += d depth / d vertices */
+int rnr_nr_backward_depth_map(const float* faces, const float* depth_map, const int32_t* face_index_map, const float* face_inv_map,
+                              const float* weight_map, const float* grad_depth_map, float* grad_faces, int batch, int num_faces,
+                              int image_size, void* stream);
+/* load_textures_cuda.cpp:20-39 / kernel :25-121: texture cubes [nf,ts,ts,ts,3] of the faces with is_update != 0 from image [H,W,3] through
+ * the uv triangles faces [nf,3,2] (wrapped in place: 0 REPEAT, 1 MIRRORED_REPEAT, 2 CLAMP_TO_EDGE, 3 CLAMP_TO_BORDER) */
+int rnr_nr_load_textures(const float* image, float* faces, float* textures, const int32_t* is_update, int num_faces, int texture_size,
+                         int image_height, int image_width, int texture_wrapping, int use_bilinear, void* stream);
+/* create_texture_image_cuda.cpp:18-33 / kernel :9-117: tiled atlas image [th*tso, tw*tso, 3] from the texture cubes */
+int rnr_nr_create_texture_image(const float* vertices_all, const float* textures, float* image, int64_t image_numel, int num_faces,
+                                int texture_size_in, int texture_size_out, int tile_width, float eps, void* stream);
 
 #ifdef __cplusplus
 }

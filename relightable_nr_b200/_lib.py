@@ -56,7 +56,7 @@ class GSrc(C.Structure):
 class WPrepJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("dst_dtype", C.c_int32), ("nr", C.c_int32), ("nr_pad", C.c_int32),
                 ("nc", C.c_int32), ("cpad", C.c_int32), ("ntaps", C.c_int32), ("s_r", C.c_int64), ("s_c", C.c_int64),
-                ("tapoff", C.c_int32 * 16), ("chunked", C.c_int32)]
+                ("tapoff", C.c_int32 * 16), ("chunked", C.c_int32), ("ld", C.c_int64)]
 
 
 class WUnpackJob(C.Structure):

@@ -37,6 +37,7 @@ constexpr int kMaxGroups = 128;
 constexpr int kMaxSub = 4;           // sub-problems fused into one launch (the 4 output parities of a stride-2 layer)
 constexpr int kMaxTaps = 512;
 constexpr int kAStages = 2;
+constexpr int kMaxStatC = 1024;      // BatchNorm statistics: output channels per layer (DNR at nf0 = 80 has 640)
 
 struct HaloCfg {           // per-problem constants of the tap pattern (kernel parameter -> constant bank -> uniform registers)
     int a_off[kMaxSub][16];   // byte offset of tap k inside the halo tile (identical for every group of a sub-problem)
@@ -89,8 +90,8 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
     HaloGroup* s_groups = (HaloGroup*)(tmem_slot + 4);               // [kMaxGroups]
     HaloTap* s_taps = (HaloTap*)(s_groups + kMaxGroups);             // [kMaxTaps]
-    float* s_acc = (float*)(s_taps + kMaxTaps);                      // [2][512] per-CTA BatchNorm sums
-    float* s_stage = s_acc + 1024;                                   // [128][68] epilogue staging slab (16-byte aligned)
+    float* s_acc = (float*)(s_taps + kMaxTaps);                      // [2][kMaxStatC] per-CTA BatchNorm sums
+    float* s_stage = s_acc + 2 * kMaxStatC;                                   // [128][68] epilogue staging slab (16-byte aligned)
     int64_t* s_rowoff = (int64_t*)(s_stage + 128 * 68);              // [128] output offset of each tile row
     float* s_colp = (float*)(s_rowoff + 128);                        // [2][8][64] per-pass column partial sums
 
@@ -109,7 +110,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
 
     for (int i = threadIdx.x; i < n_groups * hc.nsub; i += kThreads) s_groups[i] = groups[i];
     for (int i = threadIdx.x; i < n_taps; i += kThreads) s_taps[i] = taps[i];
-    for (int i = threadIdx.x; i < 1024; i += kThreads) s_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * kMaxStatC; i += kThreads) s_acc[i] = 0.f;
 
     if (warp == kProducerWarp && lane == 0) {
         for (int v = 0; v < RNR_MAX_VIEWS; v++)
@@ -371,12 +372,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     // threads 0..63: sum of x, threads 64..127: sum of x^2 (the next pass rewrites s_colp only after its own barrier)
                     const int col = e & 63, which = e >> 6;
                     const int co = n0 + c0 + col;
-                    if (col < pw && co < p.cout && co < 512) {
+                    if (col < pw && co < p.cout && co < kMaxStatC) {
                         const float* pp = s_colp + which * 512 + col;
                         float a = 0.f;
 #pragma unroll
                         for (int k = 0; k < 8; k++) a += pp[k * 64];
-                        s_acc[which * 512 + co] += a;
+                        s_acc[which * kMaxStatC + co] += a;
                     }
                 }
             }
@@ -391,7 +392,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             for (int co = e; co < p.cout; co += kEpiThreads) {
                 p.stats[((int64_t)blockIdx.x * 2 + 0) * p.ldstats + co] = s_acc[co];
-                p.stats[((int64_t)blockIdx.x * 2 + 1) * p.ldstats + co] = s_acc[512 + co];
+                p.stats[((int64_t)blockIdx.x * 2 + 1) * p.ldstats + co] = s_acc[kMaxStatC + co];
             }
             if (bnf.enabled) {
                 // ---- fused BatchNorm finalize: last CTA to arrive reduces every CTA's row (same order as bn_finalize_kernel) ----
@@ -486,7 +487,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     if (env && env[0] == '0') return 0;
     if (nsub < 1 || nsub > kMaxSub) return 0;
     if (prob->bk != 64) return 0;
-    if (prob->cout > 512 && (prob->epi & RNR_EPI_STATS)) return 0;
+    if (prob->cout > kMaxStatC && (prob->epi & RNR_EPI_STATS)) return 0;
     // ---- group the K-steps: maximal runs of consecutive K-steps on the same (view, channel chunk) ----
     // (the engine emits the K-steps chunk-major, so all taps of a chunk are adjacent in K and in Wmat)
     struct Key { int view, c0; };
@@ -587,7 +588,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     pl->bn = bn;
     pl->tiles_n = tiles_n;
     const int a_stage = ((rows * pitch * 128) + 1023) / 1024 * 1024;
-    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 1024 * 4 + 128 * 68 * 4 + 128 * 8 + 1024 * 4;
+    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 2 * kMaxStatC * 4 + 128 * 68 * 4 + 128 * 8 + 1024 * 4;
     const int budget = 212 * 1024 - aux - kAStages * a_stage;
     // taps per B stage: one mbarrier hand-shake (~400 cycles of latency in the single-thread producer / issuer loops) must
     // cover enough tensor work, so a stage holds T taps = T*4 MMAs; T divides the taps of a group

@@ -22,7 +22,7 @@ struct WJob {
     const float* src;
     void* dst;
     int32_t dtype, nr, nr_pad, nc, cpad, ntaps, ts, tiles_c, chunked;
-    int64_t s_r, s_c;
+    int64_t s_r, s_c, ld;        // ld: destination row pitch in elements (>= ntaps * cpad)
     int32_t tapoff[MAXT];
     int32_t blk0, nblk;
 };
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict
             }
             const int c = c0 + cg * 8;
             const int64_t col = J.chunked ? ((int64_t)((c >> 6) * J.ntaps + tl) * 64 + (c & 63)) : ((int64_t)tl * J.cpad + c);
-            *(uint4*)(dst + (int64_t)(r0 + rr) * J.ntaps * J.cpad + col) = *(const uint4*)o;
+            *(uint4*)(dst + (int64_t)(r0 + rr) * J.ld + col) = *(const uint4*)o;
         }
     }
 }
@@ -134,6 +134,8 @@ extern "C" int rnr_wprep_plan_create(const rnr_wprep_job_t* jobs, int njobs, rnr
         d.src = s.src; d.dst = s.dst; d.dtype = s.dst_dtype;
         d.nr = s.nr; d.nr_pad = s.nr_pad; d.nc = s.nc; d.cpad = s.cpad; d.ntaps = s.ntaps; d.ts = (int)ts;
         d.s_r = s.s_r; d.s_c = s.s_c; d.chunked = s.chunked;
+        d.ld = s.ld > 0 ? s.ld : (int64_t)s.ntaps * s.cpad;
+        RNR_REQUIRE(d.ld >= (int64_t)s.ntaps * s.cpad && d.ld % 8 == 0, "weight prep: row pitch %lld too small / not a multiple of 8", (long long)d.ld);
         RNR_REQUIRE(s.cpad % 8 == 0 && ((uintptr_t)s.dst & 15) == 0, "weight prep: cpad %% 8 == 0 and a 16-byte aligned destination required (cpad %d)", s.cpad);
         RNR_REQUIRE(!s.chunked || s.cpad % 64 == 0, "weight prep: chunk-major layout needs cpad %% 64 == 0 (got %d)", s.cpad);
         for (int t = 0; t < s.ntaps; t++) {

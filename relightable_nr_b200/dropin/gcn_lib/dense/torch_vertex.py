@@ -25,20 +25,31 @@ _lib.register_sigs({
 def _edgeconv_torch(seq, x, edge_index):
     x_i = batched_index_select(x, edge_index[1])
     x_j = batched_index_select(x, edge_index[0])
-    return torch.max(seq(torch.cat([x_i, x_j - x_i], dim=1)), -1, keepdim=True)[0]
+    feat = torch.cat([x_i, x_j - x_i], dim=1)                         # [B, 2C, V, k]
+    if isinstance(seq[0], nn.Linear):
+        # node-major MLP of gcn_lib.sparse (Linear / BatchNorm1d over the E = V*k edge rows): same numbers, other layout
+        B, C2, V, K = feat.shape
+        out = seq(feat.permute(0, 2, 3, 1).reshape(B * V * K, C2)).view(B, V, K, -1).permute(0, 3, 1, 2)
+        return torch.max(out, -1, keepdim=True)[0]
+    return torch.max(seq(feat), -1, keepdim=True)[0]
 
 
 def _fusable(seq, x, edge_index):
     if not (x.is_cuda and x.dtype == torch.float32 and x.shape[0] == 1 and x.shape[-1] == 1):
         return None
     mods = list(seq)
-    if not mods or not isinstance(mods[0], nn.Conv2d) or mods[0].kernel_size != (1, 1):
+    if not mods:
+        return None
+    if isinstance(mods[0], nn.Conv2d):
+        if mods[0].kernel_size != (1, 1):
+            return None
+    elif not isinstance(mods[0], nn.Linear):           # (nn.Linear: the node-major MLP of gcn_lib.sparse -- the same 1x1 map)
         return None
     conv, act, bn = mods[0], None, None
     for m in mods[1:]:
         if isinstance(m, (nn.ReLU, nn.LeakyReLU)) and act is None and bn is None:
             act = m
-        elif isinstance(m, nn.BatchNorm2d) and bn is None:
+        elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)) and bn is None:
             bn = m
         else:
             return None
@@ -55,9 +66,9 @@ class _EdgeConvFn(torch.autograd.Function):
         L = _lib.lib()
         s = torch.cuda.current_stream().cuda_stream
         V, K = edge_index.shape[2], edge_index.shape[3]
-        Cin, Cout = x.shape[1], conv.out_channels
+        Cin, Cout = x.shape[1], conv.weight.shape[0]
         X = x[0, :, :, 0].t().contiguous()                                  # [V, Cin]
-        W = conv.weight.detach()[:, :, 0, 0]                                # [Cout, 2 Cin] acting on cat[x_i, x_j - x_i]
+        W = conv.weight.detach().reshape(Cout, -1)                          # [Cout, 2 Cin] acting on cat[x_i, x_j - x_i]
         Wcat = torch.cat((W[:, :Cin] - W[:, Cin:], W[:, Cin:]), 0).t().contiguous()      # [Cin, 2 Cout] -> P | Q
         bias = torch.zeros(2 * Cout, dtype=torch.float32, device=x.device)
         if conv.bias is not None:

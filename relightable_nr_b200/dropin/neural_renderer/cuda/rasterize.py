@@ -1,8 +1,8 @@
 """``neural_renderer.cuda.rasterize``: same five entry points as cuda/rasterize_cuda.cpp:70-199, caller-allocated
 contiguous CUDA tensors filled in place and returned.  ``forward_face_index_map`` runs the tile-culled B200 kernels;
 the rgb sampling and the three backward functions are outside the hot path (the reference never consumes the rgb of
-its all-zero face texture, network.py:157, and never differentiates the rasterizer) and raise instead of silently
-returning something else."""
+its all-zero face texture, network.py:157, and never differentiates the rasterizer); they run the kernels of csrc/nr_cold.cu,
+which restate the reference's and are checked against it on the GPU (tests/test_b2_gpu.py)."""
 import ctypes as C
 
 import torch
@@ -43,16 +43,62 @@ def forward_face_index_map(faces, face_index_map, weight_map, depth_map, face_in
     return [face_index_map, weight_map, depth_map, face_inv_map]
 
 
-def _out_of_scope(name):
-    def f(*a, **k):
-        raise NotImplementedError(
-            'neural_renderer.cuda.rasterize.%s is outside the relighting hot path (the rasterizer is forward-only and its rgb '
-            'output is never consumed: SURVEY.md 8a rows a3/a4); librnr_b200 does not provide it' % name)
-    f.__name__ = name
-    return f
+_lib.register_sigs({
+    "rnr_nr_forward_texture_sampling": [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+    "rnr_nr_backward_pixel_map": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, vp],
+    "rnr_nr_backward_textures": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+    "rnr_nr_backward_depth_map": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+})
 
 
-forward_texture_sampling = _out_of_scope('forward_texture_sampling')
-backward_pixel_map = _out_of_scope('backward_pixel_map')
-backward_textures = _out_of_scope('backward_textures')
-backward_depth_map = _out_of_scope('backward_depth_map')
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def forward_texture_sampling(faces, textures, face_index_map, weight_map, depth_map, rgb_map, sampling_index_map, sampling_weight_map,
+                             image_size, eps):
+    """rasterize_cuda.cpp:97-122: per-pixel trilinear sample of the face's texture cube [B,nf,ts,ts,ts,3]; fills rgb_map and the 8
+    sampling indices / weights per pixel in place.  Cold: the relighting path discards this output (network.py:157)."""
+    _check(faces, 'faces'); _check(textures, 'textures'); _check(face_index_map, 'face_index_map', torch.int32)
+    _check(weight_map, 'weight_map'); _check(depth_map, 'depth_map'); _check(rgb_map, 'rgb_map')
+    _check(sampling_index_map, 'sampling_index_map', torch.int32); _check(sampling_weight_map, 'sampling_weight_map')
+    B, nf = faces.shape[0], faces.shape[1]
+    _lib.check(_lib.lib().rnr_nr_forward_texture_sampling(
+        faces.data_ptr(), textures.data_ptr(), face_index_map.data_ptr(), weight_map.data_ptr(), depth_map.data_ptr(), rgb_map.data_ptr(),
+        sampling_index_map.data_ptr(), sampling_weight_map.data_ptr(), B, nf, int(image_size), int(textures.shape[2]), float(eps), _stream()),
+        'rnr_nr_forward_texture_sampling')
+    return [rgb_map, sampling_index_map, sampling_weight_map]
+
+
+def backward_pixel_map(faces, face_index_map, rgb_map, alpha_map, grad_rgb_map, grad_alpha_map, grad_faces, image_size, eps, return_rgb,
+                       return_alpha):
+    """rasterize_cuda.cpp:124-148: silhouette gradient w.r.t. the projected faces (grad_faces [B,nf,3,3], written in place)."""
+    _check(faces, 'faces'); _check(face_index_map, 'face_index_map', torch.int32); _check(rgb_map, 'rgb_map'); _check(alpha_map, 'alpha_map')
+    _check(grad_rgb_map, 'grad_rgb_map'); _check(grad_alpha_map, 'grad_alpha_map'); _check(grad_faces, 'grad_faces')
+    B, nf = faces.shape[0], faces.shape[1]
+    _lib.check(_lib.lib().rnr_nr_backward_pixel_map(
+        faces.data_ptr(), face_index_map.data_ptr(), rgb_map.data_ptr(), alpha_map.data_ptr(), grad_rgb_map.data_ptr(), grad_alpha_map.data_ptr(),
+        grad_faces.data_ptr(), B, nf, int(image_size), float(eps), int(return_rgb), int(return_alpha), _stream()), 'rnr_nr_backward_pixel_map')
+    return grad_faces
+
+
+def backward_textures(face_index_map, sampling_weight_map, sampling_index_map, grad_rgb_map, grad_textures, num_faces):
+    """rasterize_cuda.cpp:150-167: grad_textures [B,nf,ts,ts,ts,3] += scatter of grad_rgb_map through the sampling maps."""
+    _check(face_index_map, 'face_index_map', torch.int32); _check(sampling_weight_map, 'sampling_weight_map')
+    _check(sampling_index_map, 'sampling_index_map', torch.int32); _check(grad_rgb_map, 'grad_rgb_map'); _check(grad_textures, 'grad_textures')
+    B, is_ = face_index_map.shape[0], face_index_map.shape[1]
+    _lib.check(_lib.lib().rnr_nr_backward_textures(
+        face_index_map.data_ptr(), sampling_weight_map.data_ptr(), sampling_index_map.data_ptr(), grad_rgb_map.data_ptr(), grad_textures.data_ptr(),
+        B, int(num_faces), is_, int(grad_textures.shape[2]), _stream()), 'rnr_nr_backward_textures')
+    return grad_textures
+
+
+def backward_depth_map(faces, depth_map, face_index_map, face_inv_map, weight_map, grad_depth_map, grad_faces, image_size):
+    """rasterize_cuda.cpp:169-191: grad_faces += d depth / d projected vertices."""
+    _check(faces, 'faces'); _check(depth_map, 'depth_map'); _check(face_index_map, 'face_index_map', torch.int32)
+    _check(face_inv_map, 'face_inv_map'); _check(weight_map, 'weight_map'); _check(grad_depth_map, 'grad_depth_map'); _check(grad_faces, 'grad_faces')
+    B, nf = faces.shape[0], faces.shape[1]
+    _lib.check(_lib.lib().rnr_nr_backward_depth_map(
+        faces.data_ptr(), depth_map.data_ptr(), face_index_map.data_ptr(), face_inv_map.data_ptr(), weight_map.data_ptr(), grad_depth_map.data_ptr(),
+        grad_faces.data_ptr(), B, nf, int(image_size), _stream()), 'rnr_nr_backward_depth_map')
+    return grad_faces

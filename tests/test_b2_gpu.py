@@ -1,0 +1,188 @@
+"""The seven entry points of ``neural_renderer.cuda`` (SURVEY.md 8b "B2") against the REFERENCE'S OWN CUDA kernels recompiled for
+sm_100a (tools/build_ref_ext.py -> baseline/_ref/nr_ext: host glue patched for torch 2.x, __global__ bodies untouched), on the same
+inputs on the same GPU.  Integer maps (face index, sampling indices) must be identical; float outputs within 1e-5 (sampled values /
+weights) and 1e-4 relative (atomically accumulated gradients); the silhouette gradient -- a sum of terms divided by near-zero edge
+distances -- on >= 99.5 % of the entries to 1e-3."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXT = os.path.join(ROOT, 'baseline', '_ref', 'nr_ext')
+
+
+def _ref(name):
+    so = os.path.join(EXT, name, name + '.so')
+    if not os.path.exists(so):
+        pytest.skip('reference extension not built (tools/build_ref_ext.py, build container only)')
+    spec = importlib.util.spec_from_file_location(name, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope='module')
+def scene():
+    """Projected faces of a small sphere + the forward maps of OUR rasterizer (bit-identical to the reference's, test_raster_gpu.py)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import make_scene
+    from relightable_nr_b200.dropin import neural_renderer as nr
+    from relightable_nr_b200.dropin.neural_renderer.cuda import rasterize as ours
+    dev = torch.device('cuda:0')
+    v, vt, vn, f = make_scene.uv_sphere(12, 24)
+    verts = torch.tensor(v, dtype=torch.float32, device=dev)[None]
+    faces_idx = torch.tensor(f, dtype=torch.int32, device=dev)[None]
+    is_ = 96
+    RT, _ = make_scene.spiral_pose(40)
+    K = torch.tensor([[1.2 * is_, 0, is_ / 2.0], [0, 1.2 * is_, is_ / 2.0], [0, 0, 1.0]], dtype=torch.float32, device=dev)[None]
+    R = torch.tensor(RT[:3, :3], dtype=torch.float32, device=dev)[None]
+    t = torch.tensor(RT[:3, 3], dtype=torch.float32, device=dev)[None, None]
+    vp = nr.projection(verts, K, R, t, torch.zeros(1, 5, device=dev), is_)
+    faces = nr.vertices_to_faces(vp, faces_idx).contiguous()
+    nf = faces.shape[1]
+    fim = torch.full((1, is_, is_), -1, dtype=torch.int32, device=dev)
+    wm = torch.zeros((1, is_, is_, 3), device=dev)
+    dm = torch.full((1, is_, is_), 1e5, device=dev)
+    fiv = torch.zeros((1, is_, is_, 3, 3), device=dev)
+    finv = torch.zeros((1, nf, 3, 3), device=dev)
+    ours.forward_face_index_map(faces, fim, wm, dm, fiv, finv, is_, 0.0, 1e5, 1, 1, 1)
+    assert (fim >= 0).float().mean() > 0.2
+    return dict(faces=faces, fim=fim, wm=wm, dm=dm, fiv=fiv, nf=nf, is_=is_, dev=dev)
+
+
+def test_forward_face_index_map_matches_reference_extension(scene):
+    ref = _ref('ref_rasterize')
+    s = scene
+    fim = torch.full_like(s['fim'], -1)
+    wm = torch.zeros_like(s['wm'])
+    dm = torch.full_like(s['dm'], 1e5)
+    fiv = torch.zeros_like(s['fiv'])
+    finv = torch.zeros((1, s['nf'], 3, 3), device=s['dev'])
+    ref.forward_face_index_map(s['faces'], fim, wm, dm, fiv, finv, s['is_'], 0.0, 1e5, 1, 1, 1)
+    # Face indices: identical.  Weights / depth: the product kernel evaluates the reference's arithmetic WITHOUT FMA contraction
+    # (bit-identical to the kernel bodies compiled with -ffp-contract=off, tests/test_raster_gpu.py), this nvcc build of the
+    # reference contracts multiply-adds: a few ulp apart.
+    assert torch.equal(fim, s['fim'])
+    assert (wm - s['wm']).abs().max().item() <= 2e-6
+    fgd = s['fim'] >= 0
+    assert ((dm - s['dm']).abs()[fgd] / s['dm'][fgd]).max().item() <= 1e-6 and torch.equal(dm[~fgd], s['dm'][~fgd])
+    assert torch.allclose(fiv[fgd], s['fiv'][fgd], rtol=1e-5, atol=1e-6)
+
+
+def test_texture_sampling_and_texture_gradient(scene):
+    ref = _ref('ref_rasterize')
+    from relightable_nr_b200.dropin.neural_renderer.cuda import rasterize as ours
+    s = scene
+    g = torch.Generator(device='cpu').manual_seed(0)
+    ts = 4
+    tex = torch.rand((1, s['nf'], ts, ts, ts, 3), generator=g).to(s['dev'])
+    out = {}
+    for name, mod in (('ref', ref), ('ours', ours)):
+        rgb = torch.zeros((1, s['is_'], s['is_'], 3), device=s['dev'])
+        sidx = torch.zeros((1, s['is_'], s['is_'], 8), dtype=torch.int32, device=s['dev'])
+        sw = torch.zeros((1, s['is_'], s['is_'], 8), device=s['dev'])
+        mod.forward_texture_sampling(s['faces'], tex, s['fim'], s['wm'], s['dm'], rgb, sidx, sw, s['is_'], 1e-3)
+        out[name] = (rgb, sidx, sw)
+    assert torch.equal(out['ours'][1], out['ref'][1])
+    assert (out['ours'][0] - out['ref'][0]).abs().max().item() <= 1e-5
+    assert (out['ours'][2] - out['ref'][2]).abs().max().item() <= 1e-6
+    grad_rgb = torch.randn((1, s['is_'], s['is_'], 3), generator=g).to(s['dev'])
+    gt = {}
+    for name, mod in (('ref', ref), ('ours', ours)):
+        gtex = torch.zeros_like(tex)
+        mod.backward_textures(s['fim'], out['ref'][2], out['ref'][1], grad_rgb, gtex, s['nf'])
+        gt[name] = gtex
+    assert gt['ref'].abs().max() > 0
+    assert torch.allclose(gt['ours'], gt['ref'], rtol=1e-4, atol=1e-5)
+
+
+def test_backward_depth_map(scene):
+    ref = _ref('ref_rasterize')
+    from relightable_nr_b200.dropin.neural_renderer.cuda import rasterize as ours
+    s = scene
+    gd = torch.randn((1, s['is_'], s['is_']), generator=torch.Generator().manual_seed(1)).to(s['dev'])
+    res = {}
+    for name, mod in (('ref', ref), ('ours', ours)):
+        gf = torch.zeros((1, s['nf'], 3, 3), device=s['dev'])
+        mod.backward_depth_map(s['faces'], s['dm'], s['fim'], s['fiv'], s['wm'], gd, gf, s['is_'])
+        res[name] = gf
+    assert res['ref'].abs().max() > 0
+    assert torch.allclose(res['ours'], res['ref'], rtol=1e-4, atol=1e-4 * res['ref'].abs().max().item())
+
+
+@pytest.mark.parametrize('return_rgb,return_alpha', [(1, 1), (0, 1), (1, 0)])
+def test_backward_pixel_map(scene, return_rgb, return_alpha):
+    ref = _ref('ref_rasterize')
+    from relightable_nr_b200.dropin.neural_renderer.cuda import rasterize as ours
+    s = scene
+    g = torch.Generator().manual_seed(2)
+    alpha = (s['fim'] >= 0).float().contiguous()
+    rgb = (torch.rand((1, s['is_'], s['is_'], 3), generator=g).to(s['dev']) * alpha[..., None]).contiguous()
+    grgb = torch.randn((1, s['is_'], s['is_'], 3), generator=g).to(s['dev'])
+    galpha = torch.randn((1, s['is_'], s['is_']), generator=g).to(s['dev'])
+    res = {}
+    for name, mod in (('ref', ref), ('ours', ours)):
+        gf = torch.zeros((1, s['nf'], 3, 3), device=s['dev'])
+        mod.backward_pixel_map(s['faces'], s['fim'], rgb, alpha, grgb, galpha, gf, s['is_'], 1e-3, return_rgb, return_alpha)
+        res[name] = gf
+    a, b = res['ours'], res['ref']
+    assert b.abs().max() > 0
+    ok = (a - b).abs() <= 1e-3 * b.abs().clamp(min=1.0)
+    print('backward_pixel_map(rgb=%d, alpha=%d): %.3f %% of %d entries within 1e-3, %d non-zero' % (return_rgb, return_alpha, 100 * ok.float().mean().item(),
+                                                                                                   ok.numel(), int((b != 0).sum())))
+    assert ok.float().mean().item() >= 0.995
+    assert torch.equal(a == 0, b == 0) or ((a == 0) != (b == 0)).float().mean().item() <= 0.005
+
+
+@pytest.mark.parametrize('wrapping', [0, 1, 2, 3])
+@pytest.mark.parametrize('bilinear', [1, 0])
+def test_load_textures(wrapping, bilinear):
+    ref = _ref('ref_load_textures')
+    from relightable_nr_b200.dropin.neural_renderer.cuda import load_textures as ours
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(3 + wrapping)
+    nf, ts = 37, 4
+    image = torch.rand((20, 28, 3), generator=g).to(dev)
+    lo, hi = (-0.7, 1.8) if wrapping != 3 else (0.05, 0.95)
+    # (coordinates that are exact integers are a race in the reference's in-place wrap: avoided)
+    uv = (torch.rand((nf, 3, 2), generator=g) * (hi - lo) + lo).to(dev)
+    upd = (torch.rand(nf, generator=g) > 0.3).to(torch.int32).to(dev)
+    res = {}
+    for name, fn in (('ref', ref.load_textures), ('ours', ours.load_textures)):
+        faces = uv.clone()
+        tex = torch.full((nf, ts, ts, ts, 3), -1.0, device=dev)
+        if wrapping in (0, 1, 2) or name == 'ours' or True:
+            fn(image, faces, tex, upd, wrapping, bilinear)
+        res[name] = (tex, faces)
+    assert torch.allclose(res['ours'][0], res['ref'][0], rtol=1e-5, atol=1e-5), (res['ours'][0] - res['ref'][0]).abs().max().item()
+    assert torch.allclose(res['ours'][1], res['ref'][1], rtol=0, atol=1e-6)
+    assert (res['ref'][0][upd == 0] == -1).all() and (res['ours'][0][upd == 0] == -1).all()
+
+
+def test_create_texture_image():
+    ref = _ref('ref_create_texture_image')
+    from relightable_nr_b200.dropin.neural_renderer.cuda import create_texture_image as ours
+    dev = torch.device('cuda:0')
+    nf, tsi, tso = 16, 4, 16                     # a full 4 x 4 atlas (the reference reads out of bounds for partially filled rows)
+    tex = torch.rand((nf, tsi, tsi, tsi, 3), generator=torch.Generator().manual_seed(4)).to(dev)
+    tile_w = int((nf - 1.) ** 0.5) + 1
+    tile_h = int((nf - 1.) / tile_w) + 1
+    vertices = torch.zeros((nf, 3, 2), dtype=torch.float32)
+    n = torch.arange(nf)
+    col, row = (n % tile_w).float(), (n // tile_w).float()
+    vertices[:, 0, 0] = col * tso; vertices[:, 0, 1] = row * tso
+    vertices[:, 1, 0] = col * tso; vertices[:, 1, 1] = (row + 1) * tso - 1
+    vertices[:, 2, 0] = (col + 1) * tso - 1; vertices[:, 2, 1] = (row + 1) * tso - 1
+    vertices = vertices.to(dev)
+    res = {}
+    for name, fn in (('ref', ref.create_texture_image), ('ours', ours.create_texture_image)):
+        img = torch.zeros((tile_h * tso, tile_w * tso, 3), device=dev)
+        fn(vertices, tex, img, 1e-5)
+        res[name] = img
+    assert res['ref'].abs().max() > 0
+    assert torch.allclose(res['ours'], res['ref'], rtol=1e-5, atol=1e-5), (res['ours'] - res['ref']).abs().max().item()

@@ -145,11 +145,23 @@ def test_rasterizer_module_matches_oracle():
     _check_forward(out, Rr.rasterizer_forward(mesh, size, K, pose), 1e-5, 5e-4, 5e-3)
 
 
-def test_extension_guards_and_out_of_scope_entry_points():
+def test_extension_guards():
+    """CHECK_CUDA / CHECK_CONTIGUOUS of the extension (rasterize_cuda.cpp:66-68): every entry point refuses CPU tensors loudly
+    (their arithmetic is checked against the reference's own kernels in tests/test_b2_gpu.py)."""
     from relightable_nr_b200.dropin.neural_renderer.cuda import rasterize as ext, load_textures, create_texture_image
+    z = torch.zeros(1, 1, 3, 3)
+    zi = torch.zeros(1, 8, 8, dtype=torch.int32)
     with pytest.raises(RuntimeError):
-        ext.forward_face_index_map(torch.zeros(1, 1, 3, 3), None, None, None, None, None, 8, 0.0, 1.0, 0, 0, 0)   # CPU tensor
-    for fn in (ext.forward_texture_sampling, ext.backward_pixel_map, ext.backward_textures, ext.backward_depth_map,
-               load_textures.load_textures, create_texture_image.create_texture_image):
-        with pytest.raises(NotImplementedError):
-            fn()
+        ext.forward_face_index_map(z, None, None, None, None, None, 8, 0.0, 1.0, 0, 0, 0)   # CPU tensor
+    with pytest.raises(RuntimeError):
+        ext.forward_texture_sampling(z, z, zi, z, z, z, zi, z, 8, 1e-3)
+    with pytest.raises(RuntimeError):
+        ext.backward_pixel_map(z, zi, z, z, z, z, z, 8, 1e-3, 1, 1)
+    with pytest.raises(RuntimeError):
+        ext.backward_textures(zi, z, zi, z, z, 1)
+    with pytest.raises(RuntimeError):
+        ext.backward_depth_map(z, z, zi, z, z, z, z, 8)
+    with pytest.raises(RuntimeError):
+        load_textures.load_textures(z, z, z, zi, 0, 1)
+    with pytest.raises(RuntimeError):
+        create_texture_image.create_texture_image(z, z, z, 1e-5)

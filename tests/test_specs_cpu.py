@@ -39,3 +39,22 @@ def test_dnr_flops():
 
 def test_quarter_resolution_scales_flops_by_four():
     assert abs(_gflop(_specs(108, 78, 64, 256)) * 4 - _gflop(_specs(108, 78, 64))) < 1e-6
+
+
+def test_gcn_lib_sparse_names_and_scatter_path():
+    """gcn_lib.sparse exposes the reference's class / function names (gcn_lib/sparse/__init__.py star imports) and its edge-list
+    EdgConv equals a naive per-node loop on CPU tensors (the scatter path; the fused CUDA path is checked in tests/test_gcn_gpu.py)."""
+    import torch
+    from relightable_nr_b200.dropin.gcn_lib import sparse
+    for name in ('MRConv', 'EdgConv', 'GraphConv', 'DynConv', 'ResDynBlock', 'DenseDynBlock', 'Dilated', 'DilatedKnnGraph', 'pairwise_distance',
+                 'knn_matrix', 'knn_graph_matrix', 'act_layer', 'norm_layer', 'MultiSeq', 'MLP'):
+        assert hasattr(sparse, name), name
+    torch.manual_seed(0)
+    conv = sparse.EdgConv(5, 7, 'relu', None, True)
+    x = torch.randn(12, 5)
+    ei = sparse.knn_graph_matrix(x, 3, torch.zeros(12, dtype=torch.long))
+    out = conv(x, ei)
+    for i in range(12):
+        js = ei[0][ei[1] == i]
+        want = torch.stack([conv.nn(torch.cat([x[i], x[j] - x[i]])[None])[0] for j in js]).max(0)[0]
+        assert torch.allclose(out[i], want, atol=1e-6)
