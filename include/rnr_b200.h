@@ -488,6 +488,15 @@ int rnr_nr_load_textures(const float* image, float* faces, float* textures, cons
 int rnr_nr_create_texture_image(const float* vertices_all, const float* textures, float* image, int64_t image_numel, int num_faces,
                                 int texture_size_in, int texture_size_out, int tile_width, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Validation metrics on the device: metric.py:19-84 (masked MAE / MSE / PSNR inputs)           */
+/*   box [N,4] int32 pre-set to {W,-1,H,-1}, cnt [N] u64 and sums [N,4] f64 pre-zeroed:          */
+/*   box = bounding box of mask == 1, cnt = its pixel count, sums = {sum|d|, sum d^2} over the   */
+/*   image and over the box with d = (est - gt) where mask == 1, 0 elsewhere                     */
+/* ------------------------------------------------------------------------------------------ */
+int rnr_metric_sums(const float* est, const float* gt, const float* mask, int N, int C, int H, int W, int* box,
+                    unsigned long long* cnt, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

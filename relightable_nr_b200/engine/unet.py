@@ -140,6 +140,7 @@ class _WPrep:
     tapoff: torch.Tensor    # int32 device
     tapoff_host: Tuple[int, ...] = ()
     chunked: int = 0        # 1: Wmat columns are [chunk of 64 channels][tap][64] (halo-kernel order)
+    ld: int = 0             # destination row pitch in elements (0: ntaps * cpad) -- a job may fill one source's column block
 
 
 @dataclass
@@ -388,6 +389,7 @@ class UNetEngine:
             j.dst_dtype, j.nr, j.nr_pad, j.nc, j.cpad, j.ntaps = w.dtype, w.nr, w.nr_pad, w.nc, w.cpad, w.ntaps
             j.s_r, j.s_c = w.s_r, w.s_c
             j.chunked = w.chunked
+            j.ld = w.ld
             for t, o in enumerate(w.tapoff.host):
                 j.tapoff[t] = o
         h = C.c_void_p()
@@ -400,15 +402,22 @@ class UNetEngine:
         adt_t, gdt_t = _TORCH_DT[self.act_dt], _TORCH_DT[self.grad_dt]
         srcs = [self.acts[s] for s in sp.src]
         cpads = [t.C for t in srcs]           # stored channel counts (input layer is padded)
+        # Channel counts that are not multiples of 64 (DNR at nf0 = 80: 80 / 160; the 16-channel DNR input; test-sized nets): the
+        # K loop still runs in 64-channel chunks -- the TMA box simply reaches past the tensor's last channel and the hardware
+        # zero-fills what is out of bounds, so the activations stay UNPADDED in HBM and every layer runs on the halo kernel.  Only
+        # the weight matrix carries the (zero) padding columns.  RNR_CONV_OOB=0 restores exact 16 / 32-channel chunks (per-tap kernel).
+        oob = (self.impl == 1 and any(c % 64 for c in cpads) and all(c % 8 == 0 for c in cpads)
+               and os.environ.get('RNR_CONV_OOB', '1') != '0')
+        kpads = [_rup(c, 64) for c in cpads] if oob else list(cpads)
         cin_tot = sum(sp.cin)
-        cpad_tot = sum(cpads)
+        cpad_tot = sum(kpads)
         final = sp.dst == 'out'
         Ho, Wo = sp.Ho, sp.Wo
         cout = sp.cout
         ld_out = self.out_ld if final else cout
         k = 3 if sp.kind == 'c3' else 4
         kk = k * k
-        bk = self._bk_for(cpads)
+        bk = 64 if oob else self._bk_for(cpads)
         n_rows = _rup(cout, 16)
         epi = 0
         bias_t = None
@@ -427,15 +436,29 @@ class UNetEngine:
             ks = []
             if chunked:
                 for si in range(len(srcs)):
-                    for c0 in range(0, cpads[si], bk):
+                    for c0 in range(0, kpads[si], bk):
                         for (vidx, dx, dy) in taps:
                             ks.append((vidx[si], c0, dx, dy))
                 return ks
             for (vidx, dx, dy) in taps:
                 for si in range(len(srcs)):
-                    for c0 in range(0, cpads[si], bk):
+                    for c0 in range(0, kpads[si], bk):
                         ks.append((vidx[si], c0, dx, dy))
             return ks
+
+        def fwd_wprep(wm, ntaps, s_r, s_c, tapoffs):
+            """Weight-preparation job(s) of one forward matrix ``wm`` [rows, ntaps * cpad_tot].  With out-of-bounds chunks every
+            source owns its own (padded) column block [chunks of the source][tap][64]: one job per source, row pitch = the matrix."""
+            toff = self._tapoff(tapoffs)
+            if not oob or len(srcs) == 1:
+                return [_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, ntaps, s_r, s_c, toff, chunked=chunked)]
+            jobs, ci0, col0 = [], 0, 0
+            for si in range(len(srcs)):
+                jobs.append(_WPrep(sp.w_key, ci0 * s_c, wm[:, col0:], self.act_dt, cout, n_rows, sp.cin[si], kpads[si], ntaps, s_r, s_c, toff,
+                                   chunked=chunked, ld=ntaps * cpad_tot))
+                ci0 += sp.cin[si]
+                col0 += ntaps * kpads[si]
+            return jobs
 
         # ------------------------------ forward ------------------------------
         if sp.kind == 'c3':
@@ -443,8 +466,7 @@ class UNetEngine:
             taps = [([si for si in range(len(srcs))], kw, kh) for kh in range(3) for kw in range(3)]
             tapoffs = [kh * 3 + kw for kh in range(3) for kw in range(3)]
             wm = self._alloc((n_rows, 9 * cpad_tot), adt_t, zero=True)
-            st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 9,
-                                       cin_tot * 9, 9, self._tapoff(tapoffs), chunked=chunked))
+            st.wprep_fwd += fwd_wprep(wm, 9, cin_tot * 9, 9, tapoffs)
             th, tw = tile_shape(Wo)
             tiles = max(N * -(-Ho // th) * -(-Wo // tw), 148)      # rows of the partial-sum buffer: one per tile or per CTA
             if epi & EPI_STATS:
@@ -466,8 +488,7 @@ class UNetEngine:
                             taps.append(([si * 4 + p * 2 + q for si in range(len(srcs))], b, a))
                             tapoffs.append(kh * 4 + kw)
             wm = self._alloc((n_rows, 16 * cpad_tot), adt_t, zero=True)
-            st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 16,
-                                       cin_tot * 16, 16, self._tapoff(tapoffs), chunked=chunked))
+            st.wprep_fwd += fwd_wprep(wm, 16, cin_tot * 16, 16, tapoffs)
             th, tw = tile_shape(Wo)
             tiles = max(N * -(-Ho // th) * -(-Wo // tw), 148)
             if epi & EPI_STATS:
@@ -499,8 +520,7 @@ class UNetEngine:
                     sidx = ph * 2 + pw
                     wm = wm_all[sidx * n_rows:(sidx + 1) * n_rows]
                     # weight [Cin, Cout, 4, 4]: rows = co (stride 16), cols = ci (stride Cout*16)
-                    st.wprep_fwd.append(_WPrep(sp.w_key, 0, wm, self.act_dt, cout, n_rows, cin_tot, cpad_tot, 4,
-                                               16, cout * 16, self._tapoff(tapoffs), chunked=chunked))
+                    st.wprep_fwd += fwd_wprep(wm, 4, 16, cout * 16, tapoffs)
                     probs.append(self._conv_problem(
                         views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Hi, Wi, st.raw, F32 if final else self.raw_dt,
                         (Ho * Wo * ld_out, Wo * ld_out, ld_out), (2, 2, ph, pw), epi, bias_t, st.stats, cout, self.impl, defer=True))
@@ -621,7 +641,9 @@ class UNetEngine:
         nci_pad = _rup(nci, 16)
         Hi, Wi = sp.H, sp.W
         gC = G.C
-        gbk = self._bk_for([gC])
+        g_oob = (self.impl == 1 and gC % 64 != 0 and gC % 8 == 0 and os.environ.get('RNR_CONV_OOB', '1') != '0')
+        gbk = 64 if g_oob else self._bk_for([gC])
+        gK = _rup(gC, 64) if g_oob else gC            # K extent of the gradient operand (chunks past gC are zero-filled by the TMA)
         if sp.kind == 'c3':
             # gxp[ih,iw,ci] = sum_{kh,kw,co} Gp[ih-kh+1, iw-kw+1, co] W[co,ci,kh,kw]   over the padded input plane
             Hp, Wp = Hi + 2, Wi + 2
@@ -629,11 +651,11 @@ class UNetEngine:
             st.gx_fold, st.gx_ld = True, nci_pad
             gch = 1 if gbk == 64 else 0
             tapl = [(1 - kw, 1 - kh, kh * 3 + kw) for kh in range(3) for kw in range(3)]
-            ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gC, gbk, gch)
+            ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gK, gbk, gch)
             tapoffs = [o for (_, _, o) in tapl]
-            wm = self._alloc((nci_pad, 9 * gC), gdt_t, zero=True)
+            wm = self._alloc((nci_pad, 9 * gK), gdt_t, zero=True)
             # rows = ci (stride 9), cols = co (stride Cin*9)
-            st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 9, wm, self.grad_dt, nci, nci_pad, cout, gC, 9, 9, cin_tot * 9,
+            st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 9, wm, self.grad_dt, nci, nci_pad, cout, gK, 9, 9, cin_tot * 9,
                                          self._tapoff(tapoffs), chunked=gch))
             st.dgrad_plans.append(self._conv_problem(
                 [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp, Wp, st.gx, self.grad_dt,
@@ -642,17 +664,17 @@ class UNetEngine:
             Hp, Wp = Hi + 2, Wi + 2
             st.gx = self._alloc((N, Hp, Wp, nci_pad), gdt_t, zero=True)
             st.gx_fold, st.gx_ld = True, nci_pad
-            wm_all = self._alloc((4 * nci_pad, 4 * gC), gdt_t, zero=True)
+            wm_all = self._alloc((4 * nci_pad, 4 * gK), gdt_t, zero=True)
             probs = []
             for ph in range(2):
                 for pw in range(2):
                     gch = 1 if gbk == 64 else 0
                     tapl = [(1 - b, 1 - a, (2 * a + ph) * 4 + (2 * b + pw)) for a in range(2) for b in range(2)]
-                    ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gC, gbk, gch)
+                    ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gK, gbk, gch)
                     tapoffs = [o for (_, _, o) in tapl]
                     sidx = ph * 2 + pw
                     wm = wm_all[sidx * nci_pad:(sidx + 1) * nci_pad]
-                    st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 16, wm, self.grad_dt, nci, nci_pad, cout, gC, 4, 16,
+                    st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 16, wm, self.grad_dt, nci, nci_pad, cout, gK, 4, 16,
                                                  cin_tot * 16, self._tapoff(tapoffs), chunked=gch))
                     probs.append(self._conv_problem(
                         [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp // 2, Wp // 2, st.gx, self.grad_dt,
@@ -671,11 +693,11 @@ class UNetEngine:
             gch = 1 if gbk == 64 else 0
             # parity-major tap order: the 4 taps reading one parity view of G are adjacent
             tapl = [(p * 2 + q, b, a, (2 * a + p) * 4 + (2 * b + q)) for p in range(2) for q in range(2) for a in range(2) for b in range(2)]
-            ks = self._order_ksteps([(v, dx, dy) for (v, dx, dy, _) in tapl], gC, gbk, gch)
+            ks = self._order_ksteps([(v, dx, dy) for (v, dx, dy, _) in tapl], gK, gbk, gch)
             tapoffs = [o for (_, _, _, o) in tapl]
-            wm = self._alloc((nci_pad, 16 * gC), gdt_t, zero=True)
+            wm = self._alloc((nci_pad, 16 * gK), gdt_t, zero=True)
             # weight [Cin, Cout, 4,4]: rows = ci (stride Cout*16), cols = co (stride 16)
-            st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * cout * 16, wm, self.grad_dt, nci, nci_pad, cout, gC, 16, cout * 16, 16,
+            st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * cout * 16, wm, self.grad_dt, nci, nci_pad, cout, gK, 16, cout * 16, 16,
                                          self._tapoff(tapoffs), chunked=gch))
             st.dgrad_plans.append(self._conv_problem(
                 gviews, ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hi, Wi, st.gx, self.grad_dt,
@@ -737,6 +759,8 @@ class UNetEngine:
 
     def _wprep(self, items: List[_WPrep], s):
         for w in items:
+            if w.ld:
+                raise NotImplementedError('per-matrix weight prep has no row pitch: use the batched plan')
             src = self.params[w.src_key]
             _lib.check(self.L.rnr_weight_prep(src.data_ptr() + 4 * w.src_off, w.dst.data_ptr(), w.dtype, w.nr, w.nr_pad,
                                               w.nc, w.cpad, w.ntaps, w.s_r, w.s_c, w.tapoff.data_ptr(), w.chunked, s), 'rnr_weight_prep')

@@ -162,6 +162,64 @@ def test_precompute_outputs_match_the_reference_functions(scene):
         assert q <= tol, (name, q)
 
 
+def test_one_pass_precompute_equals_the_script_output_and_feeds_the_step(scene, tmp_path):
+    """relightable_nr_b200.precompute.ViewPrecompute (the whole of precompute.py:140-253 as one device pass, no
+    numpy / .mat round trips) produces the maps the UNCHANGED script wrote for the same cameras -- equal to 1e-6 (same kernels; the
+    script's copy went through float64 .mat files and an 8-bit alpha PNG) -- and a PackedViewCache of them feeds a training step."""
+    import scipy.io
+    import cv2
+    from relightable_nr_b200.precompute import PackedViewCache, ViewPrecompute
+    from relightable_nr_b200.pipeline import RNRPipeline
+    root = scene['root']
+    hi = os.path.join(root, 'precomp_mesh', 'resol_%d' % SIZE)
+    pre = ViewPrecompute(os.path.join(root, 'mesh.obj'), SIZE, global_RT=torch.eye(4))
+    vws = _views(os.path.join(root, 'calib.mat'), SIZE)
+    proj = torch.cat([v['proj'] for v in vws]).cuda()
+    pose = torch.cat([v['pose'] for v in vws]).cuda()
+    maps = pre.maps(proj, pose, with_raster=True)
+    assert maps['uv_map'].shape == (scene['n_views'], SIZE, SIZE, 2)
+    for i in range(scene['n_views']):
+        name = '%05d' % i
+        for key in ('TBN_map', 'uv_map', 'normal_map', 'view_dir_map', 'view_dir_map_tangent', 'sh_basis_map', 'reflect_dir_map'):
+            want = scipy.io.loadmat(os.path.join(hi, key, name + '.mat'))[key].astype(np.float32)
+            if key == 'uv_map':
+                want = want - np.floor(want)                              # dataio.py:228
+            err = np.abs(maps[key][i].cpu().numpy() - want).max()
+            assert err <= 1e-6, (key, i, err)
+        alpha = cv2.imread(os.path.join(hi, 'alpha_map', name + '.png'), cv2.IMREAD_UNCHANGED).astype(np.float32) / 255.0
+        assert np.array_equal(maps['alpha_map'][i].cpu().numpy(), alpha)
+    # the reference layout written by the pass itself is readable by the reference's own dataio.ViewDataset
+    out_dir = str(tmp_path / 'precomp_mesh')
+    pre.write_reference_layout(out_dir, ['%05d' % i for i in range(scene['n_views'])], maps)
+    sys.path.insert(0, REF)
+    ref_import.import_reference()
+    import dataio
+    ds = dataio.ViewDataset(root_dir=root, img_dir=os.path.join(root, 'rgb0') + '/', calib_path=os.path.join(root, 'calib.mat'), calib_format='convert',
+                            img_size=[SIZE, SIZE], sampling_pattern='all', load_precompute=True, precomp_high_dir=out_dir, precomp_low_dir=out_dir)
+    item = ds.read_view(1)
+    for key in ('TBN_map', 'uv_map', 'normal_map', 'view_dir_map', 'view_dir_map_tangent', 'sh_basis_map', 'alpha_map'):
+        assert np.abs(item[key].numpy().astype(np.float32) - maps[key][1].cpu().numpy()).max() <= 1e-6, key
+    # packed cache -> pinned staging -> device -> one fused training step per view
+    keys = ('uv_map', 'sh_basis_map', 'normal_map', 'view_dir_map', 'view_dir_map_tangent', 'TBN_map', 'alpha_map')
+    views = []
+    for i in range(scene['n_views']):
+        v = {k: maps[k][i] for k in keys}
+        v['img_gt'] = item['img_gt'] if i == 1 else ds.read_view(i)['img_gt']
+        views.append(v)
+    cache = PackedViewCache.write(str(tmp_path / 'views.rnrcache'), views)
+    pipe = RNRPipeline(device='cuda:0', img_size=SIZE, dropout=False)
+    copy_stream = torch.cuda.Stream()
+    losses = []
+    for it in range(4):
+        v = cache.load(it % len(cache), device='cuda:0', stream=copy_stream, slot=it)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        assert torch.equal(v['uv_map'][0], maps['uv_map'][it % len(cache)])
+        losses.append(pipe.train_step(v, fused=True)[0].item())
+        torch.cuda.synchronize()
+    print('losses from the packed cache:', losses)
+    assert all(np.isfinite(losses))
+
+
 def test_train_rnr_then_test_rnr(scene):
     root = scene['root']
     out = _run('train_rnr.py', '--data_root', root, '--gpu_id', '0', '--img_size', SIZE, '--lp_dir', '_/light_probe',

@@ -58,3 +58,28 @@ def test_gcn_lib_sparse_names_and_scatter_path():
         js = ei[0][ei[1] == i]
         want = torch.stack([conv.nn(torch.cat([x[i], x[j] - x[i]])[None])[0] for j in js]).max(0)[0]
         assert torch.allclose(out[i], want, atol=1e-6)
+
+
+def test_packed_view_cache_round_trip(tmp_path):
+    """relightable_nr_b200.precompute.PackedViewCache: every map of every view survives the one-file cache bit for bit (host side;
+    the pinned / device staging is exercised in tests/test_scripts_gpu.py)."""
+    import numpy as np
+    import torch
+    from relightable_nr_b200.precompute import PackedViewCache
+    rng = np.random.RandomState(0)
+    views = [{'uv_map': torch.from_numpy(rng.rand(6, 5, 2).astype(np.float32)), 'alpha_map': torch.from_numpy((rng.rand(6, 5) > 0.5).astype(np.float32)),
+              'TBN_map': torch.from_numpy(rng.randn(6, 5, 3, 3).astype(np.float32)), 'idx': np.array(i, dtype=np.int64)} for i in range(3)]
+    cache = PackedViewCache.write(str(tmp_path / 'views.rnrcache'), views, names=['a', 'b', 'c'])
+    again = PackedViewCache(str(tmp_path / 'views.rnrcache'))
+    assert len(again) == 3 and again.header['names'] == ['a', 'b', 'c']
+    for i, v in enumerate(views):
+        got = again.view_numpy(i)
+        assert set(got) == set(v)
+        for k in v:
+            want = v[k].numpy() if isinstance(v[k], torch.Tensor) else v[k]
+            assert got[k].dtype == want.dtype and np.array_equal(got[k], want), k
+    with open(str(tmp_path / 'junk'), 'wb') as fh:
+        fh.write(b'not a cache at all')
+    import pytest
+    with pytest.raises(ValueError):
+        PackedViewCache(str(tmp_path / 'junk'))
