@@ -67,6 +67,11 @@ class UnetRunner:
         #: channels of the input that need a gradient (None = all).  network.RenderingNet narrows this to the
         #: neural-texture channels, the only differentiable part of the 108-channel RNR input.
         self.input_grad_range = None
+        #: how the Dropout2d channel masks are drawn.  'fast': one uniform draw for all 21 live layers.  'reference': one
+        #: bernoulli_ per Dropout2d call of the reference's forward, IN ITS ORDER -- including the 22 calls of the dead GCN pass of
+        #: the outermost block (pytorch_prototyping.py:407-415) -- from torch's CUDA generator, so that under
+        #: the same torch.manual_seed the live layers get bit-identical masks to the reference module running on the same GPU.
+        self.rng_order = 'fast'
 
     def _engine(self, x, need_backward, apply_tanh):
         unet = self._unet()
@@ -154,7 +159,32 @@ class UnetRunner:
             if isinstance(m, torch.nn.Dropout2d) and (bool(m.training) != bool(drop_mod.training) or float(m.p) != float(drop_mod.p)):
                 raise NotImplementedError('Unet: Dropout2d modules differ in mode or p (%s)' % name)
         drop_masks = None
-        if drop_mod.training and drop_mod.p > 0:
+        if drop_mod.training and drop_mod.p > 0 and self.rng_order == 'reference':
+            p = float(drop_mod.p)
+
+            def draw(c):
+                # torch's feature_dropout: noise = empty([N, C, 1, 1]).bernoulli_(1 - p).div_(1 - p)
+                return torch.empty((eng.N, c, 1, 1), dtype=torch.float32, device=eng.device).bernoulli_(1 - p).div_(1 - p).view(eng.N, c).contiguous()
+
+            cout = {sp.name: sp.cout for sp in eng.specs}
+            nd = unet._cfg['num_down']
+            body = ['b0.down1', 'b0.down2']
+            inner = []
+            for i in range(1, nd):
+                inner += ['b%d.down1' % i, 'b%d.down2' % i]
+            for i in reversed(range(1, nd)):
+                inner += ['b%d.up1' % i, 'b%d.up2' % i]
+            tail = ['b0.up1', 'b0.up2']
+            drop_masks = {'in': draw(cout['in'])}
+            if unet.use_gcn:
+                # the dead pass of the outermost block: down (2 draws), fuse (2: its DownBlock keeps inner_nc + out_channels_gcn
+                # channels in the middle), the whole submodule, up (2) -- drawn and discarded, only to advance the generator
+                fuse_mid, fuse_out = unet.unet_block.fuse.net[1].out_channels, unet.unet_block.fuse.net[6].out_channels
+                for c in [cout[n] for n in body] + [fuse_mid, fuse_out] + [cout[n] for n in inner] + [cout[n] for n in tail]:
+                    draw(c)
+            for n in body + inner + tail:
+                drop_masks[n] = draw(cout[n])
+        elif drop_mod.training and drop_mod.p > 0:
             p = float(drop_mod.p)
             names = [sp.name for sp in eng.specs if sp.drop and sp.dst != 'out']
             chans = [eng.layers[n].spec.cout for n in names]

@@ -127,3 +127,38 @@ def test_batched_weight_prep_is_bit_identical_to_per_layer():
     torch.cuda.synchronize()
     for w, r in zip(items, ref):
         assert torch.equal(w.dst.view(torch.int16), r.view(torch.int16)), (w.src_key, w.ntaps, w.s_r, w.s_c)
+
+
+@pytest.mark.parametrize('use_gcn', [True, False])
+def test_dropout_reference_rng_order_matches_the_real_module(use_gcn):
+    """Dropout ON (the training configuration, train_rnr.py:398-405): with ``rng_order = 'reference'`` the drop-in draws one
+    bernoulli per Dropout2d call of the reference's forward in the reference's order -- including the 22 draws of the dead GCN pass
+     -- so that under the same torch.manual_seed its output equals the REAL reference module's (staged copy,
+    run on the same GPU, TF32 off): PSNR >= 50 dB.  A single wrong draw would put the two ~25 dB apart (checked: the 'fast' order is)."""
+    from tests.golden import ref_import
+    if not ref_import.available():
+        pytest.skip('reference not staged')
+    ref = ref_import.import_reference()
+    from relightable_nr_b200.dropin import network
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    kw = dict(nf0=16, in_channels=20, out_channels=6, num_down_unet=5, use_gcn=use_gcn)
+    ref_net = ref.network.RenderingNet(**kw).cuda().train()
+    ours = network.RenderingNet(**kw).cuda().train()
+    ours.load_state_dict(ref_net.state_dict(), strict=True)
+    x = torch.randn(2, 20, 64, 64, device='cuda')
+    v_fea = torch.zeros(2, 512, device='cuda')
+    with torch.no_grad():
+        torch.manual_seed(1234)
+        want = ref_net(x, v_fea if use_gcn else None)
+        ours.net._runner.rng_order = 'reference'
+        torch.manual_seed(1234)
+        got = ours(x, None)
+        ours.net._runner.rng_order = 'fast'
+        torch.manual_seed(1234)
+        other = ours(x, None)
+    p, p_fast = psnr(got * 0.5 + 0.5, want * 0.5 + 0.5), psnr(other * 0.5 + 0.5, want * 0.5 + 0.5)
+    print('dropout on, use_gcn=%s: PSNR vs the real module %.1f dB with the reference draw order, %.1f dB with the fast order' % (use_gcn, p, p_fast))
+    assert p >= 50.0
+    assert p_fast < 45.0, 'the two draw orders must differ for this test to mean anything'
