@@ -191,6 +191,20 @@ int  rnr_wgrad_unpack_run(const rnr_wunpack_plan_t* plan, void* stream);
 /*   (fused-Adam arithmetic: m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2;                        */
 /*    p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)), step counter resident on the device   */
 /* ------------------------------------------------------------------------------------------ */
+/* A 16-bit GEMM matrix family re-derived from an updated conv weight inside the optimiser pass (what rnr_wprep_run produces):
+ * `nsub` sub-matrices of `sub_rows` rows stacked row-wise behind `base` (the output-parity sub-problems of a stride-2 layer),
+ * columns chunk-major [64-channel chunk][dst tap][64].  inv[t] = s*16 + k places source tap t (kh*KW + kw) at tap slot k of
+ * sub-matrix s (-1: unused).  Forward family: row = output channel, column channel = input channel.  Data-gradient family:
+ * row = input channel - r0 for r0 <= ci < r1, column channel = output channel.  base = NULL: family not produced here. */
+typedef struct {
+    void*        base;
+    int64_t      ld;           /* row pitch in elements */
+    int32_t      dtype;        /* RNR_F16 / RNR_BF16 */
+    int32_t      ntaps;        /* tap slots per sub-matrix */
+    int32_t      sub_rows;
+    int32_t      r0, r1;       /* data-gradient family only */
+    int8_t       inv[16];
+} rnr_wmat_t;
 typedef struct {               /* a conv weight whose gradient sits in GEMM order (see rnr_wunpack_job_t) */
     float*       scratch;      /* [ntaps, cout, cin] gradient; re-zeroed by the pass when zero_grad */
     float*       p;            /* fp32 master weight, parameter layout: (co, ci, t) at co*s_co + ci*s_ci + t */
@@ -199,6 +213,7 @@ typedef struct {               /* a conv weight whose gradient sits in GEMM orde
     float*       gdst;         /* optional: also write the un-transposed gradient here (NULL: never materialised) */
     int32_t      cout, cin, ntaps;
     int64_t      s_co, s_ci;
+    rnr_wmat_t   fwd, dgrad;   /* next step's GEMM matrices, written from the updated weight in the same pass (base NULL: skip) */
 } rnr_adam_wjob_t;
 typedef struct {               /* a plain tensor (bias, BatchNorm affine, texture level, SH coefficients) */
     float*       p;

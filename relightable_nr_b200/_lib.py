@@ -64,9 +64,15 @@ class WUnpackJob(C.Structure):
                 ("s_co", C.c_int64), ("s_ci", C.c_int64)]
 
 
+class WMat(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("ld", C.c_int64), ("dtype", C.c_int32), ("ntaps", C.c_int32), ("sub_rows", C.c_int32),
+                ("r0", C.c_int32), ("r1", C.c_int32), ("inv", C.c_int8 * 16)]
+
+
 class AdamWJob(C.Structure):
     _fields_ = [("scratch", C.c_void_p), ("p", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("gdst", C.c_void_p),
-                ("cout", C.c_int32), ("cin", C.c_int32), ("ntaps", C.c_int32), ("s_co", C.c_int64), ("s_ci", C.c_int64)]
+                ("cout", C.c_int32), ("cin", C.c_int32), ("ntaps", C.c_int32), ("s_co", C.c_int64), ("s_ci", C.c_int64),
+                ("fwd", WMat), ("dgrad", WMat)]
 
 
 class AdamJob(C.Structure):

@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int CB = 64, MAXT = 16, UCO = 4;
+constexpr int CB = 64, MAXT = 16, UCO = 8;
 
 struct AdamHyper {
     float lr, beta1, beta2, eps, gscale;
@@ -39,6 +39,13 @@ __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& 
     p -= step_size * (m / denom);
 }
 
+struct WMat {
+    void* base;
+    int64_t ld;
+    int32_t dtype, ntaps, sub_rows, r0, r1;
+    int8_t inv[16];
+};
+
 struct AdamWJob {
     float* scratch;        // [ntaps][cout][cin]
     float* p;              // parameter layout: element (co, ci, t) at co*s_co + ci*s_ci + t
@@ -48,46 +55,100 @@ struct AdamWJob {
     int32_t cout, cin, ntaps, tiles_c;
     int64_t s_co, s_ci;
     int32_t blk0, nblk;
+    WMat fwd, dgrad;       // 16-bit GEMM matrices of the NEXT step, written from the updated weight (base nullptr: not here)
 };
 
+// Block = 8 output channels x one 64-input-channel chunk x all taps of one conv weight.
+//   1. gradient tile from the GEMM-order scratch (re-zeroed on the way)            -> shared memory [co][tap][ci]
+//   2. Adam in parameter layout (contiguous runs of p / m / v); the updated weight replaces the gradient in the tile
+//   3. forward GEMM matrix:       row co, columns [ci chunk][tap slot][64 ci]      -> 128-byte runs, 16-byte stores
+//   4. data-gradient GEMM matrix: row ci, columns [co chunk][tap slot][64 co]      -> the block's 8 co = one 16-byte store per (ci, tap)
 __global__ void __launch_bounds__(256) adam_wunpack_kernel(const AdamWJob* __restrict__ jobs, const int* __restrict__ blk2job,
                                                          const float* __restrict__ step, const AdamHyper h, int zero_src) {
     __shared__ float tile[UCO][MAXT][CB + 1];
     const AdamWJob& J = jobs[blk2job[blockIdx.x]];
     const int local = blockIdx.x - J.blk0;
     const int cog = local / J.tiles_c, c0 = (local - cog * J.tiles_c) * CB;
-    const int r = threadIdx.x >> 6, cc = threadIdx.x & 63;     // thread = (co row of the block, input channel of the chunk)
-    const int co = cog * UCO + r;
+    const int rq = threadIdx.x >> 6, cc = threadIdx.x & 63;    // thread = (co row of the block modulo 4, input channel of the chunk)
     const int nc = min(CB, J.cin - c0);
     const int ntaps = J.ntaps;
     float step_size, bc2_sqrt;
     bias_corrections(step, h, step_size, bc2_sqrt);
-    if (co < J.cout && cc < nc) {
-        float* sp = J.scratch + (int64_t)co * J.cin + c0 + cc;
-        const int64_t tstride = (int64_t)J.cout * J.cin;
-        float g[MAXT];
+    // ---- 1. gradient tile ----
 #pragma unroll
-        for (int t = 0; t < MAXT; t++) g[t] = (t < ntaps) ? __ldcs(sp + t * tstride) : 0.f;
+    for (int half = 0; half < UCO / 4; half++) {
+        const int r = rq + 4 * half, co = cog * UCO + r;
+        if (co < J.cout && cc < nc) {
+            float* sp = J.scratch + (int64_t)co * J.cin + c0 + cc;
+            const int64_t tstride = (int64_t)J.cout * J.cin;
+            float g[MAXT];
 #pragma unroll
-        for (int t = 0; t < MAXT; t++)
-            if (t < ntaps) {
-                tile[r][t][cc] = g[t] * h.gscale;
-                if (zero_src) __stcs(sp + t * tstride, 0.f);
-            }
+            for (int t = 0; t < MAXT; t++) g[t] = (t < ntaps) ? __ldcs(sp + t * tstride) : 0.f;
+#pragma unroll
+            for (int t = 0; t < MAXT; t++)
+                if (t < ntaps) {
+                    tile[r][t][cc] = g[t] * h.gscale;
+                    if (zero_src) __stcs(sp + t * tstride, 0.f);
+                }
+        } else {
+#pragma unroll
+            for (int t = 0; t < MAXT; t++)
+                if (t < ntaps) tile[r][t][cc] = 0.f;          // padding rows / channels read as zero weights below
+        }
     }
     __syncthreads();
-    if (co < J.cout) {
-        const unsigned magic = (65536u + ntaps - 1) / ntaps;       // j / ntaps for j < 1024, ntaps <= 16: exact
-        const int64_t base = (int64_t)co * J.s_co + (int64_t)c0 * J.s_ci;
-        const int run = nc * ntaps;
-        for (int j = cc; j < run; j += 64) {
-            const int ci = (int)(((unsigned)j * magic) >> 16), t = j - ci * ntaps;
-            const int64_t idx = base + (int64_t)ci * J.s_ci + t;
-            const float g = tile[r][t][ci];
-            float p = J.p[idx], m = J.m[idx], v = J.v[idx];
-            adam_update(p, g, m, v, h, step_size, bc2_sqrt);
-            J.p[idx] = p; J.m[idx] = m; J.v[idx] = v;
-            if (J.gdst) J.gdst[idx] = g;
+    // ---- 2. Adam in parameter layout ----
+    const unsigned magic = (65536u + ntaps - 1) / ntaps;       // j / ntaps for j < 1024, ntaps <= 16: exact
+#pragma unroll
+    for (int half = 0; half < UCO / 4; half++) {
+        const int r = rq + 4 * half, co = cog * UCO + r;
+        if (co < J.cout) {
+            const int64_t base = (int64_t)co * J.s_co + (int64_t)c0 * J.s_ci;
+            const int run = nc * ntaps;
+            for (int j = cc; j < run; j += 64) {
+                const int ci = (int)(((unsigned)j * magic) >> 16), t = j - ci * ntaps;
+                const int64_t idx = base + (int64_t)ci * J.s_ci + t;
+                const float g = tile[r][t][ci];
+                float p = J.p[idx], m = J.m[idx], v = J.v[idx];
+                adam_update(p, g, m, v, h, step_size, bc2_sqrt);
+                J.p[idx] = p; J.m[idx] = m; J.v[idx] = v;
+                if (J.gdst) J.gdst[idx] = g;
+                tile[r][t][ci] = p;                            // (this thread is the only reader / writer of the element)
+            }
+        }
+    }
+    if (!J.fwd.base && !J.dgrad.base) return;
+    __syncthreads();
+    // ---- 3. forward matrix ----
+    if (J.fwd.base) {
+        unsigned short* W = (unsigned short*)J.fwd.base;
+        const int items = UCO * ntaps * 8;                     // (co row, source tap, group of 8 input channels)
+        for (int i = threadIdx.x; i < items; i += 256) {
+            const int cg = i & 7, t = (i >> 3) % ntaps, r = (i >> 3) / ntaps;
+            const int co = cog * UCO + r, slot = J.fwd.inv[t];
+            if (co >= J.cout || slot < 0) continue;
+            __align__(16) unsigned short o[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) o[e] = f2b16(tile[r][t][cg * 8 + e], J.fwd.dtype);   // (channels >= cin hold zeros)
+            const int sidx = slot >> 4, k = slot & 15;
+            *(uint4*)(W + ((int64_t)sidx * J.fwd.sub_rows + co) * J.fwd.ld + ((int64_t)(c0 >> 6) * J.fwd.ntaps + k) * 64 + cg * 8) = *(const uint4*)o;
+        }
+    }
+    // ---- 4. data-gradient matrix ----
+    if (J.dgrad.base) {
+        unsigned short* W = (unsigned short*)J.dgrad.base;
+        const int co0 = cog * UCO;
+        const int items = CB * ntaps;                          // (input channel, source tap)
+        for (int i = threadIdx.x; i < items; i += 256) {
+            const int ci = i & 63, t = i >> 6;
+            const int gci = c0 + ci, slot = J.dgrad.inv[t];
+            if (gci >= J.cin || gci < J.dgrad.r0 || gci >= J.dgrad.r1 || slot < 0) continue;
+            __align__(16) unsigned short o[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) o[e] = f2b16(tile[e][t][ci], J.dgrad.dtype);         // (rows >= cout hold zeros)
+            const int sidx = slot >> 4, k = slot & 15;
+            *(uint4*)(W + ((int64_t)sidx * J.dgrad.sub_rows + (gci - J.dgrad.r0)) * J.dgrad.ld + ((int64_t)(co0 >> 6) * J.dgrad.ntaps + k) * 64 +
+                      (co0 & 63)) = *(const uint4*)o;
         }
     }
 }
@@ -223,6 +284,22 @@ extern "C" int rnr_adam_plan_create(const rnr_adam_wjob_t* wjobs, int n_wjobs, c
             AdamWJob& d = h[i];
             d.scratch = s.scratch; d.p = s.p; d.m = s.m; d.v = s.v; d.gdst = s.gdst;
             d.cout = s.cout; d.cin = s.cin; d.ntaps = s.ntaps; d.s_co = s.s_co; d.s_ci = s.s_ci;
+            const rnr_wmat_t* src[2] = {&s.fwd, &s.dgrad};
+            WMat* dst[2] = {&d.fwd, &d.dgrad};
+            for (int f = 0; f < 2; f++) {
+                memset(dst[f], 0, sizeof(WMat));
+                if (!src[f]->base) continue;
+                RNR_REQUIRE(src[f]->dtype == RNR_F16 || src[f]->dtype == RNR_BF16, "adam plan: GEMM matrices must be 16-bit");
+                RNR_REQUIRE(src[f]->ld % 64 == 0 && ((uintptr_t)src[f]->base & 15) == 0 && src[f]->ntaps >= 1 && src[f]->ntaps <= MAXT,
+                            "adam plan: bad GEMM matrix descriptor (ld %lld, ntaps %d)", (long long)src[f]->ld, src[f]->ntaps);
+                dst[f]->base = src[f]->base; dst[f]->ld = src[f]->ld; dst[f]->dtype = src[f]->dtype; dst[f]->ntaps = src[f]->ntaps;
+                dst[f]->sub_rows = src[f]->sub_rows; dst[f]->r0 = src[f]->r0; dst[f]->r1 = src[f]->r1;
+                for (int t = 0; t < 16; t++) {
+                    dst[f]->inv[t] = src[f]->inv[t];
+                    RNR_REQUIRE(src[f]->inv[t] < 0 || (src[f]->inv[t] & 15) < src[f]->ntaps, "adam plan: tap slot out of range");
+                }
+            }
+            if (!d.dgrad.base) { d.dgrad.r0 = 0; d.dgrad.r1 = 0; }
             d.tiles_c = rnr_cdiv(s.cin, CB);
             d.blk0 = blk;
             d.nblk = rnr_cdiv(s.cout, UCO) * d.tiles_c;

@@ -168,6 +168,8 @@ class _LayerState:
     drop: Optional[torch.Tensor] = None
     ticket: Optional[torch.Tensor] = None
     bwd_totals: Optional[torch.Tensor] = None
+    wmat_fwd: Optional[dict] = None            # layout of the forward GEMM matrix family (for the optimiser pass that re-derives it)
+    wmat_dgrad: Optional[dict] = None          # same for the data-gradient family
     bn_ticket: Optional[torch.Tensor] = None   # last-CTA ticket of the fused forward BatchNorm finalize
     bn_fused: bool = False                     # statistics finalize runs inside the conv kernel (rnr_conv_plan_set_bn)
 
@@ -460,6 +462,19 @@ class UNetEngine:
                 col0 += ntaps * kpads[si]
             return jobs
 
+        def wmat_desc(base, ld, dtype, ntaps, sub_rows, sub_taps, r0=0, r1=0, ok=None):
+            """Layout record of a GEMM matrix family for the fused optimiser pass (csrc/optim.cu): source tap t sits at slot k of
+            sub-matrix s with inv[t] = s*16 + k.  None when the layout is outside what that pass writes (tap-major columns, or
+            several concatenated sources with out-of-bounds padding between them)."""
+            supported = chunked and (not oob or len(srcs) == 1) if ok is None else ok
+            if not supported:
+                return None
+            inv = [-1] * 16
+            for s_i, offs in enumerate(sub_taps):
+                for k_i, t in enumerate(offs):
+                    inv[t] = s_i * 16 + k_i
+            return dict(base=base, ld=int(ld), dtype=dtype, ntaps=int(ntaps), sub_rows=int(sub_rows), r0=int(r0), r1=int(r1), inv=inv)
+
         # ------------------------------ forward ------------------------------
         if sp.kind == 'c3':
             views = [t.padded() for t in srcs]
@@ -467,6 +482,7 @@ class UNetEngine:
             tapoffs = [kh * 3 + kw for kh in range(3) for kw in range(3)]
             wm = self._alloc((n_rows, 9 * cpad_tot), adt_t, zero=True)
             st.wprep_fwd += fwd_wprep(wm, 9, cin_tot * 9, 9, tapoffs)
+            st.wmat_fwd = wmat_desc(wm, 9 * cpad_tot, self.act_dt, 9, n_rows, [tapoffs])
             th, tw = tile_shape(Wo)
             tiles = max(N * -(-Ho // th) * -(-Wo // tw), 148)      # rows of the partial-sum buffer: one per tile or per CTA
             if epi & EPI_STATS:
@@ -489,6 +505,7 @@ class UNetEngine:
                             tapoffs.append(kh * 4 + kw)
             wm = self._alloc((n_rows, 16 * cpad_tot), adt_t, zero=True)
             st.wprep_fwd += fwd_wprep(wm, 16, cin_tot * 16, 16, tapoffs)
+            st.wmat_fwd = wmat_desc(wm, 16 * cpad_tot, self.act_dt, 16, n_rows, [tapoffs])
             th, tw = tile_shape(Wo)
             tiles = max(N * -(-Ho // th) * -(-Wo // tw), 148)
             if epi & EPI_STATS:
@@ -510,6 +527,7 @@ class UNetEngine:
             # run as ONE launch (rnr_conv_plan_create_multi): 4x the tiles per launch instead of four half-empty grids
             wm_all = self._alloc((4 * n_rows, 4 * cpad_tot), adt_t, zero=True)
             probs = []
+            sub_taps = []
             for ph in range(2):
                 for pw in range(2):
                     taps, tapoffs = [], []
@@ -517,6 +535,7 @@ class UNetEngine:
                         for (kw, dx) in sel[pw]:
                             taps.append(([si for si in range(len(srcs))], dx, dy))
                             tapoffs.append(kh * 4 + kw)
+                    sub_taps.append(tapoffs)
                     sidx = ph * 2 + pw
                     wm = wm_all[sidx * n_rows:(sidx + 1) * n_rows]
                     # weight [Cin, Cout, 4, 4]: rows = co (stride 16), cols = ci (stride Cout*16)
@@ -524,6 +543,7 @@ class UNetEngine:
                     probs.append(self._conv_problem(
                         views, ksteps_for(taps), self.act_dt, bk, wm, n_rows, cout, N, Hi, Wi, st.raw, F32 if final else self.raw_dt,
                         (Ho * Wo * ld_out, Wo * ld_out, ld_out), (2, 2, ph, pw), epi, bias_t, st.stats, cout, self.impl, defer=True))
+            st.wmat_fwd = wmat_desc(wm_all, 4 * cpad_tot, self.act_dt, 4, n_rows, sub_taps)
             self.keep.append(probs)
             fused = self._fused_plan(probs, self.impl)
             if fused is not None:
@@ -657,6 +677,7 @@ class UNetEngine:
             # rows = ci (stride 9), cols = co (stride Cin*9)
             st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 9, wm, self.grad_dt, nci, nci_pad, cout, gK, 9, 9, cin_tot * 9,
                                          self._tapoff(tapoffs), chunked=gch))
+            st.wmat_dgrad = wmat_desc(wm, 9 * gK, self.grad_dt, 9, nci_pad, [tapoffs], r0, r1, ok=bool(gch))
             st.dgrad_plans.append(self._conv_problem(
                 [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp, Wp, st.gx, self.grad_dt,
                 (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
@@ -666,12 +687,14 @@ class UNetEngine:
             st.gx_fold, st.gx_ld = True, nci_pad
             wm_all = self._alloc((4 * nci_pad, 4 * gK), gdt_t, zero=True)
             probs = []
+            dsub_taps = []
             for ph in range(2):
                 for pw in range(2):
                     gch = 1 if gbk == 64 else 0
                     tapl = [(1 - b, 1 - a, (2 * a + ph) * 4 + (2 * b + pw)) for a in range(2) for b in range(2)]
                     ks = self._order_ksteps([(0, dx, dy) for (dx, dy, _) in tapl], gK, gbk, gch)
                     tapoffs = [o for (_, _, o) in tapl]
+                    dsub_taps.append(tapoffs)
                     sidx = ph * 2 + pw
                     wm = wm_all[sidx * nci_pad:(sidx + 1) * nci_pad]
                     st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * 16, wm, self.grad_dt, nci, nci_pad, cout, gK, 4, 16,
@@ -679,6 +702,7 @@ class UNetEngine:
                     probs.append(self._conv_problem(
                         [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp // 2, Wp // 2, st.gx, self.grad_dt,
                         (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (2, 2, ph, pw), 0, None, None, 0, self.impl, defer=True))
+            st.wmat_dgrad = wmat_desc(wm_all, 4 * gK, self.grad_dt, 4, nci_pad, dsub_taps, r0, r1, ok=bool(gbk == 64))
             self.keep.append(probs)
             fused = self._fused_plan(probs, self.impl)
             if fused is not None:
@@ -699,6 +723,7 @@ class UNetEngine:
             # weight [Cin, Cout, 4,4]: rows = ci (stride Cout*16), cols = co (stride 16)
             st.wprep_dgrad.append(_WPrep(sp.w_key, r0 * cout * 16, wm, self.grad_dt, nci, nci_pad, cout, gK, 16, cout * 16, 16,
                                          self._tapoff(tapoffs), chunked=gch))
+            st.wmat_dgrad = wmat_desc(wm, 16 * gK, self.grad_dt, 16, nci_pad, [tapoffs], r0, r1, ok=bool(gch))
             st.dgrad_plans.append(self._conv_problem(
                 gviews, ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hi, Wi, st.gx, self.grad_dt,
                 (Hi * Wi * nci_pad, Wi * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
@@ -781,14 +806,18 @@ class UNetEngine:
         _lib.check(self.L.rnr_wprep_run(plan.h, self._stream()), 'rnr_wprep_run')
         self.gpu_launches += 1
 
-    def wprep_plan_for(self, layer_names, backward=True):
+    def wprep_plan_for(self, layer_names, backward=True, skip_fwd=(), skip_dgrad=()):
         """Batched weight-preparation plan (one launch) for the forward (+ data-gradient) matrices of a subset of layers: the
-        fused optimiser refreshes each group of layers right after its Adam update."""
+        fused optimiser refreshes each group of layers right after its Adam update.  ``skip_fwd`` / ``skip_dgrad``: layers whose
+        matrices the optimiser pass itself writes."""
         items = []
         for sp in self.specs:
             if sp.name in layer_names:
                 st = self.layers[sp.name]
-                items += st.wprep_fwd + (st.wprep_dgrad if backward else [])
+                if sp.name not in skip_fwd:
+                    items += st.wprep_fwd
+                if backward and sp.name not in skip_dgrad:
+                    items += st.wprep_dgrad
         return self._wprep_plan(items) if items else None
 
     def run_wprep_plan(self, plan):

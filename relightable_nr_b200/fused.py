@@ -22,6 +22,7 @@ the gradients are materialised in parameter layout instead (``param.grad`` views
 updated.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -60,9 +61,16 @@ class _AdamPlan:
     def __init__(self, L, wjobs, jobs):
         self.L = L
         wa = (AdamWJob * max(len(wjobs), 1))()
-        for d, (scratch, p, m, v, cout, cin, ntaps, s_co, s_ci) in zip(wa, wjobs):
+        for d, (scratch, p, m, v, cout, cin, ntaps, s_co, s_ci, fwd, dgrad) in zip(wa, wjobs):
             d.scratch, d.p, d.m, d.v, d.gdst = scratch, p, m, v, None
             d.cout, d.cin, d.ntaps, d.s_co, d.s_ci = cout, cin, ntaps, s_co, s_ci
+            for dst, desc in ((d.fwd, fwd), (d.dgrad, dgrad)):
+                dst.base = None
+                if desc is not None:      # the pass also writes next step's 16-bit GEMM matrix of this family (engine/unet.py wmat_desc)
+                    dst.base, dst.ld, dst.dtype = desc['base'].data_ptr(), desc['ld'], desc['dtype']
+                    dst.ntaps, dst.sub_rows, dst.r0, dst.r1 = desc['ntaps'], desc['sub_rows'], desc['r0'], desc['r1']
+                    for t in range(16):
+                        dst.inv[t] = desc['inv'][t]
         ja = (AdamJob * max(len(jobs), 1))()
         for d, (p, g, m, v, n) in zip(ja, jobs):
             d.p, d.g, d.m, d.v, d.n = p, g, m, v, n
@@ -203,10 +211,20 @@ class FusedRNRStep:
         zl = lambda t: torch.zeros_like(t, memory_format=torch.contiguous_format)
         early, late = self._groups()
         wjobs = {True: [], False: []}
+        fuse_w = os.environ.get('RNR_ADAM_WRITES_GEMM', '1') != '0'
+        skip_fwd, skip_dgrad = set(), set()
         for name, w_key, src, cout, cin, kk, s_co, s_ci in eng.wgrad_scratch_jobs():
             prm = eng.params[w_key]
             opt['m'][w_key], opt['v'][w_key] = zl(prm), zl(prm)
-            wjobs[name in early].append((src, prm.data_ptr(), opt['m'][w_key].data_ptr(), opt['v'][w_key].data_ptr(), cout, cin, kk, s_co, s_ci))
+            st = eng.layers[name]
+            fwd = st.wmat_fwd if fuse_w else None
+            dgr = st.wmat_dgrad if fuse_w else None
+            if fwd is not None:
+                skip_fwd.add(name)
+            if dgr is not None or not st.wprep_dgrad:
+                skip_dgrad.add(name)
+            wjobs[name in early].append((src, prm.data_ptr(), opt['m'][w_key].data_ptr(), opt['v'][w_key].data_ptr(), cout, cin, kk, s_co, s_ci,
+                                         fwd, dgr))
         jobs = []
         done_w = {j[1] for j in eng.wgrad_scratch_jobs()}
         for key, (o, n) in eng.grad_slices.items():
@@ -227,8 +245,10 @@ class FusedRNRStep:
         opt['plan_early'] = _AdamPlan(self.L, wjobs[True], []) if wjobs[True] else None
         opt['plan_late'] = _AdamPlan(self.L, wjobs[False], []) if wjobs[False] else None
         opt['plan_small'] = _AdamPlan(self.L, [], jobs)
-        opt['wprep_early'] = eng.wprep_plan_for(early)
-        opt['wprep_late'] = eng.wprep_plan_for(late)
+        # weight preparation left over after the optimiser pass: only the matrix families whose layout that pass does not write
+        opt['wprep_early'] = eng.wprep_plan_for(early, skip_fwd=skip_fwd, skip_dgrad=skip_dgrad)
+        opt['wprep_late'] = eng.wprep_plan_for(late, skip_fwd=skip_fwd, skip_dgrad=skip_dgrad)
+        opt['gemm_in_adam'] = (sorted(skip_fwd), sorted(skip_dgrad))
         self._opt = opt
 
     def _groups(self):

@@ -168,6 +168,40 @@ def test_fused_training_trajectory_follows_the_oracle(size, nf0):
     assert c >= 0.9
 
 
+@pytest.mark.parametrize('size,nf0,early', [(64, 64, 'down3'), (64, 16, 'down3'), (128, 64, None)])
+def test_optimiser_pass_writes_the_next_steps_gemm_matrices_bit_exactly(size, nf0, early):
+    """The fused un-transpose + Adam kernel also emits next step's 16-bit forward / data-gradient GEMM matrices (csrc/optim.cu
+    phases 3-4).  After three optimiser steps every matrix must equal, bit for bit, what the weight-preparation kernel derives
+    from the updated fp32 parameters -- for the families the optimiser pass covers AND the ones left to the preparation plan."""
+    from relightable_nr_b200.pipeline import synthetic_view
+    pipe = _pipe(img_size=size, nf0=nf0)
+    views = [synthetic_view(size, view_idx=i, device='cuda:0') for i in (2, 9, 4)]
+    for v in views:
+        pipe.train_step(v, fused=True)
+    torch.cuda.synchronize()
+    f = pipe.fused
+    eng = f.eng
+    in_adam = f._opt['gemm_in_adam']
+    print('forward matrices written by the optimiser pass:', in_adam[0])
+    print('data-gradient matrices written by the optimiser pass:', in_adam[1])
+    if nf0 == 64:
+        assert len(in_adam[0]) >= len(eng.specs) - 2, 'the 64-channel-chunk layers are expected to be covered'
+    mats = []
+    for sp in eng.specs:
+        st = eng.layers[sp.name]
+        for kind, jobs in (('fwd', st.wprep_fwd), ('dgrad', st.wprep_dgrad)):
+            for j, w in enumerate(jobs):
+                mats.append(('%s/%s/%d' % (sp.name, kind, j), w.dst))
+        for kind, d in (('fwd', st.wmat_fwd), ('dgrad', st.wmat_dgrad)):
+            if d is not None:
+                mats.append(('%s/%s/all' % (sp.name, kind), d['base']))
+    got = [(n, t.clone()) for n, t in mats]
+    eng.prepare_weights(backward=True)
+    torch.cuda.synchronize()
+    bad = [n for (n, a), (_, t) in zip(got, mats) if not torch.equal(a.view(torch.int16), t.view(torch.int16))]
+    assert not bad, bad
+
+
 def test_full_size_fused_step_matches_oracle():
     """BASELINE.json's benchmark configuration itself (512x512 view, texture 512^2 x 24 ch x 4 mips, U-Net 108 -> 78 with nf0 = 64,
     26 rays, SH lmax 10 / 256x512 envmap): one fused training step on the GPU against the CPU fp32 oracle of train_rnr.py:512-608.
