@@ -60,7 +60,8 @@ typedef struct {           /* one K-step = BK consecutive channels of one view a
 enum {
     RNR_EPI_BIAS  = 1,     /* += bias[co]                                            */
     RNR_EPI_TANH  = 2,     /* tanh() after bias                                       */
-    RNR_EPI_STATS = 4      /* per-tile channel sums: stats[(tile_m*2+{0,1})*ldstats+co] */
+    RNR_EPI_STATS = 4,     /* per-tile channel sums: stats[(tile_m*2+{0,1})*ldstats+co] */
+    RNR_EPI_GSTATS = 8     /* data-gradient plan: reserve room for rnr_conv_plan_set_gstats (no effect until that call) */
 };
 
 typedef struct {
@@ -101,6 +102,26 @@ int  rnr_conv_plan_create_multi(const rnr_conv_problem_t* probs, int n, int impl
 void rnr_conv_plan_destroy(rnr_conv_plan_t* plan);
 int  rnr_conv_run(const rnr_conv_plan_t* plan, void* stream);
 int  rnr_conv_plan_tiles_m(const rnr_conv_plan_t* plan);
+/* BatchNorm-backward statistics of the PRODUCER layer(s) of a data-gradient plan's output, accumulated in the plan's epilogue.
+ * The reference differentiates nn.BatchNorm2d + (Leaky)ReLU + Dropout2d (pytorch_prototyping.py:177-197, :250-272) with autograd:
+ * dgamma = sum(gg * xhat), dbeta = sum(gg), gg = g * drop * lrelu'(.).  Both sums are linear in the incoming gradient g, so each
+ * consumer layer's data-gradient launch adds its share (fp64 atomics into totals[2, C]: sum(gg), sum(gg * (raw - mean))) and
+ * rnr_bn_bwd_apply_src finishes the layer in one pass.  Segment i covers output columns [c_lo, c_hi) (one concatenated input of
+ * the consumer); raw == NULL leaves that segment alone.  H, W: interior size of the activation; pad = 1 when the plan's output grid
+ * is the reflect-padded plane.  Returns cudaErrorNotSupported (no error text) when the plan cannot carry the statistics. */
+typedef struct {
+    const void*  raw;        /* producer's pre-BatchNorm conv output [N, H, W, C], 16-bit */
+    int32_t      raw_dtype;
+    int32_t      C;
+    const float* scale;      /* gamma * invstd            [C] */
+    const float* shift;      /* beta - mean * scale       [C] */
+    const float* mean;       /*                           [C] */
+    const float* drop;       /* Dropout2d scale [N, C] or NULL */
+    float        slope;      /* LeakyReLU slope (0: ReLU) */
+    int32_t      c_lo, c_hi;
+    double*      totals;     /* [2, C] */
+} rnr_gstat_seg_t;
+int  rnr_conv_plan_set_gstats(rnr_conv_plan_t* plan, const rnr_gstat_seg_t* segs, int nseg, int H, int W, int pad);
 /* profiling aid: device buffer [4 CTAs][4 roles][64] of clock64 stamps written by the halo kernel (NULL = off) */
 int  rnr_debug_set_trace(long long* buf);
 /* rows of `stats` the plan writes ([rows, 2, ldstats]; the caller sizes / zero-fills the buffer accordingly) */
@@ -279,6 +300,12 @@ int rnr_bn_bwd_finalize(const float* partials, int T, int C, double count,
  * totals [2,C] (double, must be 0 before the first call; the kernel re-zeroes it) and the last block to finish (ticket: an
  * int32 in device memory, 0 before the first call, re-armed by the kernel) writes dbeta = sum(gz), dgamma = sum(gz*xhat)
  * (either may be NULL) and, when coef != NULL, the coefficients (A, B, D) of rnr_bn_bwd_apply.                          */
+/* BatchNorm backward from totals that rnr_conv_plan_set_gstats launches accumulated: gz = A*gg + B*raw + D in ONE pass over the
+ * gradient sources (no reduction pass); writes dgamma / dbeta, re-zeroes totals, re-arms ticket.  C = 8 x a power of two. */
+int rnr_bn_bwd_apply_src(const rnr_gsrc_t* srcs, int nsrc, const void* raw, int raw_dtype, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, const float* gamma, const float* drop, float slope, void* gz,
+                         double* totals, int* ticket, double count, float* dgamma, float* dbeta, int N, int H, int W, int C,
+                         void* stream);
 int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const void* raw, int raw_dtype,
                           const float* scale, const float* shift, const float* mean, const float* invstd,
                           const float* drop, float slope, void* gz, double* totals, int* ticket, double count,

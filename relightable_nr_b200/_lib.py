@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librnr_b200.so")
 
 F16, BF16, F32 = 0, 1, 2
-EPI_BIAS, EPI_TANH, EPI_STATS = 1, 2, 4
+EPI_BIAS, EPI_TANH, EPI_STATS, EPI_GSTATS = 1, 2, 4, 8
 MAX_VIEWS = 8
 
 
@@ -51,6 +51,12 @@ class WgradProblem(C.Structure):
 
 class GSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("dtype", C.c_int32), ("fold", C.c_int32), ("ld", C.c_int32), ("c0", C.c_int32)]
+
+
+class GStatSeg(C.Structure):
+    _fields_ = [("raw", C.c_void_p), ("raw_dtype", C.c_int32), ("C", C.c_int32), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("mean", C.c_void_p), ("drop", C.c_void_p), ("slope", C.c_float), ("c_lo", C.c_int32), ("c_hi", C.c_int32),
+                ("totals", C.c_void_p)]
 
 
 class WPrepJob(C.Structure):
@@ -109,6 +115,7 @@ def lib():
         "rnr_conv_plan_tiles_m": [vp],
         "rnr_conv_plan_stat_rows": [vp],
         "rnr_conv_plan_set_bn": [vp, vp, vp, f64, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp, i32],
+        "rnr_conv_plan_set_gstats": [vp, C.POINTER(GStatSeg), i32, i32, i32, i32],
         "rnr_debug_set_trace": [vp],
         "rnr_wgrad_plan_create": [C.POINTER(WgradProblem), i32, C.POINTER(vp)],
         "rnr_wgrad_run": [vp, vp],
@@ -121,6 +128,7 @@ def lib():
         "rnr_bn_act_fwd": [vp, i32, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce_fin": [C.POINTER(GSrc), i32, vp, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, f64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "rnr_bn_bwd_apply_src": [C.POINTER(GSrc), i32, vp, i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, f64, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_finalize": [vp, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "rnr_bn_bwd_apply": [vp, vp, i32, vp, i32, i32, i32, i32, vp],
         "rnr_pack_nchw_to_act": [vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -439,6 +439,136 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
     if (threadIdx.x == 0) *ticket = 0;
 }
 
+// BatchNorm backward when the per-channel sums are already in `totals` (accumulated by the data-gradient launches of the
+// consumer layers, GStats in conv_internal.cuh): ONE streaming pass
+//     gz = A * gg + B * raw + D,   gg = (sum of the gradient sources, reflect halo folded) * drop * lrelu'(raw*scale + shift)
+// Every block first turns the totals into the per-channel coefficient table (A, B, D, scale, shift) in shared memory -- one
+// channel per thread, two fp64 loads each -- then streams PB rounds of 256 / vpp pixels with one 8-channel vector per thread
+// and no per-thread constant registers: occupancy, not registers, keeps HBM busy (the variant that held 40 coefficient registers
+// per thread ran at 1.5 TB/s).  Block 0 writes dgamma / dbeta; the last block to have READ the totals (ticket) re-zeroes them.
+template <int NSRC>
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_src_kernel(const GSrcs srcs, const void* __restrict__ raw, int raw_dtype,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ drop, float slope,
+                                     __nv_bfloat16* __restrict__ gz, double* __restrict__ totals, int* __restrict__ ticket,
+                                     double inv_count, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     int N, int H, int W, int C, int lhw, int lw, int PB) {
+    extern __shared__ __align__(16) float s_coef[];      // [5][C]: A, B, D, scale, shift
+    __shared__ int s_last;
+    for (int ch = threadIdx.x; ch < C; ch += 256) {
+        const double sv = __ldcg(totals + ch);
+        const double is = (double)invstd[ch];
+        const double qv = __ldcg(totals + C + ch) * is;
+        const double gi = (double)gamma[ch] * is;
+        const double k1 = sv * inv_count, k2 = qv * inv_count;
+        s_coef[ch] = (float)gi;
+        s_coef[C + ch] = (float)(-gi * is * k2);
+        s_coef[2 * C + ch] = (float)(gi * ((double)mean[ch] * is * k2 - k1));
+        s_coef[3 * C + ch] = scale[ch];
+        s_coef[4 * C + ch] = shift[ch];
+        if (blockIdx.x == 0) {
+            if (dbeta) dbeta[ch] = (float)sv;
+            if (dgamma) dgamma[ch] = (float)qv;
+        }
+    }
+    __threadfence();                              // the loads of `totals` above are performed before the ticket moves
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        for (int i = threadIdx.x; i < 2 * C; i += 256) totals[i] = 0.0;
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+    const int vpp = C >> 3;                       // power of two, <= 256
+    const int cv = threadIdx.x & (vpp - 1), pl = threadIdx.x / vpp, ppb = 256 / vpp;
+    const int c = cv * 8;
+    const int Hp = H + 2, Wp = W + 2;
+    const int HW = H * W;
+    const int P = N * HW;
+    const rnr_gsrc_t S0 = srcs.s[0];
+    const rnr_gsrc_t S1 = srcs.s[NSRC - 1];
+    const int pix0 = blockIdx.x * PB * ppb + pl;
+    const bool pre0 = S0.dtype != RNR_F32;
+    const bool pre1 = NSRC > 1 && S1.dtype != RNR_F32;
+    for (int j0 = 0; j0 < PB; j0 += 2) {
+        // ---- load phase: two pixel vectors (raw + packed 16-bit gradient sources) in flight per thread ----
+        uint4 rr[2], q0[2], q1[NSRC > 1 ? 2 : 1];
+        int pixv[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int pix = pix0 + (j0 + j) * ppb;
+            pixv[j] = (j0 + j < PB && pix < P) ? pix : -1;
+            if (pixv[j] >= 0) {
+                rr[j] = __ldcs((const uint4*)((const unsigned short*)raw + (int64_t)pix * C + c));
+                int n, h, w;
+                split_pix(pix, HW, W, lhw, lw, n, h, w);
+                const int64_t ctr = ((int64_t)n * Hp + h + 1) * Wp + w + 1;
+                if (pre0) q0[j] = *(const uint4*)((const unsigned short*)S0.ptr + (S0.fold ? ctr : (int64_t)pix) * S0.ld + S0.c0 + c);
+                if (NSRC > 1 && pre1) q1[j] = *(const uint4*)((const unsigned short*)S1.ptr + (S1.fold ? ctr : (int64_t)pix) * S1.ld + S1.c0 + c);
+            }
+        }
+        // ---- compute phase ----
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int pix = pixv[j];
+            if (pix < 0) continue;
+            int n, h, w;
+            split_pix(pix, HW, W, lhw, lw, n, h, w);
+            const int64_t ctr = ((int64_t)n * Hp + h + 1) * Wp + w + 1;
+            float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const bool border = (h == 1) | (h == H - 2) | (w == 1) | (w == W - 2);
+            {
+                const int64_t o = (S0.fold ? ctr : (int64_t)pix) * S0.ld + S0.c0 + c;
+                if (pre0) acc_packed(q0[j], S0.dtype, g); else load8(S0.ptr, o, S0.dtype, g);
+                if (S0.fold && border) {              // (rare; a scratch array keeps g itself in registers)
+                    float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    fold_border(S0, o, h, w, H, W, Wp, t);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) g[e] += t[e];
+                }
+            }
+            if (NSRC > 1) {
+                const int64_t o = (S1.fold ? ctr : (int64_t)pix) * S1.ld + S1.c0 + c;
+                if (pre1) acc_packed(q1[j], S1.dtype, g); else load8(S1.ptr, o, S1.dtype, g);
+                if (S1.fold && border) {
+                    float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    fold_border(S1, o, h, w, H, W, Wp, t);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) g[e] += t[e];
+                }
+            }
+            float dr[8];
+            if (drop) {
+                const float4 d0 = __ldg((const float4*)(drop + n * C + c)), d1 = __ldg((const float4*)(drop + n * C + c + 4));
+                dr[0] = d0.x; dr[1] = d0.y; dr[2] = d0.z; dr[3] = d0.w; dr[4] = d1.x; dr[5] = d1.y; dr[6] = d1.z; dr[7] = d1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) dr[e] = 1.f;
+            }
+            const unsigned short* us = (const unsigned short*)&rr[j];
+            __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const float4 A = *(const float4*)(s_coef + c + hh * 4), B = *(const float4*)(s_coef + C + c + hh * 4);
+                const float4 D = *(const float4*)(s_coef + 2 * C + c + hh * 4);
+                const float4 sc = *(const float4*)(s_coef + 3 * C + c + hh * 4), sh = *(const float4*)(s_coef + 4 * C + c + hh * 4);
+                const float Av[4] = {A.x, A.y, A.z, A.w}, Bv[4] = {B.x, B.y, B.z, B.w}, Dv[4] = {D.x, D.y, D.z, D.w};
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int e = hh * 4 + k;
+                    const float r = cvt16(us[e], raw_dtype);
+                    const float z = r * scv[k] + shv[k];
+                    const float gg = g[e] * (z > 0.f ? 1.f : slope) * dr[e];
+                    o[e] = __float2bfloat16_rn(Av[k] * gg + Bv[k] * r + Dv[k]);
+                }
+            }
+            *(uint4*)(gz + ctr * C + c) = *(const uint4*)o;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __restrict__ partials, int T, int C, double count,
                                        float* dgamma, float* dbeta, float* c1, float* c2, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ invstd, float* coef) {
@@ -595,6 +725,48 @@ extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const voi
     if (nsrc == 1) { if (ru == 2) RNR_BN_LAUNCH(1, 2); else if (ru == 3) RNR_BN_LAUNCH(1, 3); else RNR_BN_LAUNCH(1, 4); }
     else { if (ru == 2) RNR_BN_LAUNCH(2, 2); else if (ru == 3) RNR_BN_LAUNCH(2, 3); else RNR_BN_LAUNCH(2, 4); }
 #undef RNR_BN_LAUNCH
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bn_bwd_apply_src(const rnr_gsrc_t* srcs, int nsrc, const void* raw, int raw_dtype, const float* scale,
+                                    const float* shift, const float* mean, const float* invstd, const float* gamma, const float* drop,
+                                    float slope, void* gz, double* totals, int* ticket, double count, float* dgamma, float* dbeta,
+                                    int N, int H, int W, int C, void* stream) {
+    const int vpp = C / 8;
+    RNR_REQUIRE(C % 8 == 0 && vpp >= 1 && vpp <= 256 && (vpp & (vpp - 1)) == 0, "rnr_bn_bwd_apply_src: C=%d must be 8 x a power of two <= 2048", C);
+    RNR_REQUIRE(nsrc >= 1 && nsrc <= 2, "rnr_bn_bwd_apply_src: nsrc must be 1 or 2");
+    RNR_REQUIRE(raw_dtype != RNR_F32, "rnr_bn_bwd_apply_src: 16-bit raw tensor required");
+    RNR_REQUIRE(ticket && totals && gamma, "rnr_bn_bwd_apply_src: ticket / totals / gamma required");
+    RNR_REQUIRE((int64_t)N * H * W < (1ll << 31), "rnr_bn_bwd_apply_src: too many pixels");
+    GSrcs gs;
+    gs.n = nsrc;
+    for (int i = 0; i < nsrc; i++) gs.s[i] = srcs[i];
+    const int ppb = 256 / vpp;
+    const int64_t P = (int64_t)N * H * W;
+    const int64_t rounds = (P + ppb - 1) / ppb;             // pixel rounds of one block-wide sweep
+    // PB rounds per block: enough blocks to fill the machine several times over, few enough that the per-block coefficient
+    // prologue (2 fp64 loads per channel, one ticket atomic) stays a small fraction of the block's work
+    int PB = 8;
+    while (PB > 2 && rounds / PB < 148 * 8) PB /= 2;
+    const int blocks = (int)((rounds + PB - 1) / PB);
+    const size_t smem = (size_t)5 * C * sizeof(float);
+    int lhw = -1, lw = -1;
+    {
+        const int HW = H * W;
+        if ((HW & (HW - 1)) == 0 && (W & (W - 1)) == 0) {
+            lhw = 0; while ((1 << lhw) < HW) lhw++;
+            lw = 0; while ((1 << lw) < W) lw++;
+        }
+    }
+    if (nsrc == 1)
+        bn_bwd_apply_src_kernel<1><<<blocks, 256, smem, (cudaStream_t)stream>>>(gs, raw, raw_dtype, scale, shift, mean, invstd, gamma, drop, slope,
+                                                                             (__nv_bfloat16*)gz, totals, ticket, 1.0 / count, dgamma, dbeta,
+                                                                             N, H, W, C, lhw, lw, PB);
+    else
+        bn_bwd_apply_src_kernel<2><<<blocks, 256, smem, (cudaStream_t)stream>>>(gs, raw, raw_dtype, scale, shift, mean, invstd, gamma, drop, slope,
+                                                                             (__nv_bfloat16*)gz, totals, ticket, 1.0 / count, dgamma, dbeta,
+                                                                             N, H, W, C, lhw, lw, PB);
     RNR_LAUNCH_CHECK();
     return 0;
 }

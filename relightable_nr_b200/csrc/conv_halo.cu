@@ -75,7 +75,8 @@ __device__ __forceinline__ void trace(long long* base, int role, int& idx) {
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, const HaloGroup* __restrict__ groups, int n_groups,
                  const HaloTap* __restrict__ taps, int n_taps, int bn, int tiles_n, int b_stages, int a_stage_bytes,
-                 int b_stage_bytes, int pitch, int a_bytes, int dbg, int T, int cs, int gtaps, const HaloCfg hc, const BnFin bnf) {
+                 int b_stage_bytes, int pitch, int a_bytes, int dbg, int T, int cs, int gtaps, const HaloCfg hc, const BnFin bnf,
+                 const GStats gs) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -87,13 +88,15 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     uint64_t* bempty = bfull + 8;                        // [b_stages]
     uint64_t* tfull_bar = bempty + 8;                    // [2]
     uint64_t* tempty_bar = tfull_bar + 2;                // [2]
-    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    uint64_t* raw_bar = tempty_bar + 2;                  // [2]: raw tile full / empty (fused BatchNorm-backward statistics)
+    uint32_t* tmem_slot = (uint32_t*)(raw_bar + 2);
     HaloGroup* s_groups = (HaloGroup*)(tmem_slot + 4);               // [kMaxGroups]
     HaloTap* s_taps = (HaloTap*)(s_groups + kMaxGroups);             // [kMaxTaps]
     float* s_acc = (float*)(s_taps + kMaxTaps);                      // [2][kMaxStatC] per-CTA BatchNorm sums
     float* s_stage = s_acc + 2 * kMaxStatC;                                   // [128][68] epilogue staging slab (16-byte aligned)
     int64_t* s_rowoff = (int64_t*)(s_stage + 128 * 68);              // [128] output offset of each tile row
     float* s_colp = (float*)(s_rowoff + 128);                        // [2][8][64] per-pass column partial sums
+    unsigned short* s_raw = (unsigned short*)(s_colp + 1024);        // [128][64] producer's raw conv output under the current pass (RNR_EPI_GSTATS)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // cluster of `cs` CTAs: same N tile, `cs` adjacent M tiles (rank r takes M tile mg*cs + r); the B (weight) stage is loaded once
@@ -121,6 +124,8 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         for (int s = 0; s < kAStages; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < b_stages; s++) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], (uint32_t)cs); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
+        mbar_init(&raw_bar[0], 64);            // full: the 64 threads of the two raw-tile loader warps
+        mbar_init(&raw_bar[1], kEpiWarps);     // empty: one arrival per epilogue warp
         fence_barrier_init();
     }
     if (warp == kAllocWarp) tmem_alloc(tmem_slot, 512);
@@ -253,6 +258,8 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         int it = 0;
         int t3 = 1;
         const bool tr4 = (warp == 0 && lane == 0);
+        const bool gstat = gs.nseg > 0;                        // BatchNorm-backward statistics of the producer layer(s) (GStats)
+        uint32_t rph = 0;
         for (int t = cid; t < total_tiles; t += ncl, it++) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -365,10 +372,48 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     }
                     s_colp[part * 64 + col] = a1;
                     s_colp[512 + part * 64 + col] = a2;
+                } else if (gstat) {
+                    // gg = g * drop * lrelu'(raw*scale + shift);  column sums of gg and gg * (raw - mean)   (bn_bwd_reduce_fin_kernel).
+                    // The producer's raw tile of this pass was staged in shared memory by the loader warps (below).
+                    const int col = e & 63, part = e >> 6;
+                    const int co = n0 + c0 + col;
+                    const bool s1 = gs.nseg > 1 && co >= gs.seg[1].c_lo;
+                    const int c_lo = s1 ? gs.seg[1].c_lo : gs.seg[0].c_lo, c_hi = s1 ? gs.seg[1].c_hi : gs.seg[0].c_hi;
+                    const int en = s1 ? gs.seg[1].enabled : gs.seg[0].enabled;
+                    const bool g_ok = en && col < pw && co >= c_lo && co < c_hi && tile_m < p.tiles_m;
+                    float a1 = 0.f, a2 = 0.f;
+                    float g_sc = 0.f, g_sh = 0.f, g_mu = 0.f, g_dr = 1.f;
+                    if (g_ok) {
+                        const int ch = co - c_lo;
+                        const float* dp = s1 ? gs.seg[1].drop : gs.seg[0].drop;
+                        g_sc = __ldg((s1 ? gs.seg[1].scale : gs.seg[0].scale) + ch);
+                        g_sh = __ldg((s1 ? gs.seg[1].shift : gs.seg[0].shift) + ch);
+                        g_mu = __ldg((s1 ? gs.seg[1].mean : gs.seg[0].mean) + ch);
+                        if (dp) g_dr = __ldg(dp + (int64_t)n_ * (s1 ? gs.seg[1].C : gs.seg[0].C) + ch);
+                    }
+                    const float g_slope = s1 ? gs.seg[1].slope : gs.seg[0].slope;
+                    mbar_wait(&raw_bar[0], rph);
+                    if (g_ok) {
+                        const float* sp = s_stage + (part * 16) * 68 + col;
+                        const unsigned short* rp = s_raw + (part * 16) * 64 + col;
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            const float r = cvt16(rp[k * 64], gs.seg[0].raw_dtype);
+                            const float z = r * g_sc + g_sh;
+                            const float gg = sp[k * 68] * (z > 0.f ? 1.f : g_slope) * g_dr;
+                            a1 += gg;
+                            a2 += gg * (r - g_mu);
+                        }
+                    }
+                    rph ^= 1;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&raw_bar[1]);          // this warp is done with the raw tile
+                    s_colp[part * 64 + col] = a1;
+                    s_colp[512 + part * 64 + col] = a2;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");      // staging tile is free again
                 if (tr4 && it == 0) trace(tr, 3, t3);
-                if (do_stats && e < 128) {
+                if ((do_stats || gstat) && e < 128) {
                     // threads 0..63: sum of x, threads 64..127: sum of x^2 (the next pass rewrites s_colp only after its own barrier)
                     const int col = e & 63, which = e >> 6;
                     const int co = n0 + c0 + col;
@@ -387,6 +432,21 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             }
             if (tr4) trace(tr, 2, ti);
+        }
+        if (gstat) {
+            // this CTA's share of the producers' BatchNorm-backward sums: one fp64 atomic per (channel, sum)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            for (int co = e; co < p.cout && co < kMaxStatC; co += kEpiThreads) {
+                const bool s1 = gs.nseg > 1 && co >= gs.seg[1].c_lo;
+                const int c_lo = s1 ? gs.seg[1].c_lo : gs.seg[0].c_lo, c_hi = s1 ? gs.seg[1].c_hi : gs.seg[0].c_hi;
+                const int en = s1 ? gs.seg[1].enabled : gs.seg[0].enabled;
+                if (!en || co < c_lo || co >= c_hi) continue;
+                double* tot = s1 ? gs.seg[1].totals : gs.seg[0].totals;
+                const int Cs = s1 ? gs.seg[1].C : gs.seg[0].C;
+                const float a1 = s_acc[co], a2 = s_acc[kMaxStatC + co];
+                if (a1 != 0.f) atomicAdd(tot + (co - c_lo), (double)a1);
+                if (a2 != 0.f) atomicAdd(tot + Cs + (co - c_lo), (double)a2);
+            }
         }
         if (p.epi & RNR_EPI_STATS) {
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
@@ -448,6 +508,54 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                         if (bnf.num_batches_tracked && bnf.running_mean) *bnf.num_batches_tracked += 1;
                     }
                 }
+            }
+        }
+    }
+
+    else if (gs.nseg > 0) {
+        // ================= raw-tile loader (warps 16-17, 64 threads): fused BatchNorm-backward statistics =================
+        // For every epilogue pass, in the epilogue's order: the [128 pixel x 64 channel] tile of the producer layer's raw conv
+        // output that lies under the pass (reflect-folded for a padded output grid) -> shared memory with 16-byte cp.async, one
+        // pass ahead of the epilogue warps, so that the statistics cost them shared-memory reads only.
+        const int lt = threadIdx.x - kEpiThreads;               // 0..63
+        uint32_t eph = 0;
+        for (int t = cid; t < total_tiles; t += ncl) {
+            const int sub = t / per_sub, ts = t - sub * per_sub;
+            const int tile_m = (ts / tiles_n) * cs + crank, tile_n = ts % tiles_n;
+            const int tx_ = tile_m % p.tiles_x, ty_ = (tile_m / p.tiles_x) % p.tiles_y, n_ = tile_m / (p.tiles_x * p.tiles_y);
+            const int n0 = tile_n * bn;
+            for (int c0 = 0; c0 < bn; c0 += 64) {
+                const int pw = min(64, bn - c0);
+                const int co0 = n0 + c0;
+                const bool s1 = gs.nseg > 1 && co0 >= gs.seg[1].c_lo;
+                const int c_lo = s1 ? gs.seg[1].c_lo : gs.seg[0].c_lo, c_hi = s1 ? gs.seg[1].c_hi : gs.seg[0].c_hi;
+                const int en = s1 ? gs.seg[1].enabled : gs.seg[0].enabled;
+                const int Cs = s1 ? gs.seg[1].C : gs.seg[0].C;
+                const unsigned short* rawp = (const unsigned short*)(s1 ? gs.seg[1].raw : gs.seg[0].raw);
+                mbar_wait(&raw_bar[1], eph ^ 1);
+                if (en && tile_m < p.tiles_m && co0 >= c_lo) {
+                    // thread = (pixel column rx of the tile, 16-byte piece pc of the 64 channels); its 16 copies are the 16 tile rows
+                    const int ncol = min(pw, c_hi - co0);      // live columns of the pass (multiple of 8: checked on the host)
+                    const int rx = lt >> 3, pc = (lt & 7) * 8;
+                    if (pc < ncol) {
+                        int xx = min(tx_ * TW + rx, p.mX - 1) * p.out_mx + hc.out_px[sub] - gs.pad;
+                        xx = xx < 0 ? -xx : (xx >= gs.W ? 2 * gs.W - 2 - xx : xx);
+                        const unsigned short* base = rawp + ((int64_t)n_ * gs.H * gs.W + xx) * Cs + (co0 - c_lo) + pc;
+                        const int64_t ystride = (int64_t)gs.W * Cs;
+                        const uint32_t dst0 = smem_u32(s_raw + rx * 64 + pc);
+                        const int ybase = ty_ * TH;
+#pragma unroll
+                        for (int i = 0; i < TH; i++) {
+                            int yy = min(ybase + i, p.mY - 1) * p.out_my + hc.out_py[sub] - gs.pad;
+                            yy = yy < 0 ? -yy : (yy >= gs.H ? 2 * gs.H - 2 - yy : yy);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(i * TW * 64 * 2)),
+                                         "l"(base + yy * ystride) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                }
+                mbar_arrive(&raw_bar[0]);
+                eph ^= 1;
             }
         }
     }
@@ -588,7 +696,8 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     pl->bn = bn;
     pl->tiles_n = tiles_n;
     const int a_stage = ((rows * pitch * 128) + 1023) / 1024 * 1024;
-    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 2 * kMaxStatC * 4 + 128 * 68 * 4 + 128 * 8 + 1024 * 4;
+    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 2 * kMaxStatC * 4 + 128 * 68 * 4 + 128 * 8 + 1024 * 4 +
+                    ((prob->epi & RNR_EPI_GSTATS) ? 128 * 64 * 2 : 0);     // + the raw tile of the fused BatchNorm-backward statistics
     const int budget = 212 * 1024 - aux - kAStages * a_stage;
     // taps per B stage: one mbarrier hand-shake (~400 cycles of latency in the single-thread producer / issuer loops) must
     // cover enough tensor work, so a stage holds T taps = T*4 MMAs; T divides the taps of a group
@@ -691,6 +800,39 @@ extern "C" int rnr_conv_plan_set_bn(rnr_conv_plan_t* pl, const float* gamma, con
     return 0;
 }
 
+// Fuse the BatchNorm-backward statistics of the producer layer(s) of this DATA-GRADIENT plan's output into its epilogue (see
+// GStats in conv_internal.cuh).  cudaErrorNotSupported (no error text) when the plan cannot carry them -- the caller keeps the
+// separate rnr_bn_bwd_reduce_fin pass.  May be called again (e.g. new dropout-mask pointers); nseg = 0 switches it off.
+extern "C" int rnr_conv_plan_set_gstats(rnr_conv_plan_t* pl, const rnr_gstat_seg_t* segs, int nseg, int H, int W, int pad) {
+    RNR_REQUIRE(pl, "rnr_conv_plan_set_gstats: null plan");
+    if (nseg == 0) { pl->gst.nseg = 0; return 0; }
+    if (!(pl->impl == 1 && pl->halo) || (pl->p.epi & RNR_EPI_STATS) || pl->halo_cs != 1) return (int)cudaErrorNotSupported;
+    if (nseg < 1 || nseg > 2 || pl->p.out_dtype == RNR_F32 || pl->p.cout > kMaxStatC) return (int)cudaErrorNotSupported;
+    if (!(pl->p.epi & RNR_EPI_GSTATS)) return (int)cudaErrorNotSupported;      // no shared memory reserved for the raw tile
+    if (pad != 0 && pad != 1) return (int)cudaErrorNotSupported;
+    // the output grid must be the activation's (reflect-padded) plane
+    if (pl->p.mY * pl->p.out_my != H + 2 * pad || pl->p.mX * pl->p.out_mx != W + 2 * pad || H < 2 || W < 2) return (int)cudaErrorNotSupported;
+    GStats g;
+    memset(&g, 0, sizeof(g));
+    g.nseg = nseg; g.H = H; g.W = W; g.pad = pad;
+    for (int i = 0; i < nseg; i++) {
+        const rnr_gstat_seg_t& s = segs[i];
+        GStatSeg& d = g.seg[i];
+        d.enabled = s.raw != nullptr;
+        // a 64-column epilogue pass must lie inside one segment; 16-bit raw tensors only (two values per register)
+        if (i > 0 && (s.c_lo % 64 != 0 || pl->bn % 64 != 0 || s.c_lo != segs[i - 1].c_hi)) return (int)cudaErrorNotSupported;
+        if (d.enabled && (s.raw_dtype == RNR_F32 || s.raw_dtype != segs[0].raw_dtype || !s.scale || !s.shift || !s.mean || !s.totals ||
+                          s.c_hi - s.c_lo > s.C || s.c_lo % 8 != 0 || (s.c_hi - s.c_lo) % 8 != 0 || s.C % 8 != 0 || (int64_t)pl->p.mN * H * W * s.C >= (1ll << 31)))
+            return (int)cudaErrorNotSupported;
+        d.raw = s.raw; d.scale = s.scale; d.shift = s.shift; d.mean = s.mean; d.drop = s.drop; d.totals = s.totals;
+        d.c_lo = s.c_lo; d.c_hi = s.c_hi; d.C = s.C; d.raw_dtype = s.raw_dtype; d.slope = s.slope;
+    }
+    if (!g.seg[0].enabled && g.seg[1].enabled) g.seg[0].raw_dtype = g.seg[1].raw_dtype;
+    if (!g.seg[0].enabled && !(nseg > 1 && g.seg[1].enabled)) g.nseg = 0;
+    pl->gst = g;
+    return 0;
+}
+
 extern "C" int rnr_debug_set_trace(long long* buf) {
     RNR_CHECK(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
     return 0;
@@ -727,7 +869,8 @@ int rnr_conv_halo_run(const rnr_conv_plan* pl, cudaStream_t stream) {
     }
     RNR_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel, maps, pl->p, (const HaloGroup*)pl->d_groups, pl->n_groups,
                                  (const HaloTap*)pl->d_taps, pl->n_taps, pl->bn, pl->tiles_n, pl->stages, pl->halo_a_stage,
-                                 pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc, pl->bnf));
+                                 pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc, pl->bnf,
+                                 pl->gst));
     rnr_count_launch();
     return 0;
 }

@@ -40,6 +40,31 @@ struct BnFin {
     int enabled;
 };
 
+// BatchNorm-backward statistics fused into the epilogue of a DATA-GRADIENT launch of the halo kernel.  The launch produces
+// d loss / d act for the (one or two concatenated) inputs of a layer; each input is the activation of a producer layer
+//     act = drop * lrelu(raw * scale + shift)
+// whose BatchNorm backward needs  sum(gg)  and  sum(gg * (raw - mean))  over all pixels,  gg = g * drop * lrelu'(.).  Both are
+// linear in g, so every consumer's data-gradient launch adds its own share (the epilogue holds g in fp32, reads `raw` at the
+// same -- reflect-folded -- pixel) and the separate reduction pass over the gradient tensor (bn_bwd_reduce_fin) disappears.
+struct GStatSeg {
+    const void* raw;          // producer's pre-BatchNorm conv output [N, H, W, C]
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* drop;        // [N, C] dropout scale (nullptr: none)
+    double* totals;           // [2, C]: sum(gg), sum(gg * (raw - mean)); fp64 atomics, zeroed by the consumer of the totals
+    int c_lo, c_hi;           // output columns [c_lo, c_hi) of the launch belong to this producer (channel = column - c_lo)
+    int C, raw_dtype;
+    float slope;
+    int enabled;
+};
+struct GStats {
+    GStatSeg seg[2];
+    int nseg;
+    int H, W;                 // interior size of the activation
+    int pad;                  // 1: the launch's output grid is the reflect-padded plane [H+2, W+2]
+};
+
 struct HaloGroup {       // one (view, 64-channel chunk): a single halo box load serves all of its taps
     int16_t view, c0, ox, oy, first_tap, n_taps;
 };
@@ -73,6 +98,7 @@ struct rnr_conv_plan {
     int n_groups, n_taps;
     int dbg;             // RNR_CONV_DBG ablation bits (profiling only)
     BnFin bnf;           // fused BatchNorm finalize (rnr_conv_plan_set_bn; halo kernel only)
+    GStats gst;          // fused BatchNorm-backward statistics (rnr_conv_plan_set_gstats; halo kernel only)
 };
 
 struct WgradParams {

@@ -19,7 +19,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import _lib
-from .._lib import BF16, EPI_BIAS, EPI_STATS, EPI_TANH, F16, F32, ConvProblem, GSrc, KStep, WgradProblem, WPrepJob, WTap, WUnpackJob
+from .._lib import BF16, EPI_BIAS, EPI_GSTATS, EPI_STATS, EPI_TANH, F16, F32, ConvProblem, GSrc, GStatSeg, KStep, WgradProblem, WPrepJob, WTap, WUnpackJob
 from .views import HaloTensor, tile_shape
 
 _TORCH_DT = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
@@ -302,11 +302,92 @@ class UNetEngine:
             h = C.c_void_p()
             _lib.check(self.L.rnr_wgrad_unpack_plan_create(arr, len(self._wunpack_jobs), C.byref(h)), 'rnr_wgrad_unpack_plan_create')
             self.wunpack_plan = _Plan(h, 'wunpack')
+        self.gstat_layers = set()       # BatchNorm layers whose backward statistics come out of their consumers' data-gradient launches
+        self._gstat_keys = {}
+        if self.need_backward and self.impl == 1 and os.environ.get('RNR_BN_BWD_FUSED', '1') != '0':
+            self._plan_gstats()
         fwd_items = [w for sp in self.specs for w in self.layers[sp.name].wprep_fwd]
         all_items = fwd_items + [w for sp in self.specs for w in self.layers[sp.name].wprep_dgrad]
         self.wprep_fwd_plan = self._wprep_plan(fwd_items)
         self.wprep_all_plan = self._wprep_plan(all_items) if len(all_items) > len(fwd_items) else self.wprep_fwd_plan
         self.wprep_dgrad_plan = self._wprep_plan(all_items[len(fwd_items):]) if len(all_items) > len(fwd_items) else None
+
+    # ---- BatchNorm-backward statistics inside the data-gradient launches ------------------------
+    def _gstat_segments(self, consumer, fused):
+        """rnr_gstat_seg_t array of one consumer layer's data-gradient plan: one segment per concatenated input; a segment is live
+        when its producer layer is in ``fused``."""
+        sp = self.layers[consumer].spec
+        r0 = self.input_grad_range[0] if (consumer == 'in' and self.input_grad_range is not None) else 0
+        segs = (GStatSeg * len(sp.src))()
+        c0 = 0
+        for si, src in enumerate(sp.src):
+            d = segs[si]
+            d.c_lo, d.c_hi = c0 - r0, c0 + sp.cin[si] - r0
+            c0 += sp.cin[si]
+            prod = self._producer.get(src)
+            d.raw = None
+            if prod is not None and prod in fused:
+                pst = self.layers[prod]
+                d.raw, d.raw_dtype, d.C = pst.raw.data_ptr(), self.raw_dt, pst.spec.cout
+                d.scale, d.shift, d.mean = pst.scale.data_ptr(), pst.shift.data_ptr(), pst.mean.data_ptr()
+                d.drop = pst.drop.data_ptr() if pst.drop is not None else None
+                d.slope, d.totals = pst.spec.slope, pst.bwd_totals.data_ptr()
+        return segs
+
+    def _set_gstats(self, consumer, fused):
+        st = self.layers[consumer]
+        sp = st.spec
+        segs = self._gstat_segments(consumer, fused)
+        if not any(s.raw for s in segs):
+            return self.L.rnr_conv_plan_set_gstats(st.dgrad_plans[0].h, segs, 0, sp.H, sp.W, 0) if st.dgrad_plans else 0
+        return self.L.rnr_conv_plan_set_gstats(st.dgrad_plans[0].h, segs, len(sp.src), sp.H, sp.W, 1 if st.gx_fold else 0)
+
+    def _plan_gstats(self):
+        """Decide which BatchNorm layers get their backward sums from the data-gradient epilogues of their consumers (every consumer
+        must be ONE halo-kernel launch that accepts the segment layout), then configure those plans.  The rest keep the separate
+        reduction pass (rnr_bn_bwd_reduce_fin)."""
+        self._producer = {sp.dst: sp.name for sp in self.specs}
+        fused = set()
+        for sp in self.specs:
+            vpp = sp.cout // 8
+            if (sp.bn_key is None or sp.dst == 'out' or self.raw_dt == F32 or sp.cout % 8 or vpp & (vpp - 1) or vpp > 256):
+                continue
+            cons = self.consumers.get(sp.dst, [])
+            if cons and all(self.layers[ln].gx is not None and len(self.layers[ln].dgrad_plans) == 1 for ln, _ in cons):
+                fused.add(sp.name)
+        changed = True
+        while changed and fused:
+            changed = False
+            for sp in self.specs:
+                st = self.layers[sp.name]
+                if st.gx is None or len(st.dgrad_plans) != 1:
+                    continue
+                prods = {self._producer.get(s) for s in sp.src} & fused
+                if prods and self._set_gstats(sp.name, fused) != 0:
+                    fused -= prods          # this launch cannot carry the statistics: its producers fall back (and so must every
+                    changed = True          # other consumer of theirs -- reconfigure from the top)
+                    break
+        for sp in self.specs:
+            st = self.layers[sp.name]
+            if st.gx is not None and len(st.dgrad_plans) == 1:
+                rc = self._set_gstats(sp.name, fused)
+                assert rc == 0 or not ({self._producer.get(s) for s in sp.src} & fused)
+        self.gstat_layers = fused
+        self._gstat_keys = {}
+
+    def _refresh_gstats(self):
+        """The segments hold the producers' dropout-mask pointers: re-arm a plan when a forward pass installed other masks."""
+        if not self.gstat_layers:
+            return
+        for sp in self.specs:
+            prods = [self._producer.get(s) for s in sp.src]
+            if not any(pn in self.gstat_layers for pn in prods):
+                continue
+            key = tuple(self.layers[pn].drop.data_ptr() if (pn in self.gstat_layers and self.layers[pn].drop is not None) else 0
+                        for pn in prods)
+            if self._gstat_keys.get(sp.name, tuple(0 for _ in prods)) != key:
+                _lib.check(self._set_gstats(sp.name, self.gstat_layers), 'rnr_conv_plan_set_gstats(%s)' % sp.name)
+                self._gstat_keys[sp.name] = key
 
     # ---- problem builders ---------------------------------------------------------------------
     def _conv_problem(self, views, ksteps, ab_dtype, bk, wmat, n_rows_w, cout, mN, mY, mX, out_t, out_dtype,
@@ -661,6 +742,10 @@ class UNetEngine:
         nci_pad = _rup(nci, 16)
         Hi, Wi = sp.H, sp.W
         gC = G.C
+        # room for the BatchNorm-backward statistics of the producer layer(s) in this launch's epilogue (_plan_gstats)
+        bn_of = {q.dst: q.bn_key for q in self.specs}
+        depi = EPI_GSTATS if (self.impl == 1 and self.raw_dt != F32 and os.environ.get('RNR_BN_BWD_FUSED', '1') != '0' and
+                              any(bn_of.get(a) is not None for a in sp.src)) else 0
         g_oob = (self.impl == 1 and gC % 64 != 0 and gC % 8 == 0 and os.environ.get('RNR_CONV_OOB', '1') != '0')
         gbk = 64 if g_oob else self._bk_for([gC])
         gK = _rup(gC, 64) if g_oob else gC            # K extent of the gradient operand (chunks past gC are zero-filled by the TMA)
@@ -680,7 +765,7 @@ class UNetEngine:
             st.wmat_dgrad = wmat_desc(wm, 9 * gK, self.grad_dt, 9, nci_pad, [tapoffs], r0, r1, ok=bool(gch))
             st.dgrad_plans.append(self._conv_problem(
                 [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp, Wp, st.gx, self.grad_dt,
-                (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
+                (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (1, 1, 0, 0), depi, None, None, 0, self.impl))
         elif sp.kind == 'c4s2':
             Hp, Wp = Hi + 2, Wi + 2
             st.gx = self._alloc((N, Hp, Wp, nci_pad), gdt_t, zero=True)
@@ -701,7 +786,7 @@ class UNetEngine:
                                                  cin_tot * 16, self._tapoff(tapoffs), chunked=gch))
                     probs.append(self._conv_problem(
                         [G.padded()], ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hp // 2, Wp // 2, st.gx, self.grad_dt,
-                        (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (2, 2, ph, pw), 0, None, None, 0, self.impl, defer=True))
+                        (Hp * Wp * nci_pad, Wp * nci_pad, nci_pad), (2, 2, ph, pw), depi, None, None, 0, self.impl, defer=True))
             st.wmat_dgrad = wmat_desc(wm_all, 4 * gK, self.grad_dt, 4, nci_pad, dsub_taps, r0, r1, ok=bool(gbk == 64))
             self.keep.append(probs)
             fused = self._fused_plan(probs, self.impl)
@@ -726,7 +811,7 @@ class UNetEngine:
             st.wmat_dgrad = wmat_desc(wm, 16 * gK, self.grad_dt, 16, nci_pad, [tapoffs], r0, r1, ok=bool(gch))
             st.dgrad_plans.append(self._conv_problem(
                 gviews, ks, self.grad_dt, gbk, wm, nci_pad, nci_pad, N, Hi, Wi, st.gx, self.grad_dt,
-                (Hi * Wi * nci_pad, Wi * nci_pad, nci_pad), (1, 1, 0, 0), 0, None, None, 0, self.impl))
+                (Hi * Wi * nci_pad, Wi * nci_pad, nci_pad), (1, 1, 0, 0), depi, None, None, 0, self.impl))
 
     # ------------------------------------------------------------------------------------------
     # execution
@@ -982,10 +1067,22 @@ class UNetEngine:
         if not getattr(self, 'bn_training', True) and any(sp.bn_key for sp in self.specs):
             raise NotImplementedError('backward through BatchNorm in eval() mode (running statistics) is not implemented: the '
                                       'reference scripts always differentiate with BatchNorm in train() mode')
+        self._refresh_gstats()
         for sp in reversed(self.specs):
             st = self.layers[sp.name]
             Ho, Wo, Cc = sp.Ho, sp.Wo, sp.cout
-            if sp.dst != 'out':
+            if sp.dst != 'out' and sp.name in self.gstat_layers:
+                # the consumers' data-gradient launches already accumulated sum(gg), sum(gg * (raw - mean)): one apply pass
+                srcs = self._gsrcs_for(sp.dst)
+                arr = (GSrc * len(srcs))(*srcs)
+                _lib.check(L.rnr_bn_bwd_apply_src(arr, len(srcs), st.raw.data_ptr(), self.raw_dt, st.scale.data_ptr(), st.shift.data_ptr(),
+                                                  st.mean.data_ptr(), st.invstd.data_ptr(), self.params[sp.bn_key + '.weight'].data_ptr(),
+                                                  st.drop.data_ptr() if st.drop is not None else None, sp.slope, self.gz[sp.name].ptr,
+                                                  st.bwd_totals.data_ptr(), st.ticket.data_ptr(), float(N * Ho * Wo),
+                                                  self.grad_view(sp.bn_key + '.weight').data_ptr(),
+                                                  self.grad_view(sp.bn_key + '.bias').data_ptr(), N, Ho, Wo, Cc, s), 'rnr_bn_bwd_apply_src')
+                self.gpu_launches += 1
+            elif sp.dst != 'out':
                 srcs = self._gsrcs_for(sp.dst)
                 assert 1 <= len(srcs) <= 2, (sp.name, len(srcs))
                 arr = (GSrc * len(srcs))(*srcs)
