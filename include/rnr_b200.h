@@ -539,6 +539,20 @@ int rnr_nr_create_texture_image(const float* vertices_all, const float* textures
 int rnr_metric_sums(const float* est, const float* gt, const float* mask, int N, int C, int H, int W, int* box,
                     unsigned long long* cnt, double* sums, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Light-probe stitching: stitch_lp.py:22-35 (camera2ray, spherical_mapping),  */
+/* :136-150 (per-view scatter into the equirect probe, final division).  Per view: img [h,w,3]    */
+/* fp32 and bg [h,w] uint8 (non-zero = background pixel) on the device, kinv / rinv = 9 doubles   */
+/* on the HOST (inverse intrinsics, inverse pose rotation).  numpy's fancy-index "+=" adds only the */
+/* LAST pixel (row-major order) that maps to a texel and counts one hit per view: reproduced with   */
+/* an atomicMax bid per texel.  texel [h*w] int32 scratch; winner [lp_h*lp_w] int32 = -1 before the */
+/* first view (restored by every call); env [lp_h,lp_w,3] fp64, count [lp_h,lp_w,3] fp32 zeroed by  */
+/* the caller, accumulated over views; rnr_stitch_finish divides and writes mask (255 = hit).      */
+/* ------------------------------------------------------------------------------------------ */
+int rnr_stitch_view(const float* img, const unsigned char* bg, const double* kinv, const double* rinv, int h, int w, int lp_h,
+                    int lp_w, int* texel, int* winner, double* env, float* count, void* stream);
+int rnr_stitch_finish(double* env, const float* count, unsigned char* mask, int lp_h, int lp_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

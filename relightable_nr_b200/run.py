@@ -82,7 +82,12 @@ def install_shims():
         tg.utils = _stub('torch_geometric.utils')
     _stub('torch_cluster', knn_graph=None)
     _stub('pyshtools')
-    _stub('trimesh')
+    # trimesh.load(obj, process=False).vertices / .faces (stitch_lp.py:96-97)
+    try:
+        importlib.import_module('trimesh')
+    except Exception:
+        from .compat import trimesh as _trimesh_mod
+        sys.modules['trimesh'] = _trimesh_mod
     # pytorch_msssim.ssim: called by the validation pass of the training scripts (metric.py:78-84), which the unchanged
     # train_rnr.py / train_dnr.py execute at iteration 0 -- a real Gaussian-window SSIM, not a stub
     try:

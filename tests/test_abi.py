@@ -28,7 +28,7 @@ def test_header_cites_reference_lines():
 
 def test_python_bindings_cover_header():
     """Every declared function has ctypes argtypes registered once the host modules are imported."""
-    from relightable_nr_b200 import ops, fused, metrics  # noqa: F401
+    from relightable_nr_b200 import ops, fused, metrics, stitch  # noqa: F401
     from relightable_nr_b200.dropin import camera, render, sph_harm, neural_renderer  # noqa: F401
     from relightable_nr_b200.dropin.gcn_lib import dense  # noqa: F401
     L = _lib.lib()

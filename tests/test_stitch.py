@@ -1,0 +1,121 @@
+"""Light-probe stitching: stitch_lp.py:95-159.
+
+* CPU: the UNCHANGED stitch_lp.py, run through the launcher (trimesh stand-in from relightable_nr_b200/compat) on a synthetic
+  scene, against the numpy restatement of its scatter (oracle/stitch.py) fed with the product's host-side silhouette mask
+  (relightable_nr_b200.stitch.background_mask) -- this pins both: PNG / EXR / mask / count files identical.
+* GPU: the device stitcher (csrc/stitch.cu, fp64, last-write-wins scatter) against the same restatement: hit counts and mask
+  identical on >= 99.99 % of the probe texels (an ulp of difference between numpy's BLAS dot and the kernel's multiply-adds may
+  move a ray across a texel border), colours within 1e-6 on the agreeing texels; and the module's command line against the files
+  of the unchanged script.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.golden import ref_import
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = ref_import.REF
+SIZE, LP_H, LP_W = 128, 100, 200
+
+
+@pytest.fixture(scope='module')
+def scene(tmp_path_factory):
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import make_scene
+    root = str(tmp_path_factory.mktemp('stitch_scene'))
+    make_scene.make_scene(root, n_views=5, n_test_views=1, img_size=SIZE, mesh_lat=24, mesh_lon=48)
+    for k in range(5):          # stitch_lp.py:125 reads rgb<k>/%06d<suffix>
+        shutil.copy(os.path.join(root, 'rgb0', '%05d.png' % k), os.path.join(root, 'rgb0', '%06d.png' % k))
+    return root
+
+
+def _expected(root, pattern):
+    import cv2
+    import scipy.io
+    from oracle import stitch as ost
+    from relightable_nr_b200.stitch import background_mask, read_obj_geometry, selected_views
+    calib = scipy.io.loadmat(os.path.join(root, 'calib.mat'))
+    v, f = read_obj_geometry(os.path.join(root, 'mesh.obj'))
+    gRT = calib['global_RT']
+    vh = gRT.dot(np.hstack((v, np.ones((v.shape[0], 1)))).T)
+    env = np.zeros((LP_H, LP_W, 3))
+    count = np.zeros((LP_H, LP_W, 3), np.float32)
+    for i in selected_views(calib['poses'].shape[0], pattern):
+        h, w = int(calib['img_hws'][i, 0]), int(calib['img_hws'][i, 1])
+        pose = calib['poses'][i].dot(np.linalg.inv(gRT))
+        img = cv2.imread(os.path.join(root, 'rgb0', '%06d.png' % i), cv2.IMREAD_UNCHANGED).astype(np.float32)[:, :, :3] / 255.
+        ost.scatter_view(env, count, img, background_mask(vh, f, pose, calib['projs'][i], h, w), pose, calib['projs'][i])
+    env, mask = ost.finish(env, count)
+    return env, mask, count, int(calib['poses'].shape[0])
+
+
+def _run_reference(root, pattern):
+    if not ref_import.available():
+        pytest.skip('reference scripts not staged (run tools/stage_reference.py in the build container)')
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''), OPENCV_IO_ENABLE_OPENEXR='1')
+    r = subprocess.run([sys.executable, '-m', 'relightable_nr_b200.run', os.path.join(REF, 'stitch_lp.py'), '--data_root', root,
+                        '--sampling_pattern', pattern, '--img_suffix', '.png', '--lp_h', str(LP_H), '--lp_w', str(LP_W)],
+                       cwd=REF, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return os.path.join(root, 'light_probe_stitch_' + pattern)
+
+
+def _read_outputs(d):
+    import cv2
+    os.environ.setdefault('OPENCV_IO_ENABLE_OPENEXR', '1')
+    return (cv2.imread(os.path.join(d, '0.png'), cv2.IMREAD_UNCHANGED), cv2.imread(os.path.join(d, '0.exr'), cv2.IMREAD_UNCHANGED),
+            cv2.imread(os.path.join(d, 'mask', '0.png'), cv2.IMREAD_UNCHANGED), cv2.imread(os.path.join(d, 'count', '0.png'), cv2.IMREAD_UNCHANGED))
+
+
+@pytest.mark.parametrize('pattern', ['all', 'skipinv_2'])
+def test_restatement_matches_the_unchanged_script(scene, pattern):
+    out = _run_reference(scene, pattern)
+    png, exr, mask_png, count_png = _read_outputs(out)
+    env, mask, count, num_view = _expected(scene, pattern)
+    assert mask.any() and not mask.all()
+    assert np.array_equal(mask_png, (mask * 255).astype('uint8'))
+    assert np.array_equal(count_png, (count / float(num_view) * 255.0).astype('uint8'))
+    assert np.array_equal(png, (env * 255).astype('uint8'))
+    assert np.array_equal(exr, env.astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('pattern', ['all', 'skipinv_2'])
+def test_device_stitcher_matches_the_restatement(scene, pattern):
+    import cv2
+    import scipy.io
+    from relightable_nr_b200.stitch import read_obj_geometry, stitch_scene
+    calib = scipy.io.loadmat(os.path.join(scene, 'calib.mat'))
+    v, f = read_obj_geometry(os.path.join(scene, 'mesh.obj'))
+    rd = lambda i: cv2.imread(os.path.join(scene, 'rgb0', '%06d.png' % i), cv2.IMREAD_UNCHANGED).astype(np.float32)[:, :, :3] / 255.
+    env, mask, count, num_view = stitch_scene(calib, v, f, rd, pattern, LP_H, LP_W)
+    e_env, e_mask, e_count, _ = _expected(scene, pattern)
+    same = (count == e_count).all(-1)
+    print('texels with identical hit counts: %d of %d; probe coverage %.1f %%' % (same.sum(), same.size, 100.0 * e_mask.mean()))
+    assert same.mean() >= 0.9999
+    assert (mask == e_mask)[same].all()
+    assert np.abs(env - e_env)[same].max() <= 1e-6
+    # a second pass over the same views on a fresh stitcher gives the same probe bit for bit (atomicMax bids are order-free)
+    env2, mask2, count2, _ = stitch_scene(calib, v, f, rd, pattern, LP_H, LP_W)
+    assert np.array_equal(env, env2) and np.array_equal(count, count2)
+
+
+@pytest.mark.gpu
+def test_command_line_writes_the_files_of_the_unchanged_script(scene):
+    ref_dir = _run_reference(scene, 'skipinv_3')
+    ref = _read_outputs(ref_dir)
+    shutil.move(ref_dir, ref_dir + '_reference')
+    from relightable_nr_b200 import stitch
+    assert stitch.main(['--data_root', scene, '--sampling_pattern', 'skipinv_3', '--img_suffix', '.png', '--lp_h', str(LP_H),
+                        '--lp_w', str(LP_W)]) == 0
+    got = _read_outputs(ref_dir)
+    for name, a, b in zip(('png', 'exr', 'mask', 'count'), got, ref):
+        assert a.shape == b.shape and a.dtype == b.dtype, name
+        diff = (a != b).reshape(a.shape[0] * a.shape[1], -1).any(-1).mean()
+        print('%s: %.4f %% of the texels differ' % (name, 100.0 * diff))
+        assert diff <= 1e-4, name
