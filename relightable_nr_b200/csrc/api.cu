@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Library info + error plumbing of librnr_b200.so.
 #include "common.cuh"
 #include <stdarg.h>
@@ -23,4 +24,11 @@ extern "C" int rnr_device_sm_count(int device) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
     return n;
+}
+
+// RNR_PDL=0 disables programmatic dependent launch (common.cuh); read once.
+int rnr_pdl_enabled(void) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RNR_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
 }

@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
                                    float* mean, float* invstd, float* scale, float* shift,
                                    float* running_mean, float* running_var, float momentum) {
     __shared__ double s_s[16][33], s_q[16][33];
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;   // 16 warps
     const int c = blockIdx.x * 32 + lane;
     double s = 0.0, q = 0.0;
@@ -67,6 +69,8 @@ __device__ __forceinline__ void load_raw8(const void* raw, int64_t idx, int dtyp
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const void* __restrict__ raw, int raw_dtype, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ drop, float slope,
                                   __half* __restrict__ act, __nv_bfloat16* __restrict__ act_b, int N, int H, int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     // grid.y = image row (n*H + h); threads of a row = (w, 8-channel vector): 32-bit index math only
     const unsigned vpp = (unsigned)C >> 3;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,6 +297,8 @@ __global__ void __launch_bounds__(512, 1) bn_bwd_reduce_fin_kernel(const GSrcs s
                                      int N, int H, int W, int C, int ppb, int prow, int lhw, int lw) {
     extern __shared__ float smem[];    // [prow][2C] partial rows
     __shared__ int s_last;
+    pdl_launch_dependents();
+    pdl_wait();
     float* s_part = smem;
     const int vpp = C >> 3;
     const int cv = threadIdx.x % vpp, pl = threadIdx.x / vpp;
@@ -456,6 +462,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_src_kernel(const GSrcs sr
                                      int N, int H, int W, int C, int lhw, int lw, int PB) {
     extern __shared__ __align__(16) float s_coef[];      // [5][C]: A, B, D, scale, shift
     __shared__ int s_last;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int ch = threadIdx.x; ch < C; ch += 256) {
         const double sv = __ldcg(totals + ch);
         const double is = (double)invstd[ch];
@@ -604,6 +612,8 @@ __global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __res
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __restrict__ gz, const void* __restrict__ raw, int raw_dtype,
                                     const float* __restrict__ coef, int N, int H, int W, int C) {
     // gz <- A*gz + B*raw + D with the per-channel coefficients of bn_bwd_finalize (3 vector loads instead of 5x8 scalars)
+    pdl_launch_dependents();
+    pdl_wait();
     const unsigned vpp = (unsigned)C >> 3;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)W * vpp) return;
@@ -634,8 +644,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(__nv_bfloat16* __rest
 extern "C" int rnr_bn_finalize(const float* partials, int T, int ld, int C, double count, const float* gamma,
                                const float* beta, float eps, float* mean, float* invstd, float* scale, float* shift,
                                float* running_mean, float* running_var, float momentum, void* stream) {
-    bn_finalize_kernel<<<rnr_cdiv(C, 32), 512, 0, (cudaStream_t)stream>>>(partials, T, ld, C, count, gamma, beta, eps, mean,
-                                                                        invstd, scale, shift, running_mean, running_var, momentum);
+    RNR_PDL_LAUNCH(bn_finalize_kernel, rnr_cdiv(C, 32), 512, 0, stream, partials, T, ld, C, count, gamma, beta, eps, mean,
+                   invstd, scale, shift, running_mean, running_var, momentum);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -646,7 +656,7 @@ extern "C" int rnr_bn_act_fwd(const void* raw, int raw_dtype, const float* scale
     RNR_REQUIRE(H >= 2 && W >= 2, "rnr_bn_act_fwd: reflect halo needs H,W >= 2");
     RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_act_fwd: N*H=%lld exceeds the grid limit", (long long)N * H);
     dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
-    bn_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, raw_dtype, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
+    RNR_PDL_LAUNCH(bn_act_fwd_kernel, grid, 256, 0, stream, raw, raw_dtype, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -718,7 +728,7 @@ extern "C" int rnr_bn_bwd_reduce_fin(const rnr_gsrc_t* srcs, int nsrc, const voi
 #define RNR_BN_LAUNCH(NS, RU)                                                                                                        \
     do {                                                                                                                             \
         RNR_ONCE_PER_DEVICE({ RNR_CHECK(cudaFuncSetAttribute(bn_bwd_reduce_fin_kernel<NS, RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); }); \
-        bn_bwd_reduce_fin_kernel<NS, RU><<<T, threads, smem, (cudaStream_t)stream>>>(                                                \
+        RNR_PDL_LAUNCH((bn_bwd_reduce_fin_kernel<NS, RU>), T, threads, smem, stream,                                                \
             gs, raw, raw_dtype, scale, shift, mean, invstd, drop, slope, (__nv_bfloat16*)gz, totals, ticket, count, dgamma, dbeta,   \
             gamma, coef, N, H, W, C, ppb, prow, lhw, lw);                                                                            \
     } while (0)
@@ -760,11 +770,11 @@ extern "C" int rnr_bn_bwd_apply_src(const rnr_gsrc_t* srcs, int nsrc, const void
         }
     }
     if (nsrc == 1)
-        bn_bwd_apply_src_kernel<1><<<blocks, 256, smem, (cudaStream_t)stream>>>(gs, raw, raw_dtype, scale, shift, mean, invstd, gamma, drop, slope,
+        RNR_PDL_LAUNCH(bn_bwd_apply_src_kernel<1>, blocks, 256, smem, stream, gs, raw, raw_dtype, scale, shift, mean, invstd, gamma, drop, slope,
                                                                              (__nv_bfloat16*)gz, totals, ticket, 1.0 / count, dgamma, dbeta,
                                                                              N, H, W, C, lhw, lw, PB);
     else
-        bn_bwd_apply_src_kernel<2><<<blocks, 256, smem, (cudaStream_t)stream>>>(gs, raw, raw_dtype, scale, shift, mean, invstd, gamma, drop, slope,
+        RNR_PDL_LAUNCH(bn_bwd_apply_src_kernel<2>, blocks, 256, smem, stream, gs, raw, raw_dtype, scale, shift, mean, invstd, gamma, drop, slope,
                                                                              (__nv_bfloat16*)gz, totals, ticket, 1.0 / count, dgamma, dbeta,
                                                                              N, H, W, C, lhw, lw, PB);
     RNR_LAUNCH_CHECK();
@@ -785,7 +795,7 @@ extern "C" int rnr_bn_bwd_apply(void* gz, const void* raw, int raw_dtype, const 
     RNR_REQUIRE(C % 8 == 0, "rnr_bn_bwd_apply: C=%d must be a multiple of 8", C);
     RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_bwd_apply: N*H=%lld exceeds the grid limit", (long long)N * H);
     dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
-    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)gz, raw, raw_dtype, coef, N, H, W, C);
+    RNR_PDL_LAUNCH(bn_bwd_apply_kernel, grid, 256, 0, stream, (__nv_bfloat16*)gz, raw, raw_dtype, coef, N, H, W, C);
     RNR_LAUNCH_CHECK();
     return 0;
 }

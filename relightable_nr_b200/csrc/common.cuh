@@ -53,6 +53,43 @@ void rnr_count_launch(void);          // every kernel launch of the library is c
         }                                                                                 \
     } while (0)
 
+// ---- programmatic dependent launch ------------------------------------------------------------
+// The training step is a chain of ~145 short dependent launches; with plain stream order every one of them pays the launch latency
+// and its own prologue (barrier / TMEM set-up, constant loads) AFTER its predecessor has drained.  Kernels on that chain are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization (RNR_PDL_LAUNCH) and
+//   * call pdl_launch_dependents() first: once every CTA of the grid has started, the NEXT kernel of the stream may be scheduled
+//     onto whatever SM resources are free;
+//   * call pdl_wait() before they touch anything a predecessor wrote (or overwrite anything it reads): it returns when all
+//     prerequisite grids have completed and flushed.  Everything above the wait -- launch latency, set-up, loads of plan
+//     constants -- overlaps the predecessor's tail.
+// A kernel that takes the attribute MUST execute pdl_wait(); without the attribute both instructions are no-ops.
+// RNR_PDL=0 launches everything with plain stream order.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+int rnr_pdl_enabled(void);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rnr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = rnr_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define RNR_PDL_LAUNCH(kernel, grid, block, smem, stream, ...)                                         \
+    do {                                                                                               \
+        cudaError_t _le = rnr_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__); \
+        if (_le != cudaSuccess) {                                                                      \
+            rnr_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_le));  \
+            return (int)_le;                                                                           \
+        }                                                                                              \
+    } while (0)
+
 static inline int rnr_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int rnr_dtype_size(int dt) { return dt == RNR_F32 ? 4 : 2; }
 

@@ -110,6 +110,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     long long* tr = (g_trace && blockIdx.x < 4) ? g_trace + (size_t)blockIdx.x * 4 * 64 : nullptr;
     int ti = 0;
     if (threadIdx.x == 0) { int z = 0; trace(tr, 3, z); }
+    if (dbg & 256) pdl_launch_dependents();
 
     for (int i = threadIdx.x; i < n_groups * hc.nsub; i += kThreads) s_groups[i] = groups[i];
     for (int i = threadIdx.x; i < n_taps; i += kThreads) s_taps[i] = taps[i];
@@ -139,7 +140,6 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         // stream was still running -- everything above (barrier init, TMEM allocation, table loads of constant plan data) overlaps
         // the predecessor's tail; no activation / weight byte is touched before the predecessor has completed and flushed
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
 
     if (warp == kProducerWarp) {
@@ -779,7 +779,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
         RNR_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     });
     { const char* d = getenv("RNR_CONV_DBG"); pl->dbg = d ? atoi(d) : 0; }
-    { const char* d = getenv("RNR_PDL"); if (d && atoi(d) != 0) pl->dbg |= 256; }
+    if (rnr_pdl_enabled()) pl->dbg |= 256;      // programmatic dependent launch (common.cuh)
     pl->halo = 1;
     return 0;
 }

@@ -46,6 +46,8 @@ struct HeadParams {
 };
 
 __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(const HeadParams q) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     const int R = q.Rs + q.Rd;
     float* s_out = sm;                                   // [kHeadPx][Cpad]
@@ -257,6 +259,8 @@ __device__ __forceinline__ float block_sum256(float v, float* s_tmp) {
 }
 
 __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailParams q) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_dyn[];
     const int kRawPitch = raw_pitch(q.R), kUvPitch = uv_pitch(q.R);
     float* s_raw = s_dyn;                              // [32][kRawPitch]: tanh outputs, then rays_lt * envmap colour
@@ -367,6 +371,8 @@ struct TailBwdParams {
 };
 
 __global__ void __launch_bounds__(kTailThreads) tail_bwd_kernel(const TailBwdParams qq) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_dyn[];
     const TailParams& q = qq.f;
     const int kRawPitch = raw_pitch(q.R), kUvPitch = uv_pitch(q.R);
@@ -499,7 +505,7 @@ extern "C" int rnr_head_fwd(const float* const* tex, const int* sizes, int n_lev
     RNR_ONCE_PER_DEVICE({ RNR_CHECK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); });
     RNR_REQUIRE(smem <= 64 * 1024, "head: shared memory %zu too large", smem);
     const int64_t P = (int64_t)N * H * W;
-    head_fwd_kernel<<<rnr_cdiv(P, kHeadPx), kHeadThreads, smem, (cudaStream_t)stream>>>(q);
+    RNR_PDL_LAUNCH(head_fwd_kernel, rnr_cdiv(P, kHeadPx), kHeadThreads, smem, stream, q);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -540,7 +546,7 @@ extern "C" int rnr_tail_fwd(const float* raw, int ldraw, const float* rays_uv, c
     });
     int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    tail_fwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(q);
+    RNR_PDL_LAUNCH(tail_fwd_kernel, blocks, kTailThreads, smem, stream, q);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -565,7 +571,7 @@ extern "C" int rnr_tail_bwd(const float* raw, int ldraw, const float* rays_uv, c
     });
     int blocks = rnr_cdiv((int64_t)N * H * W, kTailPx);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    tail_bwd_kernel<<<blocks, kTailThreads, smem, (cudaStream_t)stream>>>(qq);
+    RNR_PDL_LAUNCH(tail_bwd_kernel, blocks, kTailThreads, smem, stream, qq);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -11,6 +11,8 @@ constexpr int TP = 32;   // pixels per tile (along w)
 // NCHW fp32 -> fp16 [N,H+2,W+2,Cpad] with reflect halo, channels >= C zero-filled
 __global__ void __launch_bounds__(256) pack_nchw_to_act_kernel(const float* __restrict__ src, __half* __restrict__ act,
                                                              __nv_bfloat16* __restrict__ act_b, int N, int C, int Cpad, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float tile[];   // [Cpad][TP+1]
     const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -54,6 +56,8 @@ __global__ void __launch_bounds__(256) pack_nchw_to_act_kernel(const float* __re
 // fp32 NHWC [N,H,W,ld] -> NCHW [N,C,H,W]
 __global__ void __launch_bounds__(256) unpack_nhwc_to_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                                 int N, int C, int ld, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float tile[];   // [C][TP+1]
     const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
     for (int i = threadIdx.x; i < TP * C; i += 256) {
@@ -74,6 +78,8 @@ constexpr int TANH_MAXC8 = 16;       // ld <= 128
 __global__ void __launch_bounds__(256) tanh_bwd_pack_kernel(const float* __restrict__ grad, const float* __restrict__ th,
                                                           __nv_bfloat16* __restrict__ gz, float* __restrict__ dbias,
                                                           int N, int C, int ld, int H, int W) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float tile[];   // [ld][TP+1]
     const int w0 = blockIdx.x * TP, n = blockIdx.z;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -128,6 +134,8 @@ __global__ void __launch_bounds__(256) tanh_bwd_pack_kernel(const float* __restr
 __global__ void __launch_bounds__(256) fold_to_nchw_kernel(const void* __restrict__ gpad, int dtype, float* __restrict__ dst,
                                                          int N, int C, int c0, int ld, int H, int W,
                                                          const float* __restrict__ add, int nadd) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float tile[];   // [C][TP+1]
     const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
     const int Hp = H + 2, Wp = W + 2;
@@ -167,7 +175,7 @@ extern "C" int rnr_pack_nchw_to_act(const float* src, void* act, void* act_bf16,
     const size_t smem = (size_t)Cpad * (TP + 1) * sizeof(float);
     RNR_REQUIRE(smem <= 48 * 1024, "rnr_pack_nchw_to_act: too many channels (%d)", Cpad);
     dim3 grid(rnr_cdiv(W, TP), H, N);
-    pack_nchw_to_act_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, (__half*)act, (__nv_bfloat16*)act_bf16, N, C, Cpad, H, W);
+    RNR_PDL_LAUNCH(pack_nchw_to_act_kernel, grid, 256, smem, stream, src, (__half*)act, (__nv_bfloat16*)act_bf16, N, C, Cpad, H, W);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -176,7 +184,7 @@ extern "C" int rnr_unpack_nhwc_to_nchw(const float* src, float* dst, int N, int 
     const size_t smem = (size_t)C * (TP + 1) * sizeof(float);
     RNR_REQUIRE(smem <= 48 * 1024, "rnr_unpack_nhwc_to_nchw: too many channels (%d)", C);
     dim3 grid(rnr_cdiv(W, TP), H, N);
-    unpack_nhwc_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(src, dst, N, C, ld, H, W);
+    RNR_PDL_LAUNCH(unpack_nhwc_to_nchw_kernel, grid, 256, smem, stream, src, dst, N, C, ld, H, W);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -186,7 +194,7 @@ extern "C" int rnr_tanh_bwd_pack(const float* grad_nchw, const float* tanh_nhwc,
     const size_t smem = (size_t)ld * (TP + 1) * sizeof(float);
     RNR_REQUIRE(smem <= 48 * 1024 && ld <= 8 * TANH_MAXC8, "rnr_tanh_bwd_pack: too many channels (%d)", ld);
     dim3 grid(rnr_cdiv(W, TP), rnr_cdiv(H, TANH_ROWS), N);
-    tanh_bwd_pack_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(grad_nchw, tanh_nhwc, (__nv_bfloat16*)gz, dbias, N, C, ld, H, W);
+    RNR_PDL_LAUNCH(tanh_bwd_pack_kernel, grid, 256, smem, stream, grad_nchw, tanh_nhwc, (__nv_bfloat16*)gz, dbias, N, C, ld, H, W);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -196,7 +204,7 @@ extern "C" int rnr_fold_to_nchw(const void* gpad, int dtype, float* dst, int N, 
     const size_t smem = (size_t)C * (TP + 1) * sizeof(float);
     RNR_REQUIRE(smem <= 48 * 1024, "rnr_fold_to_nchw: too many channels (%d)", C);
     dim3 grid(rnr_cdiv(W, TP), H, N);
-    fold_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gpad, dtype, dst, N, C, c0, ld, H, W, nullptr, 0);
+    RNR_PDL_LAUNCH(fold_to_nchw_kernel, grid, 256, smem, stream, gpad, dtype, dst, N, C, c0, ld, H, W, nullptr, 0);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -208,7 +216,7 @@ extern "C" int rnr_fold_to_nchw_add(const void* gpad, int dtype, float* dst, int
     RNR_REQUIRE(smem <= 48 * 1024, "rnr_fold_to_nchw_add: too many channels (%d)", C);
     RNR_REQUIRE(nadd >= 0 && nadd <= C && (nadd == 0 || add), "rnr_fold_to_nchw_add: bad add tensor");
     dim3 grid(rnr_cdiv(W, TP), H, N);
-    fold_to_nchw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gpad, dtype, dst, N, C, c0, ld, H, W, add, nadd);
+    RNR_PDL_LAUNCH(fold_to_nchw_kernel, grid, 256, smem, stream, gpad, dtype, dst, N, C, c0, ld, H, W, add, nadd);
     RNR_LAUNCH_CHECK();
     return 0;
 }

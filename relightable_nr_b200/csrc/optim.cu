@@ -65,6 +65,8 @@ struct AdamWJob {
 //   4. data-gradient GEMM matrix: row ci, columns [co chunk][tap slot][64 co]      -> the block's 8 co = one 16-byte store per (ci, tap)
 __global__ void __launch_bounds__(256) adam_wunpack_kernel(const AdamWJob* __restrict__ jobs, const int* __restrict__ blk2job,
                                                          const float* __restrict__ step, const AdamHyper h, int zero_src) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[UCO][MAXT][CB + 1];
     const AdamWJob& J = jobs[blk2job[blockIdx.x]];
     const int local = blockIdx.x - J.blk0;
@@ -166,6 +168,8 @@ constexpr int kAdamChunk = 2048;     // elements per block: 256 threads x 2 x fl
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restrict__ jobs, const int* __restrict__ blk2job, float* step,
                                                        int* ticket, const AdamHyper h, int zero_grad, int advance_step) {
+    pdl_launch_dependents();
+    pdl_wait();
     const AdamJob& J = jobs[blk2job[blockIdx.x]];
     const int64_t e0 = (int64_t)(blockIdx.x - J.blk0) * kAdamChunk;
     const int64_t n = min((int64_t)kAdamChunk, J.n - e0);
@@ -214,6 +218,8 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restri
 // loss_rays_lt_chrom + loss_alb), from the device-side accumulators of the tail / small-loss kernels
 __global__ void loss_combine_kernel(double* __restrict__ sums, double cnt, double R, double w_chrom, const double* __restrict__ extra,
                                     int n_extra, float* __restrict__ out, int n_clear) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double l = sums[2] / cnt + (sums[1] != 0.0 ? sums[0] / sums[1] / R * w_chrom : 0.0);
         for (int i = 0; i < n_extra; i++) l += extra[i];
@@ -233,6 +239,8 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 // every launch draws fresh masks without host involvement (CUDA-graph replays included); one block.
 __global__ void __launch_bounds__(1024) dropout_mask_kernel(float* __restrict__ out, int n, float p, unsigned long long seed,
                                                           unsigned long long* counter) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ unsigned long long s_ctr;
     if (threadIdx.x == 0) s_ctr = *counter;
     __syncthreads();
@@ -346,11 +354,11 @@ extern "C" int rnr_adam_run(const rnr_adam_plan_t* p, float* step, float lr, flo
     RNR_REQUIRE(!advance_step || p->blocks > 0, "rnr_adam_run: advance_step needs at least one tensor job in the plan");
     AdamHyper h{lr, beta1, beta2, eps, gscale};
     if (p->wblocks > 0) {
-        adam_wunpack_kernel<<<p->wblocks, 256, 0, (cudaStream_t)stream>>>(p->d_wjobs, p->d_wblk, step, h, zero_grad);
+        RNR_PDL_LAUNCH(adam_wunpack_kernel, p->wblocks, 256, 0, stream, p->d_wjobs, p->d_wblk, step, h, zero_grad);
         RNR_LAUNCH_CHECK();
     }
     if (p->blocks > 0) {
-        adam_multi_kernel<<<p->blocks, 256, 0, (cudaStream_t)stream>>>(p->d_jobs, p->d_blk, step, p->d_ticket, h, zero_grad, advance_step);
+        RNR_PDL_LAUNCH(adam_multi_kernel, p->blocks, 256, 0, stream, p->d_jobs, p->d_blk, step, p->d_ticket, h, zero_grad, advance_step);
         RNR_LAUNCH_CHECK();
     }
     return 0;
@@ -359,14 +367,14 @@ extern "C" int rnr_adam_run(const rnr_adam_plan_t* p, float* step, float lr, flo
 extern "C" int rnr_loss_combine(double* sums, double cnt, double R, double w_chrom, const double* extra, int n_extra, float* out,
                                 int n_clear, void* stream) {
     RNR_REQUIRE(sums && out && cnt > 0 && R > 0, "rnr_loss_combine: bad arguments");
-    loss_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, cnt, R, w_chrom, extra, n_extra, out, n_clear);
+    RNR_PDL_LAUNCH(loss_combine_kernel, 1, 32, 0, stream, sums, cnt, R, w_chrom, extra, n_extra, out, n_clear);
     RNR_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int rnr_dropout_masks(float* out, int n, float p, unsigned long long seed, unsigned long long* counter, void* stream) {
     RNR_REQUIRE(out && counter && n >= 1 && p >= 0.f && p < 1.f, "rnr_dropout_masks: bad arguments");
-    dropout_mask_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(out, n, p, seed, counter);
+    RNR_PDL_LAUNCH(dropout_mask_kernel, 1, 1024, 0, stream, out, n, p, seed, counter);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(128) sh_basis_general_kernel(const float* __re
 // out[l, p, c] = sum_b basis[p, b] * coeff[l, b, c]        one warp per (l, p)
 __global__ void __launch_bounds__(256) sh_reconstruct_kernel(const float* __restrict__ basis, const float* __restrict__ coeff,
                                                            float* __restrict__ out, int64_t P, int B, int Cc, int Lc, int ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= P * Lc) return;
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(256) sh_reconstruct_kernel(const float* __rest
 __global__ void __launch_bounds__(128) sh_project_kernel(const float* __restrict__ basis, float* __restrict__ v,
                                                        float* __restrict__ res, int64_t P, int B, int Cc, int Lc, float scale,
                                                        int chunk, int ldv, int zero_v) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_v[];    // [chunk][Cc]
     const int l = blockIdx.y;
     const int64_t p0 = (int64_t)blockIdx.x * chunk;
@@ -177,7 +181,7 @@ extern "C" int rnr_sh_basis(const float* dirs, double* out, int64_t P, int lmax,
 extern "C" int rnr_sh_reconstruct(const float* basis, const float* coeff, float* out, int64_t P, int B, int Cc, int Lc,
                                   void* stream) {
     if (P * Lc == 0) return 0;
-    sh_reconstruct_kernel<<<rnr_cdiv(P * Lc * 32, 256), 256, 0, (cudaStream_t)stream>>>(basis, coeff, out, P, B, Cc, Lc, Cc);
+    RNR_PDL_LAUNCH(sh_reconstruct_kernel, rnr_cdiv(P * Lc * 32, 256), 256, 0, stream, basis, coeff, out, P, B, Cc, Lc, Cc);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -187,7 +191,7 @@ extern "C" int rnr_sh_reconstruct_ld(const float* basis, const float* coeff, flo
                                      void* stream) {
     RNR_REQUIRE(ldo >= Cc, "rnr_sh_reconstruct_ld: ldo %d < Cc %d", ldo, Cc);
     if (P == 0) return 0;
-    sh_reconstruct_kernel<<<rnr_cdiv(P * 32, 256), 256, 0, (cudaStream_t)stream>>>(basis, coeff, out, P, B, Cc, 1, ldo);
+    RNR_PDL_LAUNCH(sh_reconstruct_kernel, rnr_cdiv(P * 32, 256), 256, 0, stream, basis, coeff, out, P, B, Cc, 1, ldo);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -198,7 +202,7 @@ extern "C" int rnr_sh_project(const float* basis, const float* v, float* res, in
     int chunk = 256;
     RNR_REQUIRE((size_t)chunk * Cc * 4 <= 48 * 1024, "sh_project: too many channels (%d)", Cc);
     dim3 grid(rnr_cdiv(P, chunk), Lc);
-    sh_project_kernel<<<grid, 128, (size_t)chunk * Cc * 4, (cudaStream_t)stream>>>(basis, const_cast<float*>(v), res, P, B, Cc, Lc, scale, chunk, Cc, 0);
+    RNR_PDL_LAUNCH(sh_project_kernel, grid, 128, (size_t)chunk * Cc * 4, stream, basis, const_cast<float*>(v), res, P, B, Cc, Lc, scale, chunk, Cc, 0);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -212,7 +216,7 @@ extern "C" int rnr_sh_project_ld(const float* basis, float* v, float* res, int64
     int chunk = 256;
     RNR_REQUIRE((size_t)chunk * Cc * 4 <= 48 * 1024, "sh_project: too many channels (%d)", Cc);
     dim3 grid(rnr_cdiv(P, chunk), 1);
-    sh_project_kernel<<<grid, 128, (size_t)chunk * Cc * 4, (cudaStream_t)stream>>>(basis, v, res, P, B, Cc, 1, scale, chunk, ldv, zero_v);
+    RNR_PDL_LAUNCH(sh_project_kernel, grid, 128, (size_t)chunk * Cc * 4, stream, basis, v, res, P, B, Cc, 1, scale, chunk, ldv, zero_v);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256) lighting_l1_kernel(const float* __restric
                                                         const float* __restrict__ l_init, const unsigned char* __restrict__ mask,
                                                         int S, int B, float w_cov, float w_unc, float* __restrict__ sgn,
                                                         double* __restrict__ loss) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ double s_tmp[8];
     const int lane = threadIdx.x & 31;
     const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(256) lighting_l1_kernel(const float* __restric
 // sums[0] = #touched (diffuse, ch 0:3), sums[1] = #touched (specular, ch 3:6), sums[2 + c] = sum of channel c over its group's touched texels
 __global__ void __launch_bounds__(256) albedo_reduce_kernel(const float* __restrict__ tex6, const float* __restrict__ init6, int64_t P,
                                                           double* __restrict__ sums) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ double s_tmp[8];
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(256) albedo_reduce_kernel(const float* __restr
 __global__ void __launch_bounds__(256) albedo_grad_kernel(const float* __restrict__ tex6, const float* __restrict__ init6, int64_t P,
                                                         const double* __restrict__ sums, float w_alb, float* __restrict__ gout,
                                                         double* __restrict__ loss) {
+    pdl_launch_dependents();
+    pdl_wait();
     float gc[6];
     double l = 0.0;
 #pragma unroll
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(256) albedo_grad_kernel(const float* __restric
 extern "C" int rnr_lighting_l1(const float* basis, const float* coeff, const float* l_init, const unsigned char* mask, int S, int B,
                                float w_cov, float w_unc, float* sgn, double* loss, void* stream) {
     RNR_REQUIRE(basis && coeff && l_init && mask && sgn && loss && S >= 1 && B >= 1, "rnr_lighting_l1: bad arguments");
-    lighting_l1_kernel<<<rnr_cdiv((int64_t)S * 32, 256), 256, 0, (cudaStream_t)stream>>>(basis, coeff, l_init, mask, S, B, w_cov, w_unc, sgn, loss);
+    RNR_PDL_LAUNCH(lighting_l1_kernel, rnr_cdiv((int64_t)S * 32, 256), 256, 0, stream, basis, coeff, l_init, mask, S, B, w_cov, w_unc, sgn, loss);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -122,9 +128,9 @@ extern "C" int rnr_albedo_mean_loss(const float* tex6, const float* init6, int64
     RNR_REQUIRE(tex6 && init6 && sums && gout && loss && P >= 1, "rnr_albedo_mean_loss: bad arguments");
     int blocks = rnr_cdiv(P, 256);
     if (blocks > 148 * 4) blocks = 148 * 4;
-    albedo_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tex6, init6, P, sums);
+    RNR_PDL_LAUNCH(albedo_reduce_kernel, blocks, 256, 0, stream, tex6, init6, P, sums);
     RNR_LAUNCH_CHECK();
-    albedo_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tex6, init6, P, sums, w_alb, gout, loss);
+    RNR_PDL_LAUNCH(albedo_grad_kernel, blocks, 256, 0, stream, tex6, init6, P, sums, w_alb, gout, loss);
     RNR_LAUNCH_CHECK();
     return 0;
 }

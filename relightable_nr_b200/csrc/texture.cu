@@ -22,6 +22,8 @@ template <int CMAX>
 __global__ void __launch_bounds__(128) texmap_fwd_kernel(const TexLevels lv, int C, const float* __restrict__ uv,
                                                        const float* __restrict__ sh, int sh_start,
                                                        float* __restrict__ out, int64_t HW, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW * N) return;
     const int n = (int)(pix / HW);
@@ -131,6 +133,8 @@ template <int CMAX>
 __global__ void __launch_bounds__(128) texmap_bwd_kernel(const TexLevels lv, int C, const float* __restrict__ uv,
                                                        const float* __restrict__ sh, int sh_start,
                                                        const float* __restrict__ gout, int H, int W, int N) {
+    pdl_launch_dependents();
+    pdl_wait();
     // block = 4 warps = 16 x 8 pixels; warp = 8 x 4 pixels
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -248,8 +252,8 @@ extern "C" int rnr_texmap_fwd(const float* const* tex, const int* sizes, int L, 
     RNR_REQUIRE(!sh || (sh_start >= 0 && sh_start + 9 <= C), "texture mapper: SH channels [%d,%d) exceed C=%d", sh_start, sh_start + 9, C);
     const int64_t HW = (int64_t)H * W;
     const int blocks = rnr_cdiv(HW * N, 128);
-    if (C <= 16) texmap_fwd_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, out_nchw, HW, N);
-    else texmap_fwd_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, out_nchw, HW, N);
+    if (C <= 16) RNR_PDL_LAUNCH(texmap_fwd_kernel<16>, blocks, 128, 0, stream, lv, C, uv, sh, sh_start, out_nchw, HW, N);
+    else RNR_PDL_LAUNCH(texmap_fwd_kernel<32>, blocks, 128, 0, stream, lv, C, uv, sh, sh_start, out_nchw, HW, N);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -261,8 +265,8 @@ extern "C" int rnr_texmap_bwd(float* const* gtex, const int* sizes, int L, int C
     if (rc) return rc;
     RNR_REQUIRE(C >= 1 && C <= 32, "texture mapper: 1..32 channels supported, got %d", C);
     dim3 blocks(rnr_cdiv(W, 16), rnr_cdiv(H, 8), N);
-    if (C <= 16) texmap_bwd_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, H, W, N);
-    else texmap_bwd_kernel<32><<<blocks, 128, 0, (cudaStream_t)stream>>>(lv, C, uv, sh, sh_start, gout_nchw, H, W, N);
+    if (C <= 16) RNR_PDL_LAUNCH(texmap_bwd_kernel<16>, blocks, 128, 0, stream, lv, C, uv, sh, sh_start, gout_nchw, H, W, N);
+    else RNR_PDL_LAUNCH(texmap_bwd_kernel<32>, blocks, 128, 0, stream, lv, C, uv, sh, sh_start, gout_nchw, H, W, N);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -309,6 +313,8 @@ __device__ __forceinline__ void up_coord(int dst, int in, int out, int& i0, int&
 
 __global__ void __launch_bounds__(256) flatten_mipmap_kernel(const TexLevels lv, int C, int c0, int nc, float* __restrict__ out,
                                                            const float* __restrict__ gout, int backward) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int S0 = lv.size[0];
     const int64_t total = (int64_t)S0 * S0 * nc;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -351,7 +357,7 @@ extern "C" int rnr_flatten_mipmap(const float* const* tex, float* const* gtex, c
     const int64_t total = (int64_t)sizes[0] * sizes[0] * nc;
     int blocks = rnr_cdiv(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    flatten_mipmap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lv, C, c0, nc, out, gout, backward);
+    RNR_PDL_LAUNCH(flatten_mipmap_kernel, blocks, 256, 0, stream, lv, C, c0, nc, out, gout, backward);
     RNR_LAUNCH_CHECK();
     return 0;
 }

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 wgrad_halo_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const HItem* __restrict__ items, int n_items,
                   int tiles_y, int tiles_x, int pitch, int a_box_stride, int a_box_bytes, int stages, int stage_bytes, int vec,
                   int nbuf) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* aux = smem + (size_t)stages * stage_bytes;
@@ -86,6 +87,7 @@ wgrad_halo_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above (barriers, TMEM, tensor-map prefetch) overlapped the predecessor's tail
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
@@ -372,7 +374,7 @@ int rnr_wgrad_halo_run(const rnr_wgrad_plan* pl, cudaStream_t stream) {
     WMaps maps;
     memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
     memcpy(maps.g, pl->tmap_g, sizeof(maps.g));
-    wgrad_halo_kernel<<<pl->grid, kThreads, pl->smem_bytes, stream>>>(maps, pl->p, (const HItem*)pl->d_work_tab, pl->n_work, pl->tiles_y,
+    RNR_PDL_LAUNCH(wgrad_halo_kernel, pl->grid, kThreads, pl->smem_bytes, stream, maps, pl->p, (const HItem*)pl->d_work_tab, pl->n_work, pl->tiles_y,
                                                                      pl->tiles_x, pl->halo_pitch, pl->halo_a_stride, pl->halo_a_bytes,
                                                                      pl->stages, pl->halo_stage_bytes, pl->vec, pl->halo_nbuf);
     RNR_LAUNCH_CHECK();

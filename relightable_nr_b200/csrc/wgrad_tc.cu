@@ -36,6 +36,7 @@ struct WorkItem {          // 8 ints
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const WorkItem* __restrict__ work, int n_work,
                 int th, int tw, int tiles_y, int tiles_x, int vec, int swap) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* aux = smem + (size_t)kStages * kStageBytes;
@@ -63,6 +64,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above (barriers, TMEM, tensor-map prefetch) overlapped the predecessor's tail
 
     if (warp == 0) {
         // TMA producer: the whole warp runs the loop, one elected lane issues (operands stay warp-uniform -> uniform registers)
@@ -293,7 +295,7 @@ int rnr_wgrad_tc_run(const rnr_wgrad_plan* pl, cudaStream_t stream) {
     WMaps maps;
     memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
     memcpy(maps.g, pl->tmap_g, sizeof(maps.g));
-    wgrad_tc_kernel<<<pl->grid, kThreads, pl->smem_bytes, stream>>>(maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
+    RNR_PDL_LAUNCH(wgrad_tc_kernel, pl->grid, kThreads, pl->smem_bytes, stream, maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
                                                                    pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec, pl->swap);
     RNR_LAUNCH_CHECK();
     return 0;

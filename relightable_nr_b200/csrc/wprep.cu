@@ -28,6 +28,8 @@ struct WJob {
 };
 
 __global__ void __launch_bounds__(256) wprep_batch_kernel(const WJob* __restrict__ jobs, const int* __restrict__ blk2job) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[RB * CB * MAXT];
     const WJob& J = jobs[blk2job[blockIdx.x]];      // every thread reads the (L1-broadcast) job record directly
     const int local = blockIdx.x - J.blk0;
@@ -170,7 +172,7 @@ extern "C" void rnr_wprep_plan_destroy(rnr_wprep_plan_t* p) {
 
 extern "C" int rnr_wprep_run(const rnr_wprep_plan_t* p, void* stream) {
     RNR_REQUIRE(p, "rnr_wprep_run: null plan");
-    wprep_batch_kernel<<<p->nblocks, 256, 0, (cudaStream_t)stream>>>(p->d_jobs, p->d_blk2job);
+    RNR_PDL_LAUNCH(wprep_batch_kernel, p->nblocks, 256, 0, stream, p->d_jobs, p->d_blk2job);
     RNR_LAUNCH_CHECK();
     return 0;
 }
@@ -195,6 +197,8 @@ struct WUnJob {
 constexpr int UCO = 4;      // co rows per block (one per group of 64 threads)
 
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const WUnJob* __restrict__ jobs, const int* __restrict__ blk2job) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[UCO][MAXT][CB + 1];
     const WUnJob& J = jobs[blk2job[blockIdx.x]];
     const int local = blockIdx.x - J.blk0;
@@ -272,7 +276,7 @@ extern "C" void rnr_wgrad_unpack_plan_destroy(rnr_wunpack_plan_t* p) {
 
 extern "C" int rnr_wgrad_unpack_run(const rnr_wunpack_plan_t* p, void* stream) {
     RNR_REQUIRE(p, "rnr_wgrad_unpack_run: null plan");
-    wgrad_unpack_kernel<<<p->nblocks, 256, 0, (cudaStream_t)stream>>>(p->d_jobs, p->d_blk2job);
+    RNR_PDL_LAUNCH(wgrad_unpack_kernel, p->nblocks, 256, 0, stream, p->d_jobs, p->d_blk2job);
     RNR_LAUNCH_CHECK();
     return 0;
 }
