@@ -72,11 +72,15 @@ __device__ __forceinline__ void trace(long long* base, int role, int& idx) {
     if (base && idx < 64) base[role * 64 + idx++] = clock64();
 }
 
+// kPair = 1: CTA-pair variant (cta_group::2).  A separate instantiation, because a kernel that CONTAINS cta_group::2 instructions is
+// rejected ("cluster misconfiguration") when launched without a 2-CTA cluster.
+template <int kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, const HaloGroup* __restrict__ groups, int n_groups,
                  const HaloTap* __restrict__ taps, int n_taps, int bn, int tiles_n, int b_stages, int a_stage_bytes,
                  int b_stage_bytes, int pitch, int a_bytes, int dbg, int T, int cs, int gtaps, const HaloCfg hc, const BnFin bnf,
                  const GStats gs) {
+    constexpr int pair = kPair;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -123,13 +127,15 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     }
     if (warp == kMmaWarp && lane == 0) {
         for (int s = 0; s < kAStages; s++) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
-        for (int s = 0; s < b_stages; s++) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], (uint32_t)cs); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
+        // CTA pair (cta_group::2, see tc_ptx.cuh): only rank 0 issues MMAs and commits, so every "empty" barrier gets ONE (multicast)
+        // arrival per use, and rank 0's accumulator-free barrier collects the epilogue warps of both CTAs
+        for (int s = 0; s < b_stages; s++) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], pair ? 1u : (uint32_t)cs); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], pair ? 2 * kEpiWarps : kEpiWarps); }
         mbar_init(&raw_bar[0], 64);            // full: the 64 threads of the two raw-tile loader warps
         mbar_init(&raw_bar[1], kEpiWarps);     // empty: one arrival per epilogue warp
         fence_barrier_init();
     }
-    if (warp == kAllocWarp) tmem_alloc(tmem_slot, 512);
+    if (warp == kAllocWarp) { if (pair) tmem_alloc_cg2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync_all();          // peers' barriers must exist before anyone multicasts into them
@@ -156,7 +162,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 const HaloGroup G = s_groups[sub * n_groups + g];
                 mbar_wait(&aempty[as], aph ^ 1);
                 if (elect_one_sync()) {
-                    if (dbg & 16) mbar_arrive(&afull[as]);
+                    if (pair) {
+                        // both CTAs load their own halo tile; the bytes of both land on rank 0's barrier
+                        if (crank == 0) mbar_expect_tx(&afull[as], (uint32_t)(2 * a_bytes));
+                        tma_load_4d_cg2(&maps.a[G.view], &afull[as], smem_a + (size_t)as * a_stage_bytes, G.c0, x0 + G.ox, y0 + G.oy, n_);
+                    } else if (dbg & 16) mbar_arrive(&afull[as]);
                     else {
                         mbar_expect_tx(&afull[as], (uint32_t)a_bytes);
                         tma_load_4d(&maps.a[G.view], &afull[as], smem_a + (size_t)as * a_stage_bytes, G.c0, x0 + G.ox, y0 + G.oy, n_);
@@ -170,7 +180,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     mbar_wait(&bempty[bs], bph ^ 1);
                     if ((dbg & 128) && lane == 0) trace(tr, 0, ti);
                     if (elect_one_sync()) {
-                        if (dbg & 4) mbar_arrive(&bfull[bs]);
+                        if (pair) {
+                            // my half of the weight rows of T taps (the MMA reads the other half from the peer's shared memory)
+                            if (crank == 0) mbar_expect_tx(&bfull[bs], (uint32_t)(T * bn * 128));
+                            tma_load_3d_cg2(&maps.b, &bfull[bs], smem_b + (size_t)bs * b_stage_bytes, 0, n0 + crank * (bn >> 1), kblk);
+                        } else if (dbg & 4) mbar_arrive(&bfull[bs]);
                         else {
                             mbar_expect_tx(&bfull[bs], (uint32_t)(T * bn * 128));
                             if (cs == 1) tma_load_3d(&maps.b, &bfull[bs], smem_b + (size_t)bs * b_stage_bytes, 0, n0, kblk);
@@ -188,11 +202,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             }
             if (lane == 0) trace(tr, 0, ti);
         }
-    } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (whole warp runs the loop, one elected lane issues) =================
-        const uint32_t idesc = make_idesc(128, bn, p.ab_dtype, p.ab_dtype, 0, 0);
+    } else if (warp == kMmaWarp && !(pair && crank != 0)) {
+        // ================= MMA issuer (whole warp runs the loop, one elected lane issues; rank 0 only in a CTA pair) =================
+        const uint32_t idesc = make_idesc(pair ? 256 : 128, bn, p.ab_dtype, p.ab_dtype, 0, 0);
         const uint32_t sbo = (uint32_t)pitch * 128u;
-        const uint32_t b_tap_bytes = (uint32_t)bn * 128u;
+        const uint32_t b_tap_bytes = (uint32_t)(pair ? (bn >> 1) : bn) * 128u;
         const uint32_t a_smem0 = smem_u32(smem_a), b_smem0 = smem_u32(smem_b);
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
@@ -222,24 +236,33 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                             for (int tt = 0; tt < T; tt++) {
                                 const uint64_t da = make_halo_desc(a_base + (uint32_t)hc.a_off[sub][k + tt], sbo);
                                 const uint64_t db = make_kmajor_desc(b_base + (uint32_t)tt * b_tap_bytes, 64);
+                                if (pair) {
 #pragma unroll
-                                for (int kk = 0; kk < 4; kk++) {
-                                    umma_f16((dbg & 64) ? (d_tmem ^ ((uint32_t)(kk & 1) << 8)) : d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accum);
-                                    accum = 1;
+                                    for (int kk = 0; kk < 4; kk++) {
+                                        umma_f16_cg2(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accum);
+                                        accum = 1;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int kk = 0; kk < 4; kk++) {
+                                        umma_f16((dbg & 64) ? (d_tmem ^ ((uint32_t)(kk & 1) << 8)) : d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, accum);
+                                        accum = 1;
+                                    }
                                 }
                             }
                         }
-                        if (cs == 1) umma_commit(&bempty[bs]); else umma_commit_mc(&bempty[bs], cmask);
+                        if (pair) umma_commit_cg2(&bempty[bs], cmask);
+                        else if (cs == 1) umma_commit(&bempty[bs]); else umma_commit_mc(&bempty[bs], cmask);
                     }
                     __syncwarp();
                     accum = 1;
                     if (++bs == b_stages) { bs = 0; bph ^= 1; }
                 }
-                if (elect_one_sync()) umma_commit(&aempty[as]);
+                if (elect_one_sync()) { if (pair) umma_commit_cg2(&aempty[as], cmask); else umma_commit(&aempty[as]); }
                 __syncwarp();
                 if (++as == kAStages) { as = 0; aph ^= 1; }
             }
-            if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+            if (elect_one_sync()) { if (pair) umma_commit_cg2(&tfull_bar[acc], cmask); else umma_commit(&tfull_bar[acc]); }
             __syncwarp();
             if (lane == 0) trace(tr, 1, ti);
         }
@@ -288,7 +311,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) { if (pair) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
                 }
                 float* srow = s_stage + r * 68 + mc0;
 #pragma unroll
@@ -429,7 +452,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             if (dbg & 32) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) { if (pair) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
             }
             if (tr4) trace(tr, 2, ti);
         }
@@ -512,7 +535,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         }
     }
 
-    else if (gs.nseg > 0) {
+    else if (gs.nseg > 0 && (warp == kAllocWarp || warp == kAllocWarp + 1)) {
         // ================= raw-tile loader (warps 16-17, 64 threads): fused BatchNorm-backward statistics =================
         // For every epilogue pass, in the epilogue's order: the [128 pixel x 64 channel] tile of the producer layer's raw conv
         // output that lies under the pass (reflect-folded for a padded output grid) -> shared memory with 16-byte cp.async, one
@@ -565,7 +588,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     if (cs > 1) cluster_sync_all();          // no CTA may exit while a peer can still arrive on its barriers
     if (warp == kAllocWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (pair) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -702,14 +725,31 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     // taps per B stage: one mbarrier hand-shake (~400 cycles of latency in the single-thread producer / issuer loops) must
     // cover enough tensor work, so a stage holds T taps = T*4 MMAs; T divides the taps of a group
     const int gtaps = uniform ? (int)members[0].size() : 1;
+    // CTA pair (tcgen05.mma.cta_group::2, M = 256): two CTAs on adjacent M tiles of the same N tile share the weight operand -- each
+    // loads and holds HALF of its rows, the pair MMA reads both halves.  Per SM that halves the weight bytes pulled from L2 and
+    // the shared-memory bytes the tensor core reads for B (the single-CTA SS MMA saturates the 128 B/clk shared-memory port at
+    // N <= 128: profiles/r02_mma_issue_bench.txt).  Measured per layer (profiles/r02_perf_unet_c21_pair*.txt): N >= 128 layers gain
+    // 10-35 % (1024->256 @128^2: 831 -> 998 TFLOP/s), the N = 64 layers at 512^2 lose ~10 % (their traffic is the activation
+    // operand, which a pair cannot share), so the pair is used from N = 128 up.
+    // RNR_CONV_PAIR=0 switches it off, RNR_CONV_PAIR_MINBN overrides the threshold.
+    int pair = 0;
+    {
+        const char* pe = getenv("RNR_CONV_PAIR");
+        const char* me = getenv("RNR_CONV_PAIR_MINBN");
+        const int want = pe ? atoi(pe) : 1;
+        const int min_bn = me ? atoi(me) : 128;
+        if (want > 0 && p.tiles_m >= 2 && bn % 16 == 0 && bn >= min_bn) pair = 1;
+    }
+    pl->halo_pair = pair;
+    const int bn_cta = pair ? bn / 2 : bn;                 // weight rows held per CTA
     int T = 1;
     for (int cand = gtaps; cand >= 1; cand--) {
         if (gtaps % cand) continue;
-        const int stage = cand * bn * 128;
+        const int stage = cand * bn_cta * 128;
         if (stage <= 72 * 1024 && budget / stage >= 2) { T = cand; break; }
     }
-    { const char* te = getenv("RNR_CONV_T"); if (te && atoi(te) >= 1 && gtaps % atoi(te) == 0 && atoi(te) * bn * 128 <= 72 * 1024) T = atoi(te); }
-    const int b_stage = T * bn * 128;                      // multiple of 1024 (bn is a multiple of 16 -> 2048 B)
+    { const char* te = getenv("RNR_CONV_T"); if (te && atoi(te) >= 1 && gtaps % atoi(te) == 0 && atoi(te) * bn_cta * 128 <= 72 * 1024) T = atoi(te); }
+    const int b_stage = T * bn_cta * 128;                  // multiple of 1024 (bn_cta is a multiple of 8 -> 1024 B)
     int b_stages = budget / b_stage;
     if (b_stages > 8) b_stages = 8;
     if (b_stages < 2) return 0;
@@ -718,8 +758,8 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     // layers (tools/perf_unet.py, RNR_CONV_CLUSTER = 1 / 2 / 4): forward 0.794 / 0.821 / 1.076 ms, data gradient 0.850 / 0.884 /
     // 1.203 ms -- at this size multicast does not reduce L2 traffic enough to pay for the cluster launch, the cluster barriers
     // and the lock-step B ring, so the default is no cluster.
-    int cs = 1;
-    {
+    int cs = pair ? 2 : 1;
+    if (!pair) {
         const char* ce = getenv("RNR_CONV_CLUSTER");
         const int want = ce ? atoi(ce) : 1;
         for (int c = want; c >= 2; c >>= 1)
@@ -748,7 +788,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
         // Wmat [n_rows, ldw] viewed as (64 channels, n rows, K blocks): one box = T consecutive K blocks = T [bn x 64] tiles
         cuuint64_t gdim[3] = {64, (cuuint64_t)prob->n_rows_w * nsub, (cuuint64_t)(p.ldw / 64)};
         cuuint64_t gstr[2] = {(cuuint64_t)p.ldw * 2, 128};
-        cuuint32_t box[3] = {64u, (cuuint32_t)bn, (cuuint32_t)T};
+        cuuint32_t box[3] = {64u, (cuuint32_t)bn_cta, (cuuint32_t)T};
         cuuint32_t estr[3] = {1, 1, 1};
         RNR_REQUIRE(gstr[0] % 16 == 0 && ((uintptr_t)prob->wmat & 15) == 0, "conv_halo: Wmat is not 16-byte aligned");
         CUresult r = enc(&pl->tmap_b, prob->ab_dtype == RNR_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
@@ -756,7 +796,7 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         RNR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(Wmat 3-D) failed with CUresult %d", (int)r);
     }
-    if (cs > 1) {
+    if (cs > 1 && !pair) {
         cuuint64_t gdim[2] = {(cuuint64_t)p.ldw, (cuuint64_t)prob->n_rows_w * nsub};
         cuuint64_t gstr[1] = {(cuuint64_t)p.ldw * 2};
         cuuint32_t box[2] = {64u, (cuuint32_t)(bn / cs)};
@@ -776,7 +816,8 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     pl->n_groups = n_groups;
     pl->n_taps = (int)taps.size();
     RNR_ONCE_PER_DEVICE({
-        RNR_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RNR_CHECK(cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RNR_CHECK(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     });
     { const char* d = getenv("RNR_CONV_DBG"); pl->dbg = d ? atoi(d) : 0; }
     if (rnr_pdl_enabled()) pl->dbg |= 256;      // programmatic dependent launch (common.cuh)
@@ -806,7 +847,7 @@ extern "C" int rnr_conv_plan_set_bn(rnr_conv_plan_t* pl, const float* gamma, con
 extern "C" int rnr_conv_plan_set_gstats(rnr_conv_plan_t* pl, const rnr_gstat_seg_t* segs, int nseg, int H, int W, int pad) {
     RNR_REQUIRE(pl, "rnr_conv_plan_set_gstats: null plan");
     if (nseg == 0) { pl->gst.nseg = 0; return 0; }
-    if (!(pl->impl == 1 && pl->halo) || (pl->p.epi & RNR_EPI_STATS) || pl->halo_cs != 1) return (int)cudaErrorNotSupported;
+    if (!(pl->impl == 1 && pl->halo) || (pl->p.epi & RNR_EPI_STATS) || (pl->halo_cs != 1 && !pl->halo_pair)) return (int)cudaErrorNotSupported;
     if (nseg < 1 || nseg > 2 || pl->p.out_dtype == RNR_F32 || pl->p.cout > kMaxStatC) return (int)cudaErrorNotSupported;
     if (!(pl->p.epi & RNR_EPI_GSTATS)) return (int)cudaErrorNotSupported;      // no shared memory reserved for the raw tile
     if (pad != 0 && pad != 1) return (int)cudaErrorNotSupported;
@@ -867,10 +908,17 @@ int rnr_conv_halo_run(const rnr_conv_plan* pl, cudaStream_t stream) {
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.numAttrs = 2;
     }
-    RNR_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel, maps, pl->p, (const HaloGroup*)pl->d_groups, pl->n_groups,
+    if (pl->halo_pair) {
+        RNR_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<1>, maps, pl->p, (const HaloGroup*)pl->d_groups, pl->n_groups,
                                  (const HaloTap*)pl->d_taps, pl->n_taps, pl->bn, pl->tiles_n, pl->stages, pl->halo_a_stage,
                                  pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc, pl->bnf,
                                  pl->gst));
+    } else {
+        RNR_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<0>, maps, pl->p, (const HaloGroup*)pl->d_groups, pl->n_groups,
+                                 (const HaloTap*)pl->d_taps, pl->n_taps, pl->bn, pl->tiles_n, pl->stages, pl->halo_a_stage,
+                                 pl->halo_b_stage, pl->halo_pitch, pl->halo_a_bytes, pl->dbg, pl->halo_T, pl->halo_cs, pl->halo_gtaps, hc, pl->bnf,
+                                 pl->gst));
+    }
     rnr_count_launch();
     return 0;
 }

@@ -88,6 +88,7 @@ struct rnr_conv_plan {
     // halo-reuse kernel (conv_halo.cu)
     int halo;
     int halo_a_stage, halo_b_stage, halo_pitch, halo_a_bytes, halo_T, halo_cs;
+    int halo_pair;       // 1: CTA pairs run M = 256 cta_group::2 MMAs (halo_cs == 2, no multicast)
     CUtensorMap tmap_b2;
     int halo_gtaps;
     int halo_a_off[4][16];
