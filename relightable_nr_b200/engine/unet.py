@@ -302,9 +302,13 @@ class UNetEngine:
             h = C.c_void_p()
             _lib.check(self.L.rnr_wgrad_unpack_plan_create(arr, len(self._wunpack_jobs), C.byref(h)), 'rnr_wgrad_unpack_plan_create')
             self.wunpack_plan = _Plan(h, 'wunpack')
-        self.gstat_layers = set()       # BatchNorm layers whose backward statistics come out of their consumers' data-gradient launches
+        # BatchNorm layers whose backward statistics come out of their consumers' data-gradient launches (RNR_BN_BWD_FUSED=1).  OFF by
+        # default: measured on B200 with the CTA-pair conv kernel, alternating on one box, 216.4 / 216.8 views/s with it and 216.3 /
+        # 215.8 without -- the 0.25 ms of reduction passes it removes come back as +0.16 ms in the data-gradient epilogues
+        # (profiles/r02_perf_unet_c23_fused{0,1}.txt), and the dominant kernel's roofline fraction drops from 0.30 to 0.27.
+        self.gstat_layers = set()
         self._gstat_keys = {}
-        if self.need_backward and self.impl == 1 and os.environ.get('RNR_BN_BWD_FUSED', '1') != '0':
+        if self.need_backward and self.impl == 1 and os.environ.get('RNR_BN_BWD_FUSED', '0') == '1':
             self._plan_gstats()
         fwd_items = [w for sp in self.specs for w in self.layers[sp.name].wprep_fwd]
         all_items = fwd_items + [w for sp in self.specs for w in self.layers[sp.name].wprep_dgrad]
@@ -744,7 +748,7 @@ class UNetEngine:
         gC = G.C
         # room for the BatchNorm-backward statistics of the producer layer(s) in this launch's epilogue (_plan_gstats)
         bn_of = {q.dst: q.bn_key for q in self.specs}
-        depi = EPI_GSTATS if (self.impl == 1 and self.raw_dt != F32 and os.environ.get('RNR_BN_BWD_FUSED', '1') != '0' and
+        depi = EPI_GSTATS if (self.impl == 1 and self.raw_dt != F32 and os.environ.get('RNR_BN_BWD_FUSED', '0') == '1' and
                               any(bn_of.get(a) is not None for a in sp.src)) else 0
         g_oob = (self.impl == 1 and gC % 64 != 0 and gC % 8 == 0 and os.environ.get('RNR_CONV_OOB', '1') != '0')
         gbk = 64 if g_oob else self._bk_for([gC])
