@@ -282,6 +282,17 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
         int t3 = 1;
         const bool tr4 = (warp == 0 && lane == 0);
         const bool gstat = gs.nseg > 0;                        // BatchNorm-backward statistics of the producer layer(s) (GStats)
+        // plain 16-bit outputs (data gradients): every thread converts its 16 accumulator columns and stores them as 32 contiguous
+        // bytes of its pixel row straight from registers -- no staging tile, no epilogue barriers
+        // BatchNorm statistics in that mode: warp-shuffle column sums (colsum16) into four private accumulator sets -- one per
+        // 32-row group, aliased onto the unused staging tile -- added in a fixed order at the end (deterministic, no barrier).
+        const bool direct = (dbg & 512) && !(p.epi & (RNR_EPI_BIAS | RNR_EPI_TANH)) && !gstat && p.out_dtype != RNR_F32;
+        const bool direct_stats = direct && (p.epi & RNR_EPI_STATS);
+        float* s_accq = s_stage;                               // [4 row groups][2][kMaxStatC]
+        if (direct_stats) {
+            for (int i = e; i < 4 * 2 * kMaxStatC; i += kEpiThreads) s_accq[i] = 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        }
         uint32_t rph = 0;
         for (int t = cid; t < total_tiles; t += ncl, it++) {
             const int acc = it & 1;
@@ -291,7 +302,9 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
             const int tx_ = tile_m % p.tiles_x, ty_ = (tile_m / p.tiles_x) % p.tiles_y, n_ = tile_m / (p.tiles_x * p.tiles_y);
             const int y = ty_ * TH + ry, x = tx_ * TW + rx, n0 = tile_n * bn;
             const bool valid = (y < p.mY && x < p.mX && tile_m < p.tiles_m);
-            if (hcol == 0)      // output element offset of every tile row (-1: outside the image)
+            const int64_t my_rowoff = (int64_t)n_ * p.out_sn + (int64_t)(y * p.out_my + hc.out_py[sub]) * p.out_sy +
+                                      (int64_t)(x * p.out_mx + hc.out_px[sub]) * p.out_sx;
+            if (hcol == 0 && !direct)      // output element offset of every tile row (-1: outside the image)
                 s_rowoff[r] = valid ? ((int64_t)n_ * p.out_sn + (int64_t)(y * p.out_my + hc.out_py[sub]) * p.out_sy +
                                        (int64_t)(x * p.out_mx + hc.out_px[sub]) * p.out_sx) : (int64_t)-1;
 
@@ -312,6 +325,35 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (pair) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
+                }
+                if (direct) {
+                    if (direct_stats && mw > 0) {
+                        // column sums over this warp's 32 rows: lane pair (l, l^1) ends up with column col16_of_lane(l)
+                        float a1[16], a2[16];
+#pragma unroll
+                        for (int k = 0; k < 16; k++) { const float f = valid ? __uint_as_float(rv[k]) : 0.f; a1[k] = f; a2[k] = f * f; }
+                        const float s1 = colsum16(a1, lane), s2 = colsum16(a2, lane);
+                        const int co = n0 + c0 + mc0 + col16_of_lane(lane);
+                        if (!(lane & 1) && co < p.cout && co < kMaxStatC) {
+                            s_accq[(q * 2 + 0) * kMaxStatC + co] += s1;        // (q, hcol) is unique per warp: no other writer
+                            s_accq[(q * 2 + 1) * kMaxStatC + co] += s2;
+                        }
+                    }
+                    if (mw > 0 && valid) {
+                        const int cbase = n0 + c0 + mc0;
+                        unsigned short* op = (unsigned short*)p.out + my_rowoff + cbase;
+                        if (cbase + 16 <= p.cout) {
+                            __align__(16) unsigned short h[16];
+#pragma unroll
+                            for (int k = 0; k < 16; k++) h[k] = f2b16(__uint_as_float(rv[k]), p.out_dtype);
+                            *(uint4*)op = *(const uint4*)h;
+                            *(uint4*)(op + 8) = *(const uint4*)(h + 8);
+                        } else {
+                            for (int k = 0; k < 16; k++)
+                                if (cbase + k < p.cout) op[k] = f2b16(__uint_as_float(rv[k]), p.out_dtype);
+                        }
+                    }
+                    continue;
                 }
                 float* srow = s_stage + r * 68 + mc0;
 #pragma unroll
@@ -469,6 +511,16 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 const float a1 = s_acc[co], a2 = s_acc[kMaxStatC + co];
                 if (a1 != 0.f) atomicAdd(tot + (co - c_lo), (double)a1);
                 if (a2 != 0.f) atomicAdd(tot + Cs + (co - c_lo), (double)a2);
+            }
+        }
+        if (direct_stats) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            for (int co = e; co < p.cout && co < kMaxStatC; co += kEpiThreads) {
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int g = 0; g < 4; g++) { t1 += s_accq[(g * 2 + 0) * kMaxStatC + co]; t2 += s_accq[(g * 2 + 1) * kMaxStatC + co]; }
+                s_acc[co] = t1;
+                s_acc[kMaxStatC + co] = t2;
             }
         }
         if (p.epi & RNR_EPI_STATS) {
@@ -821,6 +873,10 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     });
     { const char* d = getenv("RNR_CONV_DBG"); pl->dbg = d ? atoi(d) : 0; }
     if (rnr_pdl_enabled()) pl->dbg |= 256;      // programmatic dependent launch (common.cuh)
+    // epilogue straight from registers (no staging tile): measured faster for every N tile except N = 64 -- there the whole pixel row
+    // is one 128-byte line written by four warps, and the staged, row-coalesced stores win by ~3 us per 512^2 launch
+    // (profiles/r02_perf_unet_c28_direct{0,1,2}.txt).  RNR_CONV_DIRECT=0 off, =2 for every layer.
+    { const char* d = getenv("RNR_CONV_DIRECT"); const int want = d ? atoi(d) : 1; if (want >= 2 || (want == 1 && bn != 64)) pl->dbg |= 512; }
     pl->halo = 1;
     return 0;
 }
