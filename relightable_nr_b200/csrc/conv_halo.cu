@@ -98,7 +98,8 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
     HaloTap* s_taps = (HaloTap*)(s_groups + kMaxGroups);             // [kMaxTaps]
     float* s_acc = (float*)(s_taps + kMaxTaps);                      // [2][kMaxStatC] per-CTA BatchNorm sums
     float* s_stage = s_acc + 2 * kMaxStatC;                                   // [128][68] epilogue staging slab (16-byte aligned)
-    int64_t* s_rowoff = (int64_t*)(s_stage + 128 * 68);              // [128] output offset of each tile row
+    // (dbg & 1024: register-direct epilogue without statistics -- the staging slab is not allocated, the B ring got its bytes)
+    int64_t* s_rowoff = (int64_t*)(s_stage + ((dbg & 1024) ? 0 : 128 * 68));   // [128] output offset of each tile row
     float* s_colp = (float*)(s_rowoff + 128);                        // [2][8][64] per-pass column partial sums
     unsigned short* s_raw = (unsigned short*)(s_colp + 1024);        // [128][64] producer's raw conv output under the current pass (RNR_EPI_GSTATS)
 
@@ -771,8 +772,17 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     pl->bn = bn;
     pl->tiles_n = tiles_n;
     const int a_stage = ((rows * pitch * 128) + 1023) / 1024 * 1024;
-    const int aux = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 2 * kMaxStatC * 4 + 128 * 68 * 4 + 128 * 8 + 1024 * 4 +
+    // epilogue straight from registers (no staging tile): measured faster for every N tile except N = 64 -- there the whole pixel row
+    // is one 128-byte line written by four warps, and the staged, row-coalesced stores win by ~3 us per 512^2 launch
+    // (profiles/r02_perf_unet_c28_direct{0,1,2}.txt).  RNR_CONV_DIRECT=0 off, =2 for every layer.  Without BatchNorm statistics
+    // (data gradients) the staging slab is not needed at all and its 34 KB go to the weight ring.
+    int direct = 0;
+    { const char* d = getenv("RNR_CONV_DIRECT"); const int want = d ? atoi(d) : 1; if (want >= 2 || (want == 1 && bn != 64)) direct = 1; }
+    if ((prob->epi & (RNR_EPI_BIAS | RNR_EPI_TANH)) || prob->out_dtype == RNR_F32) direct = 0;
+    const int nostage = direct && !(prob->epi & (RNR_EPI_STATS | RNR_EPI_GSTATS)) && !(getenv("RNR_CONV_NOSTAGE") && getenv("RNR_CONV_NOSTAGE")[0] == '0');
+    const int aux_full = 64 * 8 + 64 + kMaxGroups * (int)sizeof(HaloGroup) + kMaxTaps * (int)sizeof(HaloTap) + 2 * kMaxStatC * 4 + 128 * 68 * 4 + 128 * 8 + 1024 * 4 +
                     ((prob->epi & RNR_EPI_GSTATS) ? 128 * 64 * 2 : 0);     // + the raw tile of the fused BatchNorm-backward statistics
+    const int aux = aux_full - (nostage ? 128 * 68 * 4 : 0);
     const int budget = 212 * 1024 - aux - kAStages * a_stage;
     // taps per B stage: one mbarrier hand-shake (~400 cycles of latency in the single-thread producer / issuer loops) must
     // cover enough tensor work, so a stage holds T taps = T*4 MMAs; T divides the taps of a group
@@ -873,10 +883,8 @@ int rnr_conv_halo_prepare(rnr_conv_plan* pl, const rnr_conv_problem_t* probs, in
     });
     { const char* d = getenv("RNR_CONV_DBG"); pl->dbg = d ? atoi(d) : 0; }
     if (rnr_pdl_enabled()) pl->dbg |= 256;      // programmatic dependent launch (common.cuh)
-    // epilogue straight from registers (no staging tile): measured faster for every N tile except N = 64 -- there the whole pixel row
-    // is one 128-byte line written by four warps, and the staged, row-coalesced stores win by ~3 us per 512^2 launch
-    // (profiles/r02_perf_unet_c28_direct{0,1,2}.txt).  RNR_CONV_DIRECT=0 off, =2 for every layer.
-    { const char* d = getenv("RNR_CONV_DIRECT"); const int want = d ? atoi(d) : 1; if (want >= 2 || (want == 1 && bn != 64)) pl->dbg |= 512; }
+    if (direct) pl->dbg |= 512;
+    if (nostage) pl->dbg |= 1024;
     pl->halo = 1;
     return 0;
 }
