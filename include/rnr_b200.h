@@ -272,6 +272,16 @@ int rnr_bn_finalize(const float* partials, int T, int ld, int C, double count,
 /* act = drop * act(raw*scale + shift), written fp16 with reflect halo [N,H+2,W+2,C];
  * act_bf16 (optional, same layout) receives a bf16 copy: the B operand of the weight-gradient MMA
  * (kind::f16 needs both operands in the same 16-bit format and gradients are bf16)               */
+/* nn.BatchNorm2d batch statistics WITHOUT a finalize launch: rnr_conv_plan_set_stat_totals makes the conv plan add its per-CTA
+ * sums to totals [2, C] (fp64, zero before the first launch); rnr_bn_act_fwd_tot derives mean / biased variance / invstd / scale /
+ * shift from them in every block (arithmetic of rnr_bn_finalize), applies scale / shift + (Leaky)ReLU + Dropout2d like
+ * rnr_bn_act_fwd, publishes mean / invstd / scale / shift and the running-statistics update from its first block, and re-zeroes
+ * totals / re-arms ticket (int32, zero before the first call) from the last block that read them. */
+int rnr_conv_plan_set_stat_totals(rnr_conv_plan_t* plan, double* totals);
+int rnr_bn_act_fwd_tot(const void* raw, int raw_dtype, double* totals, int* ticket, double count, const float* gamma,
+                       const float* beta, float eps, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
+                       float* running_var, float momentum, const float* drop, float slope, void* act, void* act_bf16, int N, int H,
+                       int W, int C, void* stream);
 int rnr_bn_act_fwd(const void* raw, int raw_dtype /* RNR_F32 or 16-bit */, const float* scale, const float* shift,
                    const float* drop /* [N,C] or NULL */, float slope,
                    void* act, void* act_bf16, int N, int H, int W, int C, void* stream);

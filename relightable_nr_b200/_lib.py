@@ -126,6 +126,8 @@ def lib():
         "rnr_wgrad_unpack_run": [vp, vp],
         "rnr_bn_finalize": [vp, i32, i32, i32, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp],
         "rnr_bn_act_fwd": [vp, i32, vp, vp, vp, f32, vp, vp, i32, i32, i32, i32, vp],
+        "rnr_conv_plan_set_stat_totals": [vp, vp],
+        "rnr_bn_act_fwd_tot": [vp, i32, vp, vp, f64, vp, vp, f32, vp, vp, vp, vp, vp, vp, f32, vp, f32, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce": [C.POINTER(GSrc), i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, C.POINTER(i32), i32, i32, i32, i32, vp],
         "rnr_bn_bwd_reduce_fin": [C.POINTER(GSrc), i32, vp, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, f64, vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "rnr_bn_bwd_apply_src": [C.POINTER(GSrc), i32, vp, i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, f64, vp, vp, i32, i32, i32, i32, vp],

@@ -120,6 +120,103 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const void* __restrict_
         }
 }
 
+// The same pass fed by fp64 TOTALS of the batch sums (rnr_conv_plan_set_stat_totals) instead of finalized scale / shift arrays:
+// every block turns the totals into the [scale | shift] table of the layer in shared memory (one channel per thread: mean, biased
+// variance, invstd in double -- the arithmetic of bn_finalize_kernel), block (0,0) also publishes mean / invstd / scale / shift for
+// the backward pass and updates the running statistics, and the last block to have read the totals (ticket) re-zeroes them.
+// A block covers RB image rows, so that a 512^2 layer runs ~2000 blocks, not 8192.  No finalize launch between the convolution
+// and this kernel.
+__global__ void __launch_bounds__(256) bn_act_fwd_tot_kernel(const void* __restrict__ raw, int raw_dtype, double* __restrict__ totals,
+                                  int* __restrict__ ticket, double count, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                  float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ running_mean,
+                                  float* __restrict__ running_var, float momentum, const float* __restrict__ drop, float slope,
+                                  __half* __restrict__ act, __nv_bfloat16* __restrict__ act_b, int N, int H, int W, int C, int RB) {
+    extern __shared__ __align__(16) float s_tab[];      // [2][C]: scale, shift
+    __shared__ int s_last;
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool first = (blockIdx.x == 0 && blockIdx.y == 0);
+    for (int ch = threadIdx.x; ch < C; ch += 256) {
+        const double sv = __ldcg(totals + ch), qv = __ldcg(totals + C + ch);
+        const double m = sv / count;
+        double var = qv / count - m * m;
+        if (var < 0.0) var = 0.0;
+        const float istd = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+        const float sc = g * istd, sh = b - (float)m * g * istd;
+        s_tab[ch] = sc;
+        s_tab[C + ch] = sh;
+        if (first) {
+            mean[ch] = (float)m;
+            invstd[ch] = istd;
+            scale[ch] = sc;
+            shift[ch] = sh;
+            if (running_mean) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+                running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+            }
+        }
+    }
+    __threadfence();                              // the loads of `totals` above are performed before the ticket moves
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
+    __syncthreads();
+    if (s_last) {
+        for (int i = threadIdx.x; i < 2 * C; i += 256) totals[i] = 0.0;
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+    const unsigned vpp = (unsigned)C >> 3;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)W * vpp) return;
+    const int w = (int)(idx / vpp);
+    const int c = (int)(idx - (unsigned)w * vpp) * 8;
+    const float4 s0 = *(const float4*)(s_tab + c), s1 = *(const float4*)(s_tab + c + 4);
+    const float4 t0 = *(const float4*)(s_tab + C + c), t1 = *(const float4*)(s_tab + C + c + 4);
+    const int Hp = H + 2, Wp = W + 2;
+    int cols[3], nc = 0;
+    cols[nc++] = w + 1;
+    if (w == 1) cols[nc++] = 0;
+    if (w == W - 2) cols[nc++] = W + 1;
+    const int row_end = min((int)(blockIdx.y + 1) * RB, N * H);
+    for (int row = blockIdx.y * RB; row < row_end; row++) {
+        const int n = row / H, h = row - n * H;
+        const int64_t pix = (int64_t)row * W + w;
+        float rr[8];
+        load_raw8(raw, pix * C + c, raw_dtype, rr);
+        float v[8] = {rr[0] * s0.x + t0.x, rr[1] * s0.y + t0.y, rr[2] * s0.z + t0.z, rr[3] * s0.w + t0.w,
+                      rr[4] * s1.x + t1.x, rr[5] * s1.y + t1.y, rr[6] * s1.z + t1.z, rr[7] * s1.w + t1.w};
+        float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (drop) {
+            const float4 d0 = *(const float4*)(drop + n * C + c), d1 = *(const float4*)(drop + n * C + c + 4);
+            dm[0] = d0.x; dm[1] = d0.y; dm[2] = d0.z; dm[3] = d0.w; dm[4] = d1.x; dm[5] = d1.y; dm[6] = d1.z; dm[7] = d1.w;
+        }
+        __align__(16) __half o[8];
+        __align__(16) __nv_bfloat16 ob[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            float z = v[e];
+            z = z > 0.f ? z : z * slope;
+            z *= dm[e];
+            o[e] = __float2half_rn(z);
+            ob[e] = __float2bfloat16_rn(z);
+        }
+        const uint4 ov = *(const uint4*)o;
+        const uint4 ovb = *(const uint4*)ob;
+        int rows[3], nr = 0;
+        rows[nr++] = h + 1;
+        if (h == 1) rows[nr++] = 0;
+        if (h == H - 2) rows[nr++] = H + 1;
+        for (int a = 0; a < nr; a++)
+            for (int b = 0; b < nc; b++) {
+                const int64_t o_ = (((int64_t)n * Hp + rows[a]) * Wp + cols[b]) * C + c;
+                *(uint4*)(act + o_) = ov;
+                if (act_b) *(uint4*)(act_b + o_) = ovb;
+            }
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // backward pass 1
 // -------------------------------------------------------------------------------------------
@@ -657,6 +754,26 @@ extern "C" int rnr_bn_act_fwd(const void* raw, int raw_dtype, const float* scale
     RNR_REQUIRE((int64_t)N * H <= 65535, "rnr_bn_act_fwd: N*H=%lld exceeds the grid limit", (long long)N * H);
     dim3 grid(rnr_cdiv((int64_t)W * (C / 8), 256), N * H);
     RNR_PDL_LAUNCH(bn_act_fwd_kernel, grid, 256, 0, stream, raw, raw_dtype, scale, shift, drop, slope, (__half*)act, (__nv_bfloat16*)act_bf16, N, H, W, C);
+    RNR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rnr_bn_act_fwd_tot(const void* raw, int raw_dtype, double* totals, int* ticket, double count, const float* gamma,
+                                  const float* beta, float eps, float* mean, float* invstd, float* scale, float* shift,
+                                  float* running_mean, float* running_var, float momentum, const float* drop, float slope, void* act,
+                                  void* act_bf16, int N, int H, int W, int C, void* stream) {
+    RNR_REQUIRE(C % 8 == 0 && C <= 4096, "rnr_bn_act_fwd_tot: C=%d must be a multiple of 8 (<= 4096)", C);
+    RNR_REQUIRE(H >= 2 && W >= 2, "rnr_bn_act_fwd_tot: reflect halo needs H,W >= 2");
+    RNR_REQUIRE(totals && ticket && mean && invstd && scale && shift, "rnr_bn_act_fwd_tot: null pointer");
+    const int bx = rnr_cdiv((int64_t)W * (C / 8), 256);
+    // rows per block: ~2000 blocks for the big layers (one ticket atomic + one coefficient prologue per block), >= 1 row
+    int RB = 1;
+    while (RB < 8 && (int64_t)bx * rnr_cdiv((int64_t)N * H, RB) > 2048) RB *= 2;
+    dim3 grid(bx, rnr_cdiv((int64_t)N * H, RB));
+    RNR_REQUIRE(grid.y <= 65535, "rnr_bn_act_fwd_tot: N*H=%lld exceeds the grid limit", (long long)N * H);
+    RNR_PDL_LAUNCH(bn_act_fwd_tot_kernel, grid, 256, (size_t)2 * C * sizeof(float), stream, raw, raw_dtype, totals, ticket, count, gamma, beta,
+                   eps, mean, invstd, scale, shift, running_mean, running_var, momentum, drop, slope, (__half*)act,
+                   (__nv_bfloat16*)act_bf16, N, H, W, C, RB);
     RNR_LAUNCH_CHECK();
     return 0;
 }

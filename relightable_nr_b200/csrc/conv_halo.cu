@@ -524,7 +524,16 @@ conv_halo_kernel(const __grid_constant__ HaloMaps maps, const ConvParams p, cons
                 s_acc[kMaxStatC + co] = t2;
             }
         }
-        if (p.epi & RNR_EPI_STATS) {
+        if ((p.epi & RNR_EPI_STATS) && p.stats_tot) {
+            // this CTA's sums straight into the layer's fp64 totals: the consumer (rnr_bn_act_fwd_tot) derives mean / invstd itself
+            // and no finalize launch sits between the convolution and its activation pass.  (fp64 accumulation of <= 148 fp32
+            // partials is exact for any realistic dynamic range, so the result does not depend on the arrival order.)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            for (int co = e; co < p.cout && co < kMaxStatC; co += kEpiThreads) {
+                atomicAdd(p.stats_tot + co, (double)s_acc[co]);
+                atomicAdd(p.stats_tot + p.cout + co, (double)s_acc[kMaxStatC + co]);
+            }
+        } else if (p.epi & RNR_EPI_STATS) {
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
             for (int co = e; co < p.cout; co += kEpiThreads) {
                 p.stats[((int64_t)blockIdx.x * 2 + 0) * p.ldstats + co] = s_acc[co];
@@ -935,6 +944,16 @@ extern "C" int rnr_conv_plan_set_gstats(rnr_conv_plan_t* pl, const rnr_gstat_seg
     if (!g.seg[0].enabled && g.seg[1].enabled) g.seg[0].raw_dtype = g.seg[1].raw_dtype;
     if (!g.seg[0].enabled && !(nseg > 1 && g.seg[1].enabled)) g.nseg = 0;
     pl->gst = g;
+    return 0;
+}
+
+// BatchNorm batch sums of this plan's output as fp64 totals [2, cout] (zero before the first launch; rnr_bn_act_fwd_tot consumes and
+// re-zeroes them) instead of per-CTA rows + rnr_bn_finalize.  totals = NULL restores the rows.  cudaErrorNotSupported (no error
+// text) when the plan is not a halo-kernel launch with RNR_EPI_STATS.
+extern "C" int rnr_conv_plan_set_stat_totals(rnr_conv_plan_t* pl, double* totals) {
+    RNR_REQUIRE(pl, "rnr_conv_plan_set_stat_totals: null plan");
+    if (!(pl->impl == 1 && pl->halo && (pl->p.epi & RNR_EPI_STATS)) || pl->p.cout > kMaxStatC || pl->bnf.enabled) return (int)cudaErrorNotSupported;
+    pl->p.stats_tot = totals;
     return 0;
 }
 

@@ -19,6 +19,7 @@ struct ConvParams {
     const float* bias;
     float* stats;
     int ldstats;
+    double* stats_tot;   // != nullptr: the per-CTA BatchNorm sums go into [2, cout] fp64 totals (atomics) instead of `stats` rows
 };
 
 // BatchNorm statistics finalize fused into the halo kernel: the LAST CTA to publish its partial sums (ticket counter) reduces

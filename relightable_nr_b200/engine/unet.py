@@ -171,6 +171,8 @@ class _LayerState:
     wmat_fwd: Optional[dict] = None            # layout of the forward GEMM matrix family (for the optimiser pass that re-derives it)
     wmat_dgrad: Optional[dict] = None          # same for the data-gradient family
     bn_ticket: Optional[torch.Tensor] = None   # last-CTA ticket of the fused forward BatchNorm finalize
+    fwd_totals: Optional[torch.Tensor] = None  # [2, C] fp64 batch sums written by the conv launch (no finalize launch)
+    fwd_ticket: Optional[torch.Tensor] = None
     bn_fused: bool = False                     # statistics finalize runs inside the conv kernel (rnr_conv_plan_set_bn)
 
 
@@ -652,6 +654,16 @@ class UNetEngine:
         if (epi & EPI_STATS) and len(st.fwd_plans) == 1 and self.impl == 1 and os.environ.get('RNR_BN_FUSED_FINALIZE', '0') == '1':
             st.bn_ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
             st.bn_fused = self._set_bn(st, True, 0.1, 1e-5, probe=True)
+        # BatchNorm batch sums as fp64 totals consumed by the activation pass itself (rnr_bn_act_fwd_tot): no finalize launch.  OFF by
+        # default: measured on B200, alternating on one box, 218.3 / 218.4 views/s with it vs 222.8 / 221.3 without -- the per-block
+        # coefficient prologue (an L2 round trip for the totals, fp64 math, one ticket atomic) of ~2000 blocks per layer costs more
+        # than the 17 tiny finalize launches it removes (RNR_BN_FWD_TOTALS=1 enables; parity-tested)
+        if ((epi & EPI_STATS) and len(st.fwd_plans) == 1 and self.impl == 1 and not st.bn_fused and
+                os.environ.get('RNR_BN_FWD_TOTALS', '0') == '1'):
+            tot = torch.zeros(2 * cout, dtype=torch.float64, device=self.device)
+            if self.L.rnr_conv_plan_set_stat_totals(st.fwd_plans[0].h, tot.data_ptr()) == 0:
+                st.fwd_totals = tot
+                st.fwd_ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
         if not self.need_backward:
             return
 
@@ -974,7 +986,23 @@ class UNetEngine:
                     st.mean.copy_(rm)
                     torch.mul(self.params[sp.bn_key + '.weight'], st.invstd, out=st.scale)
                     torch.addcmul(self.params[sp.bn_key + '.bias'], st.mean, st.scale, value=-1.0, out=st.shift)
+                    if st.fwd_totals is not None:
+                        st.fwd_totals.zero_()    # (the conv launch added its batch sums; nobody consumes them in eval mode)
                 shift = st.shift
+            elif sp.bn_key is not None and st.fwd_totals is not None:
+                # the conv launch left its batch sums in fp64 totals: the activation pass derives mean / invstd itself
+                rm, rv = self.buffers[sp.bn_key + '.running_mean'], self.buffers[sp.bn_key + '.running_var']
+                st.drop = drop_masks.get(sp.name) if (drop_masks and sp.drop) else None
+                _lib.check(L.rnr_bn_act_fwd_tot(st.raw.data_ptr(), self.raw_dt, st.fwd_totals.data_ptr(), st.fwd_ticket.data_ptr(),
+                                                float(N * Ho * Wo), self.params[sp.bn_key + '.weight'].data_ptr(),
+                                                self.params[sp.bn_key + '.bias'].data_ptr(), eps, st.mean.data_ptr(),
+                                                st.invstd.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(),
+                                                rm.data_ptr() if rm is not None else None, rv.data_ptr() if rv is not None else None,
+                                                momentum, st.drop.data_ptr() if st.drop is not None else None, sp.slope,
+                                                self.acts[sp.dst].ptr, self.acts_w[sp.dst].ptr if self.dual else None,
+                                                N, Ho, Wo, Cc, s), 'rnr_bn_act_fwd_tot')
+                self.gpu_launches += 1
+                continue
             elif sp.bn_key is not None and st.bn_fused:
                 shift = st.shift                 # mean / invstd / scale / shift were written by the conv kernel's last CTA
             elif sp.bn_key is not None:
