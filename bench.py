@@ -486,16 +486,22 @@ def run_rnr_train(args, D):
     roof = None
     # (every rank runs the eager steps: at N > 1 they contain the gradient all-reduce, a collective)
     eng = [e for k, e in pipe.render_net.net._runner._engines.items() if e.need_backward][0]
+    ROOF_ITERS = 10
+    for i in range(3):                      # untimed: the eager path (Python launches) warm again after the graph replays
+        eager_step(views[i % nviews])
     eng.timing = []
-    for i in range(3):
+    for i in range(ROOF_ITERS):
         eager_step(views[i % nviews])
     torch.cuda.synchronize()
     rec, eng.timing = eng.timing, None
     if rank == 0:
         t = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
         nl = {'fwd': 0, 'dgrad': 0, 'wgrad': 0}
+        per_layer = {}
         for kind, name, a, b in rec:
-            t[kind] += a.elapsed_time(b) / 3
+            dt = a.elapsed_time(b) / ROOF_ITERS
+            t[kind] += dt
+            per_layer.setdefault(name, {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0})[kind] += dt * 1e3
         fl = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
         for sp in eng.specs:
             f = eng.layer_flops(sp, eng.N)
@@ -526,7 +532,9 @@ def run_rnr_train(args, D):
                 'kernel_ms_per_step': conv_ms, 'share_of_step': conv_ms / (ms / args.steps),
                 'wgrad_tc_kernel': {'achieved': fl['wgrad'] / (t['wgrad'] * 1e-3) / 1e12, 'kernel_ms_per_step': t['wgrad'],
                                     'launches_per_step': nl['wgrad']},
-                'whole_step_tflops': (fl['fwd'] + fl['dgrad'] + fl['wgrad']) * args.steps / (ms * 1e-3) / 1e12}
+                'whole_step_tflops': (fl['fwd'] + fl['dgrad'] + fl['wgrad']) * args.steps / (ms * 1e-3) / 1e12,
+                # in-step duration of every layer's launches (us: forward, data gradient, weight gradient), same CUDA events
+                'per_layer_us': {k: [round(v['fwd'], 1), round(v['dgrad'], 1), round(v['wgrad'], 1)] for k, v in per_layer.items()}}
 
     # ---- extras: the paths the unchanged scripts take (module-by-module, graph and eager), and the step with the GCN of :490 ----
     extras = {}

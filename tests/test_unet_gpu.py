@@ -133,6 +133,38 @@ def test_batchnorm_backward_sums_from_the_data_gradient_epilogue(cfg, monkeypatc
     assert e_in <= 2e-2
 
 
+def test_conv_kernel_variants_agree(monkeypatch):
+    """The halo conv kernel's variants -- CTA pair (tcgen05.mma.cta_group::2, M = 256) vs single CTA, register-direct vs staged
+    epilogue -- run the same MMAs over the same K order: the first layer's raw output (no BatchNorm statistics upstream) must be
+    BIT-IDENTICAL across them, the network output and every parameter gradient agree to rounding of the statistics' summation
+    order (PSNR >= 80 dB, rel-L2 <= 2e-2 on noise-like gradients)."""
+    cfg = dict(in_ch=108, out_ch=78, nf0=64, H=128, N=1, num_down=5, grad_range=(84, 108))
+    sd, x = _setup(cfg['in_ch'], cfg['out_ch'], cfg['nf0'], cfg['H'], cfg['N'], cfg['num_down'])
+    g = torch.Generator().manual_seed(7)
+    R = (torch.randn(cfg['N'], cfg['out_ch'], cfg['H'], cfg['H'], generator=g) / (cfg['H'] * cfg['H'])).cuda()
+    res = {}
+    for name, env in (('default', {}), ('single_cta', {'RNR_CONV_PAIR': '0'}), ('staged', {'RNR_CONV_DIRECT': '0'}),
+                      ('pair_everywhere_direct_everywhere', {'RNR_CONV_PAIR_MINBN': '16', 'RNR_CONV_DIRECT': '2'})):
+        for k in ('RNR_CONV_PAIR', 'RNR_CONV_DIRECT', 'RNR_CONV_PAIR_MINBN'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng, _ = _engine(sd, x, cfg['out_ch'], cfg['nf0'], cfg['num_down'], 'tc', cfg['grad_range'], wgrad_impl='tc')
+        eng.set_input_nchw(x.cuda())
+        eng.forward(training=True, drop_masks=None)
+        out = eng.output_nchw().clone()
+        gi = eng.backward_from_nchw(R)
+        torch.cuda.synchronize()
+        res[name] = (eng.layers['in'].raw.clone(), out, {k: eng.grad_view(k).clone() for k in eng.grad_slices}, gi.clone())
+    ref = res['single_cta']
+    for name, (raw0, out, grads, gi) in res.items():
+        assert torch.equal(raw0.view(torch.int16), ref[0].view(torch.int16)), name
+        p = psnr(out.cpu() * 0.5 + 0.5, ref[1].cpu() * 0.5 + 0.5)
+        worst = max(rel_l2(grads[k].cpu(), ref[2][k].cpu()) for k in grads if ref[2][k].abs().max().item() > 0)
+        print('%-36s output PSNR vs single-CTA staged-free baseline %.1f dB, worst gradient rel-L2 %.2e' % (name, p, worst))
+        assert p >= 80.0 and worst <= 2e-2, name
+
+
 def test_eval_mode_batchnorm_uses_running_statistics():
     """module.eval() WITHOUT the scripts' set_bn_train (test_rnr.py:220-233 re-enables train mode): nn.BatchNorm2d then
     normalises with running_mean / running_var.  Engine vs oracle (F.batch_norm(training=False)) on non-trivial running

@@ -7,8 +7,8 @@ import sys
 
 
 def short(name):
-    name = name.replace('(anonymous namespace)::', '')
-    m = re.match(r'(?:void\s+)?([A-Za-z_0-9:]+)', name)
+    name = name.replace('(anonymous namespace)::', '').replace('<unnamed>::', '')
+    m = re.match(r'(?:void\s+)?([A-Za-z_0-9:]+(?:<[0-9, ]+>)?)', name)      # keep small integer template arguments (kernel variants)
     base = m.group(1) if m else name
     if base.startswith('at::') or base.startswith('at_cuda'):
         # keep the functor for torch elementwise kernels
