@@ -72,6 +72,19 @@ def _read_outputs(d):
             cv2.imread(os.path.join(d, 'mask', '0.png'), cv2.IMREAD_UNCHANGED), cv2.imread(os.path.join(d, 'count', '0.png'), cv2.IMREAD_UNCHANGED))
 
 
+def test_view_selection_and_obj_reader(tmp_path):
+    """stitch_lp.py:104-120 sampling patterns; OBJ reader: v/vt/vn corners, negative indices, polygons fanned into triangles."""
+    from relightable_nr_b200.stitch import read_obj_geometry, selected_views
+    assert selected_views(7, 'all') == list(range(7))
+    assert selected_views(7, 'skip_3') == [0, 3, 6]
+    assert selected_views(7, 'skipinv_3') == [1, 2, 4, 5]
+    assert selected_views(7, 'first_2') == [0, 1]
+    fp = tmp_path / 'quad.obj'
+    fp.write_text('v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\nf 1/1/1 2/1/1 3/1/1 4/1/1\nf -4 -3 -2\n')
+    v, f = read_obj_geometry(str(fp))
+    assert v.shape == (4, 3) and f.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]]
+
+
 @pytest.mark.parametrize('pattern', ['all', 'skipinv_2'])
 def test_restatement_matches_the_unchanged_script(scene, pattern):
     out = _run_reference(scene, pattern)
