@@ -21,8 +21,12 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kBoxBytes = 128 * 64 * 2;     // one [128 pixels x 64 channels] 16-bit box
-constexpr int kStageBytes = 4 * kBoxBytes;  // 2 G boxes (co 0..127) + 2 A boxes (ci 0..127)
-constexpr int kStages = 3;
+// A stage = 2 G boxes (co 0..127) + up to 4 A boxes (ci chunk of up to 256): `stage_bytes` / `n_stages` are per plan -- 3 x 64 KB
+// when no work item has more than 128 input channels, 2 x 96 KB for N = 256 items.  Why N = 256 where the layer has the channels:
+// every loaded tile is used by ONE group of 8 MMAs, so the shared-memory port carries the TMA writes AND the operand reads of the
+// same bytes; per 128-pixel patch that is 64 KB written + 64 KB read for 512 tensor cycles at N = 128 (256 B/clk against a
+// 128 B/clk port), 96 KB + 96 KB for 1024 tensor cycles at N = 256 (192 B/clk).
+constexpr int kMaxStages = 3;
 
 struct WMaps {
     CUtensorMap a[RNR_MAX_VIEWS];
@@ -35,14 +39,14 @@ struct WorkItem {          // 8 ints
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const WorkItem* __restrict__ work, int n_work,
-                int th, int tw, int tiles_y, int tiles_x, int vec, int swap) {
+                int th, int tw, int tiles_y, int tiles_x, int vec, int swap, int stage_bytes, int n_stages, int acc_cols) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* aux = smem + (size_t)kStages * kStageBytes;
+    uint8_t* aux = smem + (size_t)n_stages * stage_bytes;
     uint64_t* full_bar = (uint64_t*)aux;
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
@@ -55,11 +59,11 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
             if (p.gviews[v].ptr) tma_prefetch_desc(&maps.g[v]);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < n_stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)(2 * acc_cols));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -78,7 +82,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                 const int x0 = tx_ * tw, y0 = ty_ * th;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one_sync()) {
-                    uint8_t* st = smem + (size_t)stage * kStageBytes;
+                    uint8_t* st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + wi.n_ci_box) * kBoxBytes));
                     if (!swap) {
                         tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st, wi.co0, x0, y0, n_);
@@ -96,7 +100,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                     }
                 }
                 __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -113,12 +117,12 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                                         : make_idesc(128, wi.n_mma, p.g_dtype, p.a_dtype, 1, 1);
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
             uint32_t accum = 0;
             for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sbase = smem0 + (uint32_t)stage * (uint32_t)kStageBytes;
+                const uint32_t sbase = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
                 if (elect_one_sync()) {
                     const uint64_t dg = make_mnmajor_desc(sbase, kBoxBytes);
                     const uint64_t da = make_mnmajor_desc(sbase + 2 * kBoxBytes, kBoxBytes);
@@ -131,7 +135,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                 }
                 __syncwarp();
                 accum = 1;
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
             if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
             __syncwarp();
@@ -149,7 +153,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
             float* dst = p.dw + (int64_t)co * p.s_co + (int64_t)(tap.ci0 + wi.ci_off) * p.s_ci + tap.off;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 128u;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * acc_cols);
             if (swap) {
                 // lane = input channel (ci_off + row), column = output channel: lanes are adjacent in the ci-contiguous scratch,
                 // so every column is one coalesced 128-byte reduction per warp
@@ -208,7 +212,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, (uint32_t)(2 * acc_cols));
     }
 }
 
@@ -246,6 +250,10 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
     { const char* e = getenv("RNR_WGRAD_SWAP"); if (e) swap = (atoi(e) != 0 && prob->cout <= 128) ? 1 : 0; }
     pl->swap = swap;
     struct OT { int tap, co0, ci_off, nbox, valid, n_mma; };
+    // OFF by default: measured on B200 (profiles/r02_perf_unet_c32_n256_{0,1}.txt) the N = 256 items lose -- weight gradient 0.748 ->
+    // 0.782 ms per view, 512->512 @64^2: 28 -> 34 us -- the two 96 KB stages cover less TMA latency than three 64 KB stages and
+    // the items get coarser; RNR_WGRAD_N256=1 enables them (parity-tested).
+    const bool wide = !swap && getenv("RNR_WGRAD_N256") && getenv("RNR_WGRAD_N256")[0] == '1';
     std::vector<OT> tiles;
     for (int t = 0; t < prob->n_taps; t++) {
         const rnr_wtap_t& tp = prob->taps[t];
@@ -256,10 +264,13 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
             }
             continue;
         }
+        // input-channel chunk: 256 where the tap has them (N = 256 MMAs, see the note at kMaxStages), else 128
+        const int chunk = (wide && tp.nci >= 256) ? 256 : 128;
         for (int co0 = 0; co0 < prob->cout; co0 += 128)
-            for (int ci = 0; ci < tp.nci; ci += 128) {
+            for (int ci = 0; ci < tp.nci; ci += chunk) {
                 const int rem = tp.nci - ci;
-                OT o = {t, co0, ci, rem > 64 ? 2 : 1, rem > 128 ? 128 : rem, (rem > 64 ? 2 : 1) * 64};
+                const int nbox = rem >= chunk ? chunk / 64 : rnr_cdiv(rem, 64);
+                OT o = {t, co0, ci, nbox, rem > chunk ? chunk : rem, nbox * 64};
                 tiles.push_back(o);
             }
     }
@@ -283,7 +294,12 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
     pl->n_work = (int)work.size();
     RNR_CHECK(cudaMalloc(&pl->d_work_tab, work.size() * sizeof(WorkItem)));
     RNR_CHECK(cudaMemcpy(pl->d_work_tab, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-    pl->smem_bytes = kStages * kStageBytes + 256 + 1024;
+    int max_nbox = 2;
+    for (const OT& o : tiles) max_nbox = o.nbox > max_nbox ? o.nbox : max_nbox;
+    pl->tc_stage_bytes = (2 + max_nbox) * kBoxBytes;
+    pl->tc_stages = (200 * 1024) / pl->tc_stage_bytes > kMaxStages ? kMaxStages : (200 * 1024) / pl->tc_stage_bytes;
+    pl->tc_acc_cols = max_nbox > 2 ? 256 : 128;
+    pl->smem_bytes = pl->tc_stages * pl->tc_stage_bytes + 256 + 1024;
     pl->grid = pl->n_work < 148 ? pl->n_work : 148;
     RNR_ONCE_PER_DEVICE({
         RNR_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -296,7 +312,8 @@ int rnr_wgrad_tc_run(const rnr_wgrad_plan* pl, cudaStream_t stream) {
     memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
     memcpy(maps.g, pl->tmap_g, sizeof(maps.g));
     RNR_PDL_LAUNCH(wgrad_tc_kernel, pl->grid, kThreads, pl->smem_bytes, stream, maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
-                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec, pl->swap);
+                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec, pl->swap,
+                                                                   pl->tc_stage_bytes, pl->tc_stages, pl->tc_acc_cols);
     RNR_LAUNCH_CHECK();
     return 0;
 }
