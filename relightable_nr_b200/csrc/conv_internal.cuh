@@ -131,6 +131,7 @@ struct rnr_wgrad_plan {
     int n_work;          // tc work items
     int vec;             // 1: dW destination is ci-contiguous -> 128-bit vector reductions
     int swap;            // 1: M = input channels, N = output channels
+    int tc_pair;         // 1: CTA pairs (cta_group::2), 256 output channels per work item
     int tc_stage_bytes, tc_stages, tc_acc_cols;   // wgrad_tc operand ring / accumulator width (N = 256 work items need 96 KB stages)
     // halo-reuse / multi-tap kernel (wgrad_halo.cu)
     int halo, halo_pitch, halo_a_stride, halo_a_bytes, halo_stage_bytes, halo_nbuf;

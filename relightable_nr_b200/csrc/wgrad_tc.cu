@@ -26,7 +26,7 @@ constexpr int kBoxBytes = 128 * 64 * 2;     // one [128 pixels x 64 channels] 16
 // every loaded tile is used by ONE group of 8 MMAs, so the shared-memory port carries the TMA writes AND the operand reads of the
 // same bytes; per 128-pixel patch that is 64 KB written + 64 KB read for 512 tensor cycles at N = 128 (256 B/clk against a
 // 128 B/clk port), 96 KB + 96 KB for 1024 tensor cycles at N = 256 (192 B/clk).
-constexpr int kMaxStages = 3;
+constexpr int kMaxStages = 4;
 
 struct WMaps {
     CUtensorMap a[RNR_MAX_VIEWS];
@@ -37,10 +37,20 @@ struct WorkItem {          // 8 ints
     int tap, co0, ci_off, n_ci_box, ci_valid, patch_begin, patch_end, n_mma;   // n_mma: N of the MMA (columns of the accumulator)
 };
 
+// kPair = 1: CTA pair (tcgen05.mma.cta_group::2, M = 256 output channels; see tc_ptx.cuh).  Both CTAs of a 2-cluster walk the same work
+// items (tap, 256 output channels, input-channel chunk, pixel range): CTA r loads the G boxes of ITS 128 output channels and HALF
+// of the activation boxes, rank 0 issues the MMAs.  Per 128-pixel patch a CTA then pulls 48 KB instead of 64 KB through its
+// operand ring -- the kernel is bound by ring capacity x TMA latency (192 KB cover ~1500 cycles at 128 B/clk, no more), so fewer
+// bytes per FLOP is what speeds it up; the stages shrink to 48 KB and a fourth one fits.
+template <int kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const WorkItem* __restrict__ work, int n_work,
                 int th, int tw, int tiles_y, int tiles_x, int vec, int swap, int stage_bytes, int n_stages, int acc_cols) {
+    constexpr int pair = kPair;
     pdl_launch_dependents();
+    const int crank = pair ? (int)cluster_ctarank() : 0;
+    const int cid = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // work items are walked per cluster
+    const int ncl = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* aux = smem + (size_t)n_stages * stage_bytes;
@@ -60,12 +70,13 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < n_stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], pair ? 8 : 4); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)(2 * acc_cols));
+    if (warp == 2) { if (pair) tmem_alloc_cg2(tmem_slot, (uint32_t)(2 * acc_cols)); else tmem_alloc(tmem_slot, (uint32_t)(2 * acc_cols)); }
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();            // the peer's barriers must exist before rank 0's commits / the peer's TMA reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();          // everything above (barriers, TMEM, tensor-map prefetch) overlapped the predecessor's tail
@@ -74,7 +85,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
         // TMA producer: the whole warp runs the loop, one elected lane issues (operands stay warp-uniform -> uniform registers)
         int stage = 0;
         uint32_t phase = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        for (int w = cid; w < n_work; w += ncl) {
             const WorkItem wi = work[w];
             const rnr_wtap_t tap = p.taps[wi.tap];
             for (int pt = wi.patch_begin; pt < wi.patch_end; pt++) {
@@ -83,8 +94,17 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one_sync()) {
                     uint8_t* st = smem + (size_t)stage * stage_bytes;
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + wi.n_ci_box) * kBoxBytes));
-                    if (!swap) {
+                    if (pair) {
+                        // my 128 output channels of G + my half of the activation boxes; all bytes of the pair land on rank 0's barrier
+                        const int hb = wi.n_ci_box >> 1;
+                        if (crank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * (2 + hb) * kBoxBytes));
+                        tma_load_4d_cg2(&maps.g[tap.gview], &full_bar[stage], st, wi.co0 + crank * 128, x0, y0, n_);
+                        tma_load_4d_cg2(&maps.g[tap.gview], &full_bar[stage], st + kBoxBytes, wi.co0 + crank * 128 + 64, x0, y0, n_);
+                        for (int b = 0; b < hb; b++)
+                            tma_load_4d_cg2(&maps.a[tap.view], &full_bar[stage], st + (size_t)(2 + b) * kBoxBytes,
+                                            tap.c0 + wi.ci_off + 64 * (crank * hb + b), x0 + tap.dx, y0 + tap.dy, n_);
+                    } else if (!swap) {
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + wi.n_ci_box) * kBoxBytes));
                         tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st, wi.co0, x0, y0, n_);
                         tma_load_4d(&maps.g[tap.gview], &full_bar[stage], st + kBoxBytes, wi.co0 + 64, x0, y0, n_);
                         for (int b = 0; b < wi.n_ci_box; b++)
@@ -93,6 +113,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                     } else {
                         // swapped roles: the 128 input channels of the block are the M operand (boxes 0-1), the output channels the
                         // N operand (boxes 2..): layers with few output channels (64 / 78) then fill all 128 accumulator lanes
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)((2 + wi.n_ci_box) * kBoxBytes));
                         tma_load_4d(&maps.a[tap.view], &full_bar[stage], st, tap.c0 + wi.ci_off, x0 + tap.dx, y0 + tap.dy, n_);
                         tma_load_4d(&maps.a[tap.view], &full_bar[stage], st + kBoxBytes, tap.c0 + wi.ci_off + 64, x0 + tap.dx, y0 + tap.dy, n_);
                         for (int b = 0; b < wi.n_ci_box; b++)
@@ -103,18 +124,18 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // MMA issuer: same structure (see tc_ptx.cuh::elect_one_sync)
+    } else if (warp == 1 && !(pair && crank != 0)) {
+        // MMA issuer: same structure (see tc_ptx.cuh::elect_one_sync); rank 0 only in a CTA pair
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
         const uint32_t smem0 = smem_u32(smem);
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
+        for (int w = cid; w < n_work; w += ncl, it++) {
             const WorkItem wi = work[w];
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const uint32_t idesc = swap ? make_idesc(128, wi.n_mma, p.a_dtype, p.g_dtype, 1, 1)
-                                        : make_idesc(128, wi.n_mma, p.g_dtype, p.a_dtype, 1, 1);
+                                        : make_idesc(pair ? 256 : 128, wi.n_mma, p.g_dtype, p.a_dtype, 1, 1);
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
@@ -126,30 +147,39 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                 if (elect_one_sync()) {
                     const uint64_t dg = make_mnmajor_desc(sbase, kBoxBytes);
                     const uint64_t da = make_mnmajor_desc(sbase + 2 * kBoxBytes, kBoxBytes);
+                    if (pair) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {     // 128 pixels = 8 MMAs of K=16 (2 KB of rows each)
-                        umma_f16(d_tmem, dg + (uint64_t)(k * (2048 >> 4)), da + (uint64_t)(k * (2048 >> 4)), idesc, accum);
-                        accum = 1;
+                        for (int k = 0; k < 8; k++) {
+                            umma_f16_cg2(d_tmem, dg + (uint64_t)(k * (2048 >> 4)), da + (uint64_t)(k * (2048 >> 4)), idesc, accum);
+                            accum = 1;
+                        }
+                        umma_commit_cg2(&empty_bar[stage], 3);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {     // 128 pixels = 8 MMAs of K=16 (2 KB of rows each)
+                            umma_f16(d_tmem, dg + (uint64_t)(k * (2048 >> 4)), da + (uint64_t)(k * (2048 >> 4)), idesc, accum);
+                            accum = 1;
+                        }
+                        umma_commit(&empty_bar[stage]);
                     }
-                    umma_commit(&empty_bar[stage]);
                 }
                 __syncwarp();
                 accum = 1;
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
-            if (elect_one_sync()) umma_commit(&tfull_bar[acc]);
+            if (elect_one_sync()) { if (pair) umma_commit_cg2(&tfull_bar[acc], 3); else umma_commit(&tfull_bar[acc]); }
             __syncwarp();
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int it = 0;
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, it++) {
+        for (int w = cid; w < n_work; w += ncl, it++) {
             const WorkItem wi = work[w];
             const rnr_wtap_t tap = p.taps[wi.tap];
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int co = wi.co0 + row;
+            const int co = wi.co0 + crank * 128 + row;
             float* dst = p.dw + (int64_t)co * p.s_co + (int64_t)(tap.ci0 + wi.ci_off) * p.s_ci + tap.off;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -171,7 +201,7 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);        // (swapped roles never run as a pair)
                 continue;
             }
             const int ncols = wi.n_ci_box * 64;
@@ -204,15 +234,16 @@ wgrad_tc_kernel(const __grid_constant__ WMaps maps, const WgradParams p, const W
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) { if (pair) mbar_arrive_remote(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();            // no CTA may exit while its peer can still arrive on its barriers / read its operands
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, (uint32_t)(2 * acc_cols));
+        if (pair) tmem_dealloc_cg2(tmem_base, (uint32_t)(2 * acc_cols)); else tmem_dealloc(tmem_base, (uint32_t)(2 * acc_cols));
     }
 }
 
@@ -254,6 +285,14 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
     // 0.782 ms per view, 512->512 @64^2: 28 -> 34 us -- the two 96 KB stages cover less TMA latency than three 64 KB stages and
     // the items get coarser; RNR_WGRAD_N256=1 enables them (parity-tested).
     const bool wide = !swap && getenv("RNR_WGRAD_N256") && getenv("RNR_WGRAD_N256")[0] == '1';
+    // CTA pair: 256 output channels per work item, every input-channel chunk an even number of 64-channel boxes
+    // OFF by default: measured on B200 (profiles/r02_perf_unet_c33_wpair_{0,1}.txt) 0.724 vs 0.733 ms per view -- 1024->256 @128^2 gains
+    // (42 -> 38 us), the <= 32^2 layers lose (17 -> 20 us: half as many, coarser items); the deep layers are bound by fixed costs
+    // and by the fp32 reductions of their partial sums, not by operand bytes.  RNR_WGRAD_PAIR=1 enables it (parity-tested).
+    bool pair = !swap && !wide && prob->cout % 256 == 0 && getenv("RNR_WGRAD_PAIR") && getenv("RNR_WGRAD_PAIR")[0] == '1';
+    for (int t = 0; t < prob->n_taps && pair; t++)
+        if (prob->taps[t].nci % 128 != 0) pair = false;
+    pl->tc_pair = pair ? 1 : 0;
     std::vector<OT> tiles;
     for (int t = 0; t < prob->n_taps; t++) {
         const rnr_wtap_t& tp = prob->taps[t];
@@ -266,7 +305,7 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
         }
         // input-channel chunk: 256 where the tap has them (N = 256 MMAs, see the note at kMaxStages), else 128
         const int chunk = (wide && tp.nci >= 256) ? 256 : 128;
-        for (int co0 = 0; co0 < prob->cout; co0 += 128)
+        for (int co0 = 0; co0 < prob->cout; co0 += (pair ? 256 : 128))
             for (int ci = 0; ci < tp.nci; ci += chunk) {
                 const int rem = tp.nci - ci;
                 const int nbox = rem >= chunk ? chunk / 64 : rnr_cdiv(rem, 64);
@@ -274,7 +313,8 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
                 tiles.push_back(o);
             }
     }
-    int splits = (int)((148 * 2 + (int)tiles.size() - 1) / (int)tiles.size());
+    const int slots = pair ? 74 : 148;        // persistent CTAs (pairs) that walk the work list
+    int splits = (int)((slots * 2 + (int)tiles.size() - 1) / (int)tiles.size());
     if (splits > n_patches) splits = n_patches;
     if (splits < 1) splits = 1;
     const int per = rnr_cdiv(n_patches, splits);
@@ -296,13 +336,14 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
     RNR_CHECK(cudaMemcpy(pl->d_work_tab, work.data(), work.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
     int max_nbox = 2;
     for (const OT& o : tiles) max_nbox = o.nbox > max_nbox ? o.nbox : max_nbox;
-    pl->tc_stage_bytes = (2 + max_nbox) * kBoxBytes;
+    pl->tc_stage_bytes = (2 + (pair ? max_nbox / 2 : max_nbox)) * kBoxBytes;
     pl->tc_stages = (200 * 1024) / pl->tc_stage_bytes > kMaxStages ? kMaxStages : (200 * 1024) / pl->tc_stage_bytes;
     pl->tc_acc_cols = max_nbox > 2 ? 256 : 128;
     pl->smem_bytes = pl->tc_stages * pl->tc_stage_bytes + 256 + 1024;
-    pl->grid = pl->n_work < 148 ? pl->n_work : 148;
+    pl->grid = pair ? 2 * (pl->n_work < 74 ? pl->n_work : 74) : (pl->n_work < 148 ? pl->n_work : 148);
     RNR_ONCE_PER_DEVICE({
-        RNR_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RNR_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RNR_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     });
     return 0;
 }
@@ -311,9 +352,23 @@ int rnr_wgrad_tc_run(const rnr_wgrad_plan* pl, cudaStream_t stream) {
     WMaps maps;
     memcpy(maps.a, pl->tmap_a, sizeof(maps.a));
     memcpy(maps.g, pl->tmap_g, sizeof(maps.g));
-    RNR_PDL_LAUNCH(wgrad_tc_kernel, pl->grid, kThreads, pl->smem_bytes, stream, maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
-                                                                   pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec, pl->swap,
-                                                                   pl->tc_stage_bytes, pl->tc_stages, pl->tc_acc_cols);
+    if (pl->tc_pair) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(pl->grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = pl->smem_bytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = rnr_pdl_enabled() ? 2 : 1;
+        RNR_CHECK(cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<1>, maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work, pl->th, pl->tw,
+                                     pl->tiles_y, pl->tiles_x, pl->vec, pl->swap, pl->tc_stage_bytes, pl->tc_stages, pl->tc_acc_cols));
+    } else {
+        RNR_PDL_LAUNCH(wgrad_tc_kernel<0>, pl->grid, kThreads, pl->smem_bytes, stream, maps, pl->p, (const WorkItem*)pl->d_work_tab, pl->n_work,
+                       pl->th, pl->tw, pl->tiles_y, pl->tiles_x, pl->vec, pl->swap, pl->tc_stage_bytes, pl->tc_stages, pl->tc_acc_cols);
+    }
     RNR_LAUNCH_CHECK();
     return 0;
 }
