@@ -314,7 +314,13 @@ int rnr_wgrad_tc_prepare(rnr_wgrad_plan* pl, const rnr_wgrad_problem_t* prob) {
             }
     }
     const int slots = pair ? 74 : 148;        // persistent CTAs (pairs) that walk the work list
-    int splits = (int)((slots * 2 + (int)tiles.size() - 1) / (int)tiles.size());
+    // work items per persistent CTA the pixel split aims at.  Every split adds one more fp32 reduction of the whole weight gradient
+    // (red.add of splits x the weight bytes), so layers that already have ~one output tile per SM are not split further: measured
+    // per layer (profiles/r02_perf_unet_c34_waves{1,2,3}.txt) 512->512 @32^2 17 -> 14 us, 512->512 @64^2 27 -> 24 us at one wave, while
+    // the layers with few output tiles (128->128 @256^2: 9 tiles) need the second wave (26 vs 30 us).  RNR_WGRAD_WAVES overrides.
+    int waves = tiles.size() >= 100 ? 1 : 2;
+    { const char* e = getenv("RNR_WGRAD_WAVES"); if (e && atoi(e) >= 1 && atoi(e) <= 8) waves = atoi(e); }
+    int splits = (int)((slots * waves + (int)tiles.size() - 1) / (int)tiles.size());
     if (splits > n_patches) splits = n_patches;
     if (splits < 1) splits = 1;
     const int per = rnr_cdiv(n_patches, splits);
